@@ -1,0 +1,67 @@
+/* fcb200.h -- C-ABI of the B200-native FieldCalculations hot path (libfcb200.so).
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no C++ or torch types.  A maintainer
+ * of the reference binds exactly these symbols (INTEGRATION.md shows the binding): the C++ shim
+ * mi-fieldcalc_b200/csrc/shim.cc re-exports them under the reference's own mangled names
+ * miutil::fieldcalc::<op> (src/mi_fieldcalc/FieldCalculations.h:113-303 of the reference).
+ *
+ *   fcb200_<op>(...)           one field per call; signature = the reference function of the same
+ *                              name (listed with file:line in fcb200_api.inc)
+ *   fcb200_<op>_batched(...)   many fields per launch (fcb200_batched.inc)
+ *
+ * Memory: every field pointer may be DEVICE memory (used in place) or HOST memory (staged through
+ * a per-thread device arena; pinned host memory copies at full PCIe speed).  The caller owns all
+ * buffers; the library keeps no pointer after a call returns (after fcb200_end_deferred() in
+ * deferred mode).  Scalars, `fDefined` flag arrays, per-field scalar arrays, pointer tables and
+ * limits are always HOST memory.
+ *
+ * Return value: 1 = the reference would return true, 0 = the reference would return false
+ * (arguments rejected; outputs untouched unless the reference touches them), < 0 = runtime
+ * failure (no CUDA device, CUDA error); fcb200_last_error() describes it.  There is no CPU path.
+ *
+ * Threads: entry points are re-entrant; each host thread has its own stream and staging arena.
+ */
+#ifndef FCB200_H
+#define FCB200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum { FCB200_ALL_DEFINED = 0, FCB200_NONE_DEFINED = 1, FCB200_SOME_DEFINED = 2 };
+
+/* ---- runtime ------------------------------------------------------------------------------ */
+const char* fcb200_version(void);
+/* text of the calling thread's last runtime error ("" if none) */
+const char* fcb200_last_error(void);
+/* number of visible CUDA devices, < 0 if the CUDA runtime cannot be initialised */
+int fcb200_device_count(void);
+/* make `device` current for the calling thread (cudaSetDevice) */
+int fcb200_set_device(int device);
+/* run the calling thread's work on `cuda_stream` (a cudaStream_t) if use_it != 0, else on the
+ * library's own per-thread stream (default) */
+int fcb200_set_stream(void* cuda_stream, int use_it);
+/* deferred mode: calls between begin and end only enqueue work; outputs in host memory, counters
+ * and fDefined flags become final when fcb200_end_deferred() returns.  Input flags are read at
+ * call time, so a deferred call must not depend on the flag of an earlier deferred call. */
+int fcb200_begin_deferred(void);
+int fcb200_end_deferred(void);
+/* wait for the calling thread's stream */
+int fcb200_synchronize(void);
+/* kernels launched by this library since it was loaded (all threads) */
+unsigned long long fcb200_launch_count(void);
+
+/* ---- operators ----------------------------------------------------------------------------- */
+#define FC_FN(name, args) int fcb200_##name args;
+#include "fcb200_api.inc"
+#undef FC_FN
+
+#define FCB_FN(name, args) int fcb200_##name args;
+#include "fcb200_batched.inc"
+#undef FCB_FN
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* FCB200_H */

@@ -1,0 +1,791 @@
+// ops_elementwise.cu -- pressure-, hybrid- and atmospheric-level thermodynamic conversions,
+// windCooling, fieldOPERfield and the momentum coordinates.
+//
+// Every operator is a functor for the batched engine in elementwise.cuh.  Host code decodes
+// `compute` / `unit` and validates arguments with the reference's exact early-return rules, then
+// launches one kernel for the whole batch.  Citations: FC.cc = the reference's
+// src/mi_fieldcalc/FieldCalculations.cc.
+#include "elementwise.cuh"
+
+#include "../../include/fcb200.h"
+
+#include <cmath>
+#include <cstring>
+#include <vector>
+
+namespace fcb200 {
+namespace {
+
+using dev::is_def;
+using dev::K_CP;
+using dev::K_T0;
+using dev::K_XLH;
+
+enum Kind { PLEVEL = 0, HLEVEL = 1, ALEVEL = 2 };
+
+// host copies of MC.h:39-49 (same float values as the device constexprs)
+const float H_CP = 1004.f, H_P0INV = (float)(1. / 1000.f), H_KAPPA = 287.f / 1004.f, H_T0 = (float)273.15;
+
+inline float host_pidcp(float p)
+{ // FC.cc:308-311, evaluated once per field on the host with glibc powf -- exactly what the reference
+  // does for every plevel* operator (FC.cc:347, 434), so these operators carry no device-powf ulps
+  return powf(p * H_P0INV, H_KAPPA);
+}
+
+inline bool bad_hlevel(float a, float b)
+{ // FC.cc:298-301
+  return (a < 0.0) || (b < 0.0) || (a == 0.0 && b == 0.0) || (b > 1.0);
+}
+
+inline bool unit_is(const char* unit, const char* what)
+{
+  return unit && strcmp(unit, what) == 0;
+}
+
+int temp_compute(int compute, const char* unit)
+{ // FC.cc:340-345, 1060-1065, 1322-1327
+  if (compute < 3) {
+    if (unit_is(unit, "celsius"))
+      return 1;
+    if (unit_is(unit, "kelvin"))
+      return 2;
+  }
+  return compute;
+}
+
+int hum_compute(int compute, const char* unit)
+{ // FC.cc:422-425, 1174-1177, 1417-1420
+  if (compute > 8 && unit_is(unit, "celsius"))
+    return compute - 4;
+  if (compute > 4 && compute <= 8 && unit_is(unit, "kelvin"))
+    return compute + 4;
+  return compute;
+}
+
+// ------------------------------------------------------------------------------------ functors
+
+// pleveltemp c1-3 (FC.cc:351-355): pure stream through unaryFunctionField, flag untouched
+struct PTempStreamOp
+{
+  static constexpr int NIN = 1, NOUT = 1, UNROLL = 4;
+  static constexpr bool USES_EWT = false, COUNTS = false;
+  int compute;
+  __device__ __forceinline__ void point(const float* in, float* out, const PointCtx& c, long long, unsigned&) const
+  {
+    const float f = in[0], pidcp = c.m.a;
+    if (c.m.all || is_def(f, c.undef))
+      out[0] = (compute == 1) ? (f * pidcp - K_T0) : (compute == 2) ? (f * pidcp) : (f / pidcp);
+    else
+      out[0] = c.undef;
+  }
+};
+
+// *leveltemp with a table lookup or a per-point Exner function.
+// PLEVEL: only c4/c5 come here; meta.a = p, meta.b = pi.   HLEVEL: meta.a/b = alevel/blevel.
+template <int KIND>
+struct TempOp
+{
+  static constexpr int NIN = (KIND == PLEVEL) ? 1 : 2, NOUT = 1, UNROLL = 2;
+  static constexpr bool USES_EWT = true, COUNTS = true;
+  int compute;
+  __device__ __forceinline__ void point(const float* in, float* out, const PointCtx& c, long long, unsigned& nundef) const
+  {
+    const float t = in[0];
+    bool ok = c.m.all || is_def(t, c.undef);
+    if (KIND != PLEVEL)
+      ok = c.m.all || (ok && is_def(in[NIN - 1], c.undef));
+    float r = c.undef;
+    if (ok) {
+      float p, pi, pidcp = 0.f;
+      if (KIND == PLEVEL) {
+        p = c.m.a;
+        pi = c.m.b;
+      } else {
+        p = (KIND == HLEVEL) ? dev::p_hlevel(in[1], c.m.a, c.m.b) : in[1];
+        pidcp = dev::pidcp_from_p(p);
+        pi = K_CP * pidcp;
+      }
+      if (compute == 1)
+        r = t * pidcp - K_T0;
+      else if (compute == 2)
+        r = t * pidcp;
+      else if (compute == 3)
+        r = t / pidcp;
+      else if (compute == 4)
+        ok = dev::t_thesat(c.tab, t, p, pi, r);
+      else
+        ok = dev::th_thesat(c.tab, t, p, pi, r);
+    }
+    if (!ok) {
+      r = c.undef;
+      nundef += 1;
+    }
+    out[0] = r;
+  }
+};
+
+// h/alevelthe (FC.cc:1128-1139, 1378-1388)
+template <int KIND>
+struct TheOp
+{
+  static constexpr int NIN = 3, NOUT = 1, UNROLL = 2;
+  static constexpr bool USES_EWT = false, COUNTS = true;
+  int compute;
+  __device__ __forceinline__ void point(const float* in, float* out, const PointCtx& c, long long, unsigned& nundef) const
+  {
+    const float t = in[0], q = in[1];
+    if (c.m.all || (is_def(t, c.undef) && is_def(q, c.undef) && is_def(in[2], c.undef))) {
+      const float p = (KIND == HLEVEL) ? dev::p_hlevel(in[2], c.m.a, c.m.b) : in[2];
+      const float pi = K_CP * dev::pidcp_from_p(p);
+      out[0] = (compute == 1) ? ((t * K_CP + q * K_XLH) / pi) : (t + q * K_XLH / pi);
+    } else {
+      out[0] = c.undef;
+      nundef += 1;
+    }
+  }
+};
+
+// The 12-mode humidity conversion in the a/h-level numbering (FC.cc:1399-1410); plevelhum's own
+// numbering is translated by the host.  PLEVEL: meta.a = p, meta.b = tconv (pi/cp for the even
+// modes, 1 otherwise -- FC.cc:436), meta.all bit 1 = "p == undef, fill" (FC.cc:429-432).
+template <int KIND>
+struct HumOp
+{
+  static constexpr int NIN = (KIND == PLEVEL) ? 2 : 3, NOUT = 1, UNROLL = 2;
+  static constexpr bool USES_EWT = true, COUNTS = true;
+  int compute;
+  int pcheck; // test `pin != undef` (no NaN test): HLEVEL when p is needed (FC.cc:1187), ALEVEL when it is NOT (FC.cc:1429)
+  float tdconv;
+  __device__ __forceinline__ void point(const float* in, float* out, const PointCtx& c, long long, unsigned& nundef) const
+  {
+    const float t = in[0], h = in[1];
+    const bool all = (c.m.all & 1) != 0;
+    bool ok = all || (is_def(t, c.undef) && is_def(h, c.undef));
+    if (KIND == PLEVEL) {
+      if (c.m.all & 2)
+        ok = false;
+    } else if (pcheck && !all) {
+      ok = ok && (in[NIN - 1] != c.undef);
+    }
+    float r = c.undef;
+    if (ok) {
+      float p, tk = t;
+      const bool even = (compute & 1) == 0;
+      if (KIND == PLEVEL) {
+        p = c.m.a;
+        tk = t * c.m.b;
+      } else if (KIND == HLEVEL) {
+        const bool need_p = !(compute == 7 || compute == 11);
+        p = need_p ? dev::p_hlevel(in[2], c.m.a, c.m.b) : 0.f;
+        if (even)
+          tk = t * dev::pidcp_from_p(p);
+      } else {
+        p = in[2];
+        if (even)
+          tk = t * dev::pidcp_from_p(p);
+      }
+      switch (compute) {
+      case 1:
+      case 2:
+        ok = dev::tk_q_rh(c.tab, tk, h, p, r);
+        break;
+      case 3:
+      case 4:
+        ok = dev::tk_rh_q(c.tab, tk, h, p, r);
+        break;
+      case 5:
+      case 6:
+      case 9:
+      case 10:
+        ok = dev::tk_q_td(c.tab, tk, h, p, tdconv, r);
+        break;
+      default:
+        ok = dev::tk_rh_td(c.tab, tk, h, tdconv, r);
+        break;
+      }
+    }
+    if (!ok) {
+      r = c.undef;
+      nundef += 1;
+    }
+    out[0] = r;
+  }
+};
+
+// h/alevelducting (FC.cc:1256-1271, 1490-1503)
+template <int KIND>
+struct DuctOp
+{
+  static constexpr int NIN = 3, NOUT = 1, UNROLL = 2;
+  static constexpr bool USES_EWT = true, COUNTS = true;
+  int compute;
+  __device__ __forceinline__ void point(const float* in, float* out, const PointCtx& c, long long, unsigned& nundef) const
+  {
+    bool ok = c.m.all || (is_def(in[0], c.undef) && is_def(in[1], c.undef) && is_def(in[2], c.undef));
+    float r = c.undef;
+    if (ok) {
+      const float p = (KIND == HLEVEL) ? dev::p_hlevel(in[2], c.m.a, c.m.b) : in[2];
+      float tk = in[0];
+      if ((compute & 1) == 0)
+        tk *= dev::pidcp_from_p(p);
+      if (compute <= 2)
+        r = dev::tk_q_duct(tk, in[1], p);
+      else
+        ok = dev::tk_rh_duct(c.tab, tk, in[1], p, r);
+    }
+    if (!ok) {
+      r = c.undef;
+      nundef += 1;
+    }
+    out[0] = r;
+  }
+};
+
+// The reference does not validate `compute` in hleveltemp, hlevelthe, hlevelducting and alevelducting:
+// with an unknown mode a defined point keeps whatever the output array held and an undefined point
+// becomes undef (e.g. FC.cc:1080-1094).  in[NCHK] is the previous content of the output.
+template <int NCHK>
+struct KeepOrUndefOp
+{
+  static constexpr int NIN = NCHK + 1, NOUT = 1, UNROLL = 2;
+  static constexpr bool USES_EWT = false, COUNTS = true;
+  __device__ __forceinline__ void point(const float* in, float* out, const PointCtx& c, long long, unsigned& nundef) const
+  {
+    bool ok = true;
+#pragma unroll
+    for (int k = 0; k < NCHK; ++k)
+      ok = ok && is_def(in[k], c.undef);
+    if (c.m.all || ok)
+      out[0] = in[NCHK];
+    else {
+      out[0] = c.undef;
+      nundef += 1;
+    }
+  }
+};
+
+// hlevelpressure (FC.cc:1294-1301)
+struct HPressureOp
+{
+  static constexpr int NIN = 1, NOUT = 1, UNROLL = 4;
+  static constexpr bool USES_EWT = false, COUNTS = true;
+  __device__ __forceinline__ void point(const float* in, float* out, const PointCtx& c, long long, unsigned& nundef) const
+  {
+    if (c.m.all || is_def(in[0], c.undef))
+      out[0] = dev::p_hlevel(in[0], c.m.a, c.m.b);
+    else {
+      out[0] = c.undef;
+      nundef += 1;
+    }
+  }
+};
+
+// windCooling (FC.cc:2209-2221); the reference never updates the flag
+struct WindCoolingOp
+{
+  static constexpr int NIN = 3, NOUT = 1, UNROLL = 2;
+  static constexpr bool USES_EWT = false, COUNTS = false;
+  float tconv;
+  __device__ __forceinline__ void point(const float* in, float* out, const PointCtx& c, long long, unsigned&) const
+  {
+    if (c.m.all || (is_def(in[0], c.undef) && is_def(in[1], c.undef) && is_def(in[2], c.undef))) {
+      const float tc = in[0] - tconv;
+      const float ff = (float)((double)dev::absval(in[1], in[2]) * 3.6);
+      const float ffpow = powf(ff, (float)0.16);
+      float d = (float)(13.12 + 0.6215 * (double)tc - 11.37 * (double)ffpow + 0.3965 * (double)tc * (double)ffpow);
+      if ((double)d > 0.)
+        d = 0.f;
+      out[0] = d;
+    } else
+      out[0] = c.undef;
+  }
+};
+
+// fieldOPERfield (FC.cc:2611-2625)
+struct FieldOperOp
+{
+  static constexpr int NIN = 2, NOUT = 1, UNROLL = 4;
+  static constexpr bool USES_EWT = false, COUNTS = true;
+  int compute;
+  __device__ __forceinline__ void point(const float* in, float* out, const PointCtx& c, long long, unsigned& nundef) const
+  {
+    const float a = in[0], b = in[1];
+    float r = c.undef;
+    bool ok = c.m.all || (is_def(a, c.undef) && is_def(b, c.undef));
+    if (ok) {
+      if (compute == 1)
+        r = a + b;
+      else if (compute == 2)
+        r = a - b;
+      else if (compute == 3)
+        r = a * b;
+      else if (b != 0)
+        r = a / b;
+      else
+        ok = false; // divideUndef, FC.cc:84-92
+    }
+    if (!ok) {
+      r = c.undef;
+      nundef += 1;
+    }
+    out[0] = r;
+  }
+};
+
+// momentumX/Ycoordinate (FC.cc:2371-2383, 2407-2419): elementwise despite the name
+template <bool XDIR>
+struct MomentumOp
+{
+  static constexpr int NIN = 3, NOUT = 1, UNROLL = 2;
+  static constexpr bool USES_EWT = false, COUNTS = true;
+  float fcormin;
+  __device__ __forceinline__ void point(const float* in, float* out, const PointCtx& c, long long idx, unsigned& nundef) const
+  {
+    if (c.m.all || is_def(in[0], c.undef)) {
+      float fcor = in[2];
+      const float fcormax = -fcormin;
+      if (fcor >= 0.f && fcor < fcormin)
+        fcor = fcormin;
+      else if (fcor <= 0.f && fcor > fcormax)
+        fcor = fcormax;
+      const int i = (int)idx;
+      if (XDIR)
+        out[0] = (float)(i % c.nx) + in[0] * in[1] / fcor;
+      else
+        out[0] = (float)(i / c.nx) - in[0] * in[1] / fcor;
+    } else {
+      out[0] = c.undef;
+      nundef += 1;
+    }
+  }
+};
+
+// ------------------------------------------------------------------------------------ host drivers
+
+struct Batch
+{
+  int nx, ny, nfields;
+  long long n;
+  bool valid() const { return nx > 0 && ny > 0 && nfields > 0 && (long long)nx * ny < 0x7fffffffLL; }
+};
+
+Batch make_batch(int nx, int ny, int nfields)
+{
+  Batch b;
+  b.nx = nx;
+  b.ny = ny;
+  b.nfields = nfields;
+  b.n = (long long)nx * ny;
+  return b;
+}
+
+enum FlagRule { FLAG_FROM_COUNT, FLAG_UNCHANGED };
+
+// Runs one elementwise operator over a batch.  `stride[k]` = 1 for per-field arrays, 0 for arrays shared
+// by the batch.  `fill_meta(k, meta)` sets the per-field scalars.  The output may alias an input.
+template <class Op, class FillMeta>
+int run_elementwise(const Batch& b, const Op& op, const float* const* host_in, const int* per_field, float* host_out, int* fDefined, float undef,
+                    FlagRule rule, FillMeta fill_meta)
+{
+  if (!b.valid()) {
+    set_error("fcb200: invalid grid or batch size (nx=%d ny=%d nfields=%d)", b.nx, b.ny, b.nfields);
+    return -1;
+  }
+  Call call;
+  const float* in[Op::NIN];
+  long long stride[Op::NIN];
+  for (int k = 0; k < Op::NIN; ++k) {
+    stride[k] = per_field[k] ? b.n : 0;
+    in[k] = call.in(host_in[k], (size_t)(per_field[k] ? b.n * b.nfields : b.n));
+  }
+  float* out[1] = {call.out(host_out, (size_t)(b.n * b.nfields))};
+  FieldMeta* meta = call.meta_host(b.nfields);
+  if (!call.ok())
+    return -1;
+  for (int k = 0; k < b.nfields; ++k) {
+    meta[k].all = (fDefined[k] == ALL_DEFINED) ? 1 : 0;
+    meta[k].a = meta[k].b = meta[k].c = 0.f;
+    fill_meta(k, meta[k]);
+  }
+  const FieldMeta* dmeta = call.upload_meta();
+  unsigned long long* counters = Op::COUNTS ? call.counters(b.nfields) : nullptr;
+  if (!call.ok())
+    return -1;
+  if (!launch_elementwise(call, op, in, stride, out, b.n, b.nfields, b.nx, undef, dmeta, counters))
+    return -1;
+  const int nfields = b.nfields;
+  const unsigned long long n = (unsigned long long)b.n;
+  if (rule == FLAG_FROM_COUNT && Op::COUNTS)
+    return call.finish([=](const unsigned long long* cnt) {
+      for (int k = 0; k < nfields; ++k)
+        fDefined[k] = check_defined(cnt[k], n);
+    });
+  return call.finish(Finalizer());
+}
+
+struct NoMeta
+{
+  void operator()(int, FieldMeta&) const {}
+};
+
+// ---- pressure levels --------------------------------------------------------------------------------
+
+int impl_pleveltemp(const Batch& b, const float* tinp, const float* p, const char* unit, int compute, float* tout, int* fDefined, float undef)
+{ // FC.cc:328-367
+  for (int k = 0; k < b.nfields; ++k)
+    if (p[k] <= 0)
+      return 0;
+  compute = temp_compute(compute, unit);
+  if (compute < 1 || compute > 5)
+    return 0;
+  const float* in[1] = {tinp};
+  const int pf[1] = {1};
+  if (compute <= 3) {
+    PTempStreamOp op{compute};
+    return run_elementwise(b, op, in, pf, tout, fDefined, undef, FLAG_UNCHANGED, [&](int k, FieldMeta& m) { m.a = host_pidcp(p[k]); });
+  }
+  TempOp<PLEVEL> op{compute};
+  return run_elementwise(b, op, in, pf, tout, fDefined, undef, FLAG_FROM_COUNT, [&](int k, FieldMeta& m) {
+    m.a = p[k];
+    m.b = host_pidcp(p[k]) * H_CP;
+  });
+}
+
+int impl_plevelhum(const Batch& b, const float* t, const float* huminp, const float* p, const char* unit, int compute, float* humout, int* fDefined,
+                   float undef)
+{ // FC.cc:400-464
+  if (compute <= 0 || compute >= 13)
+    return 0;
+  for (int k = 0; k < b.nfields; ++k)
+    if (p[k] <= 0)
+      return 0;
+  compute = hum_compute(compute, unit);
+  const bool rh_td = (compute == 5 || compute == 6 || compute == 9 || compute == 10);
+  // p-level numbering -> a/h-level numbering (5,6,9,10 <-> 7,8,11,12; FCT.cc:73 documents the permutation)
+  static const int to_ah[13] = {0, 1, 2, 3, 4, 7, 8, 5, 6, 11, 12, 9, 10};
+  HumOp<PLEVEL> op{to_ah[compute], 0, (compute >= 9) ? H_T0 : 0.f};
+  const bool even = (compute % 2 == 0);
+  const float* in[2] = {t, huminp};
+  const int pf[2] = {1, 1};
+  return run_elementwise(b, op, in, pf, humout, fDefined, undef, FLAG_FROM_COUNT, [&](int k, FieldMeta& m) {
+    if (p[k] == undef && !rh_td)
+      m.all |= 2; // fillUndef -> every point undefined -> NONE_DEFINED (FC.cc:429-432)
+    const float pi = H_CP * host_pidcp(p[k]);
+    m.a = p[k];
+    m.b = even ? (pi / H_CP) : 1.f;
+  });
+}
+
+// ---- hybrid / atmospheric levels --------------------------------------------------------------------
+
+template <int KIND>
+int impl_xleveltemp(const Batch& b, const float* tinp, const float* pin, const float* alevel, const float* blevel, int compute, float* tout,
+                    int* fDefined, float undef)
+{ // FC.cc:1074-1097 / 1329-1352
+  const int pf[3] = {1, KIND == ALEVEL ? 1 : 0, 1};
+  auto levels = [&](int k, FieldMeta& m) {
+    if (KIND == HLEVEL) {
+      m.a = alevel[k];
+      m.b = blevel[k];
+    }
+  };
+  if (compute < 1 || compute > 5) { // only reachable for hleveltemp
+    const float* in[3] = {tinp, pin, tout};
+    KeepOrUndefOp<2> op;
+    return run_elementwise(b, op, in, pf, tout, fDefined, undef, FLAG_FROM_COUNT, levels);
+  }
+  const float* in[2] = {tinp, pin};
+  TempOp<KIND> op{compute};
+  return run_elementwise(b, op, in, pf, tout, fDefined, undef, FLAG_FROM_COUNT, levels);
+}
+
+template <int KIND>
+int impl_xlevelthe(const Batch& b, const float* t, const float* q, const float* pin, const float* alevel, const float* blevel, int compute,
+                   float* the, int* fDefined, float undef)
+{ // FC.cc:1125-1142 / 1375-1391
+  const int pf[4] = {1, 1, KIND == ALEVEL ? 1 : 0, 1};
+  auto levels = [&](int k, FieldMeta& m) {
+    if (KIND == HLEVEL) {
+      m.a = alevel[k];
+      m.b = blevel[k];
+    }
+  };
+  if (compute != 1 && compute != 2) { // only reachable for hlevelthe
+    const float* in[4] = {t, q, pin, the};
+    KeepOrUndefOp<3> op;
+    return run_elementwise(b, op, in, pf, the, fDefined, undef, FLAG_FROM_COUNT, levels);
+  }
+  const float* in[3] = {t, q, pin};
+  TheOp<KIND> op{compute};
+  return run_elementwise(b, op, in, pf, the, fDefined, undef, FLAG_FROM_COUNT, levels);
+}
+
+template <int KIND>
+int impl_xlevelhum(const Batch& b, const float* t, const float* huminp, const float* pin, const float* alevel, const float* blevel,
+                   const char* unit, int compute, float* humout, int* fDefined, float undef)
+{ // FC.cc:1145-1217 / 1394-1458
+  compute = hum_compute(compute, unit);
+  const bool no_p = (compute == 7 || compute == 11);
+  HumOp<KIND> op{compute, (KIND == HLEVEL) ? !no_p : no_p, (compute >= 9) ? H_T0 : 0.f};
+  const float* in[3] = {t, huminp, pin};
+  const int pf[3] = {1, 1, KIND == ALEVEL ? 1 : 0};
+  return run_elementwise(b, op, in, pf, humout, fDefined, undef, FLAG_FROM_COUNT, [&](int k, FieldMeta& m) {
+    if (KIND == HLEVEL) {
+      m.a = alevel[k];
+      m.b = blevel[k];
+    }
+  });
+}
+
+template <int KIND>
+int impl_xlevelducting(const Batch& b, const float* t, const float* h, const float* pin, const float* alevel, const float* blevel, int compute,
+                       float* duct, int* fDefined, float undef)
+{ // FC.cc:1252-1273 / 1485-1504 (the a-level variant never updates the flag)
+  const FlagRule rule = (KIND == HLEVEL) ? FLAG_FROM_COUNT : FLAG_UNCHANGED;
+  const int pf[4] = {1, 1, KIND == ALEVEL ? 1 : 0, 1};
+  auto levels = [&](int k, FieldMeta& m) {
+    if (KIND == HLEVEL) {
+      m.a = alevel[k];
+      m.b = blevel[k];
+    }
+  };
+  if (compute < 1 || compute > 4) {
+    const float* in[4] = {t, h, pin, duct};
+    KeepOrUndefOp<3> op;
+    return run_elementwise(b, op, in, pf, duct, fDefined, undef, rule, levels);
+  }
+  const float* in[3] = {t, h, pin};
+  DuctOp<KIND> op{compute};
+  return run_elementwise(b, op, in, pf, duct, fDefined, undef, rule, levels);
+}
+
+bool any_bad_hlevel(const Batch& b, const float* alevel, const float* blevel)
+{
+  for (int k = 0; k < b.nfields; ++k)
+    if (bad_hlevel(alevel[k], blevel[k]))
+      return true;
+  return false;
+}
+
+} // namespace
+} // namespace fcb200
+
+// =========================================================================================== C-ABI
+using namespace fcb200;
+
+extern "C" {
+
+// ---- pressure levels
+int fcb200_pleveltemp(int nx, int ny, const float* tinp, float p, const char* unit, int compute, float* tout, int* fDefined, float undef)
+{
+  return impl_pleveltemp(make_batch(nx, ny, 1), tinp, &p, unit, compute, tout, fDefined, undef);
+}
+int fcb200_pleveltemp_batched(int nx, int ny, int nfields, const float* tinp, const float* p, const char* unit, int compute, float* tout,
+                              int* fDefined, float undef)
+{
+  return impl_pleveltemp(make_batch(nx, ny, nfields), tinp, p, unit, compute, tout, fDefined, undef);
+}
+
+int fcb200_plevelhum(int nx, int ny, const float* t, const float* huminp, float p, const char* unit, int compute, float* humout, int* fDefined,
+                     float undef)
+{
+  return impl_plevelhum(make_batch(nx, ny, 1), t, huminp, &p, unit, compute, humout, fDefined, undef);
+}
+int fcb200_plevelhum_batched(int nx, int ny, int nfields, const float* t, const float* huminp, const float* p, const char* unit, int compute,
+                             float* humout, int* fDefined, float undef)
+{
+  return impl_plevelhum(make_batch(nx, ny, nfields), t, huminp, p, unit, compute, humout, fDefined, undef);
+}
+
+// ---- hybrid levels
+int fcb200_hleveltemp_batched(int nx, int ny, int nfields, const float* tinp, const float* ps, const float* alevel, const float* blevel,
+                              const char* unit, int compute, float* tout, int* fDefined, float undef)
+{ // FC.cc:1046-1098: unit remap first, then bad_hlevel
+  const Batch b = make_batch(nx, ny, nfields);
+  compute = temp_compute(compute, unit);
+  if (any_bad_hlevel(b, alevel, blevel))
+    return 0;
+  return impl_xleveltemp<HLEVEL>(b, tinp, ps, alevel, blevel, compute, tout, fDefined, undef);
+}
+int fcb200_hleveltemp(int nx, int ny, const float* tinp, const float* ps, float alevel, float blevel, const char* unit, int compute, float* tout,
+                      int* fDefined, float undef)
+{
+  return fcb200_hleveltemp_batched(nx, ny, 1, tinp, ps, &alevel, &blevel, unit, compute, tout, fDefined, undef);
+}
+
+int fcb200_hlevelthe_batched(int nx, int ny, int nfields, const float* t, const float* q, const float* ps, const float* alevel,
+                             const float* blevel, int compute, float* the, int* fDefined, float undef)
+{ // FC.cc:1100-1143
+  const Batch b = make_batch(nx, ny, nfields);
+  if (any_bad_hlevel(b, alevel, blevel))
+    return 0;
+  return impl_xlevelthe<HLEVEL>(b, t, q, ps, alevel, blevel, compute, the, fDefined, undef);
+}
+int fcb200_hlevelthe(int nx, int ny, const float* t, const float* q, const float* ps, float alevel, float blevel, int compute, float* the,
+                     int* fDefined, float undef)
+{
+  return fcb200_hlevelthe_batched(nx, ny, 1, t, q, ps, &alevel, &blevel, compute, the, fDefined, undef);
+}
+
+int fcb200_hlevelhum_batched(int nx, int ny, int nfields, const float* t, const float* huminp, const float* ps, const float* alevel,
+                             const float* blevel, const char* unit, int compute, float* humout, int* fDefined, float undef)
+{ // FC.cc:1145-1217
+  if (compute <= 0 || compute >= 13)
+    return 0;
+  const Batch b = make_batch(nx, ny, nfields);
+  if (any_bad_hlevel(b, alevel, blevel))
+    return 0;
+  return impl_xlevelhum<HLEVEL>(b, t, huminp, ps, alevel, blevel, unit, compute, humout, fDefined, undef);
+}
+int fcb200_hlevelhum(int nx, int ny, const float* t, const float* huminp, const float* ps, float alevel, float blevel, const char* unit,
+                     int compute, float* humout, int* fDefined, float undef)
+{
+  return fcb200_hlevelhum_batched(nx, ny, 1, t, huminp, ps, &alevel, &blevel, unit, compute, humout, fDefined, undef);
+}
+
+int fcb200_hlevelducting_batched(int nx, int ny, int nfields, const float* t, const float* h, const float* ps, const float* alevel,
+                                 const float* blevel, int compute, float* duct, int* fDefined, float undef)
+{ // FC.cc:1219-1274
+  const Batch b = make_batch(nx, ny, nfields);
+  if (any_bad_hlevel(b, alevel, blevel))
+    return 0;
+  return impl_xlevelducting<HLEVEL>(b, t, h, ps, alevel, blevel, compute, duct, fDefined, undef);
+}
+int fcb200_hlevelducting(int nx, int ny, const float* t, const float* h, const float* ps, float alevel, float blevel, int compute, float* duct,
+                         int* fDefined, float undef)
+{
+  return fcb200_hlevelducting_batched(nx, ny, 1, t, h, ps, &alevel, &blevel, compute, duct, fDefined, undef);
+}
+
+int fcb200_hlevelpressure_batched(int nx, int ny, int nfields, const float* ps, const float* alevel, const float* blevel, float* p, int* fDefined,
+                                  float undef)
+{ // FC.cc:1276-1304
+  const Batch b = make_batch(nx, ny, nfields);
+  if (any_bad_hlevel(b, alevel, blevel))
+    return 0;
+  const float* in[1] = {ps};
+  const int pf[1] = {0};
+  HPressureOp op;
+  return run_elementwise(b, op, in, pf, p, fDefined, undef, FLAG_FROM_COUNT, [&](int k, FieldMeta& m) {
+    m.a = alevel[k];
+    m.b = blevel[k];
+  });
+}
+int fcb200_hlevelpressure(int nx, int ny, const float* ps, float alevel, float blevel, float* p, int* fDefined, float undef)
+{
+  return fcb200_hlevelpressure_batched(nx, ny, 1, ps, &alevel, &blevel, p, fDefined, undef);
+}
+
+// ---- atmospheric levels
+int fcb200_aleveltemp_batched(int nx, int ny, int nfields, const float* tinp, const float* p, const char* unit, int compute, float* tout,
+                              int* fDefined, float undef)
+{ // FC.cc:1310-1353: range check first, then unit remap
+  if (compute <= 0 || compute >= 6)
+    return 0;
+  compute = temp_compute(compute, unit);
+  return impl_xleveltemp<ALEVEL>(make_batch(nx, ny, nfields), tinp, p, nullptr, nullptr, compute, tout, fDefined, undef);
+}
+int fcb200_aleveltemp(int nx, int ny, const float* tinp, const float* p, const char* unit, int compute, float* tout, int* fDefined, float undef)
+{
+  return fcb200_aleveltemp_batched(nx, ny, 1, tinp, p, unit, compute, tout, fDefined, undef);
+}
+
+int fcb200_alevelthe_batched(int nx, int ny, int nfields, const float* t, const float* q, const float* p, int compute, float* the, int* fDefined,
+                             float undef)
+{ // FC.cc:1355-1392
+  if (compute != 1 && compute != 2)
+    return 0;
+  return impl_xlevelthe<ALEVEL>(make_batch(nx, ny, nfields), t, q, p, nullptr, nullptr, compute, the, fDefined, undef);
+}
+int fcb200_alevelthe(int nx, int ny, const float* t, const float* q, const float* p, int compute, float* the, int* fDefined, float undef)
+{
+  return fcb200_alevelthe_batched(nx, ny, 1, t, q, p, compute, the, fDefined, undef);
+}
+
+int fcb200_alevelhum_batched(int nx, int ny, int nfields, const float* t, const float* huminp, const float* p, const char* unit, int compute,
+                             float* humout, int* fDefined, float undef)
+{ // FC.cc:1394-1458
+  if (compute <= 0 || compute >= 13)
+    return 0;
+  return impl_xlevelhum<ALEVEL>(make_batch(nx, ny, nfields), t, huminp, p, nullptr, nullptr, unit, compute, humout, fDefined, undef);
+}
+int fcb200_alevelhum(int nx, int ny, const float* t, const float* huminp, const float* p, const char* unit, int compute, float* humout,
+                     int* fDefined, float undef)
+{
+  return fcb200_alevelhum_batched(nx, ny, 1, t, huminp, p, unit, compute, humout, fDefined, undef);
+}
+
+int fcb200_alevelducting_batched(int nx, int ny, int nfields, const float* t, const float* h, const float* p, int compute, float* duct,
+                                 int* fDefined, float undef)
+{ // FC.cc:1460-1505
+  return impl_xlevelducting<ALEVEL>(make_batch(nx, ny, nfields), t, h, p, nullptr, nullptr, compute, duct, fDefined, undef);
+}
+int fcb200_alevelducting(int nx, int ny, const float* t, const float* h, const float* p, int compute, float* duct, int* fDefined, float undef)
+{
+  return fcb200_alevelducting_batched(nx, ny, 1, t, h, p, compute, duct, fDefined, undef);
+}
+
+// ---- level independent
+int fcb200_windCooling_batched(int nx, int ny, int nfields, const float* t, const float* u, const float* v, int compute, float* dtcool,
+                               int* fDefined, float undef)
+{ // FC.cc:2181-2229
+  if (compute != 1 && compute != 2)
+    return 0;
+  WindCoolingOp op{(compute == 1) ? H_T0 : 0.f};
+  const float* in[3] = {t, u, v};
+  const int pf[3] = {1, 1, 1};
+  return run_elementwise(make_batch(nx, ny, nfields), op, in, pf, dtcool, fDefined, undef, FLAG_UNCHANGED, NoMeta());
+}
+int fcb200_windCooling(int nx, int ny, const float* t, const float* u, const float* v, int compute, float* dtcool, int* fDefined, float undef)
+{
+  return fcb200_windCooling_batched(nx, ny, 1, t, u, v, compute, dtcool, fDefined, undef);
+}
+
+int fcb200_fieldOPERfield_batched(int compute, int nx, int ny, int nfields, const float* field1, const float* field2, float* fres, int* fDefined,
+                                  float undef)
+{ // FC.cc:2611-2625: only the division recomputes the flag
+  if (compute < 1 || compute > 4)
+    return 0;
+  FieldOperOp op{compute};
+  const float* in[2] = {field1, field2};
+  const int pf[2] = {1, 1};
+  return run_elementwise(make_batch(nx, ny, nfields), op, in, pf, fres, fDefined, undef, compute == 4 ? FLAG_FROM_COUNT : FLAG_UNCHANGED, NoMeta());
+}
+int fcb200_fieldOPERfield(int compute, int nx, int ny, const float* field1, const float* field2, float* fres, int* fDefined, float undef)
+{
+  return fcb200_fieldOPERfield_batched(compute, nx, ny, 1, field1, field2, fres, fDefined, undef);
+}
+
+int fcb200_momentumXcoordinate_batched(int nx, int ny, int nfields, const float* v, const float* xmapr, const float* fcoriolis, float fcoriolisMin,
+                                       float* mxy, int* fDefined, float undef)
+{ // FC.cc:2351-2386
+  if (nx < 3 || ny < 3)
+    return 0;
+  MomentumOp<true> op{fabsf(fcoriolisMin)};
+  const float* in[3] = {v, xmapr, fcoriolis};
+  const int pf[3] = {1, 0, 0};
+  return run_elementwise(make_batch(nx, ny, nfields), op, in, pf, mxy, fDefined, undef, FLAG_FROM_COUNT, NoMeta());
+}
+int fcb200_momentumXcoordinate(int nx, int ny, const float* v, const float* xmapr, const float* fcoriolis, float fcoriolisMin, float* mxy,
+                               int* fDefined, float undef)
+{
+  return fcb200_momentumXcoordinate_batched(nx, ny, 1, v, xmapr, fcoriolis, fcoriolisMin, mxy, fDefined, undef);
+}
+
+int fcb200_momentumYcoordinate_batched(int nx, int ny, int nfields, const float* u, const float* ymapr, const float* fcoriolis, float fcoriolisMin,
+                                       float* nxy, int* fDefined, float undef)
+{ // FC.cc:2388-2422
+  if (nx < 3 || ny < 3)
+    return 0;
+  MomentumOp<false> op{fabsf(fcoriolisMin)};
+  const float* in[3] = {u, ymapr, fcoriolis};
+  const int pf[3] = {1, 0, 0};
+  return run_elementwise(make_batch(nx, ny, nfields), op, in, pf, nxy, fDefined, undef, FLAG_FROM_COUNT, NoMeta());
+}
+int fcb200_momentumYcoordinate(int nx, int ny, const float* u, const float* ymapr, const float* fcoriolis, float fcoriolisMin, float* nxy,
+                               int* fDefined, float undef)
+{
+  return fcb200_momentumYcoordinate_batched(nx, ny, 1, u, ymapr, fcoriolis, fcoriolisMin, nxy, fDefined, undef);
+}
+
+} // extern "C"

@@ -1,0 +1,397 @@
+// ops_ensemble.cu -- ensemble reductions meanValue / stddevValue / extremeValue / probability
+// (reference FC.cc:2696-2860).
+//
+// One thread owns W (4 or 1) grid points and walks the M member fields IN MEMBER ORDER with float
+// accumulators, exactly like the reference's inner loops: a cross-lane tree reduction would change
+// the rounding order (51 % bit-equal) while thread-per-point is bit-exact and
+// just as coalesced -- M independent 16-byte streams per thread.  Warp/block reductions are only
+// used for the undefined-point counter.
+//
+// Batched over `ntimes`: member j is a dense [ntimes][n] array, one CTA works on one chunk of one
+// time, the output is [ntimes][n].
+#include "device_common.cuh"
+
+#include "../../include/fcb200.h"
+
+#include <vector>
+
+namespace fcb200 {
+namespace {
+
+using dev::is_def;
+
+constexpr int EN_THREADS = 256;
+enum { EN_MEAN = 0, EN_STDDEV = 1, EN_EXTREME = 2, EN_PROB = 3 };
+enum { MF_ALL = 1, MF_NOT_NONE = 2 }; // per (time, member) flag bits
+
+struct EnsArgs
+{
+  const float* const* members; // device table of M base pointers
+  const int* member_flags;     // device [ntimes][M]
+  const FieldMeta* meta;       // per time: all = input flag ALL_DEFINED (extremeValue), a = probability divisor lo, b = hi (double split)
+  const double* prob_div;      // per time: nfields_defined / 100.0 (probability c1-3), or nullptr
+  float* out;
+  unsigned long long* counters;
+  long long n;
+  int nmembers, ntimes, chunks, align0;
+  int compute;
+  int check_above, check_below;
+  float v_above, v_below;
+  float undef;
+};
+
+// W points starting at `base` of one time step: walk the members in order, then store.
+template <int MODE, int W>
+__device__ __forceinline__ void ensemble_points(const EnsArgs& a, const float* const* mptr, const int* mflag, int time, long long base, float* out,
+                                                bool in_all, unsigned& nundef)
+{
+  const float undef = a.undef;
+  const int M = a.nmembers;
+  float acc0[W], acc1[W]; // mean: sum,-   stddev: m, m2   extreme: cur, idx   probability: count,-
+  int cnt[W];
+#pragma unroll
+  for (int w = 0; w < W; ++w) {
+    acc0[w] = (MODE == EN_EXTREME) ? undef : 0.f;
+    acc1[w] = (MODE == EN_EXTREME) ? undef : 0.f;
+    cnt[w] = 0;
+  }
+  const bool want_max = (a.compute == 1 || a.compute == 3);
+
+#pragma unroll 6
+  for (int j = 0; j < M; ++j) {
+    const int fl = mflag[j];
+    if (MODE == EN_PROB && !(fl & MF_NOT_NONE))
+      continue; // a member whose FIELD flag is NONE_DEFINED is not counted (FC.cc:2841)
+    float x[W];
+    if constexpr (W == 4) {
+      const float4 q = *reinterpret_cast<const float4*>(mptr[j] + base);
+      x[0] = q.x;
+      x[1] = q.y;
+      x[2] = q.z;
+      x[3] = q.w;
+    } else {
+      x[0] = mptr[j][base];
+    }
+#pragma unroll
+    for (int w = 0; w < W; ++w) {
+      const float xv = x[w];
+      if (MODE == EN_MEAN) { // FC.cc:2709-2714
+        if ((fl & MF_ALL) || is_def(xv, undef)) {
+          cnt[w] += 1;
+          acc0[w] += xv;
+        }
+      } else if (MODE == EN_STDDEV) { // FC.cc:2739-2747, Welford in float, no FMA
+        if ((fl & MF_ALL) || is_def(xv, undef)) {
+          const float delta = xv - acc0[w];
+          cnt[w] += 1;
+          acc0[w] += delta / (float)cnt[w];
+          acc1[w] += delta * (xv - acc0[w]);
+        }
+      } else if (MODE == EN_EXTREME) { // FC.cc:2778-2783, 2792-2798
+        if (acc0[w] == undef || ((in_all || is_def(xv, undef)) && (want_max ? (acc0[w] < xv) : (acc0[w] > xv)))) {
+          acc0[w] = xv;
+          acc1[w] = (float)j;
+        }
+      } else { // FC.cc:2843-2846
+        if ((xv != undef) && (!a.check_above || xv > a.v_above) && (!a.check_below || xv < a.v_below))
+          acc0[w] += 1.f;
+      }
+    }
+  }
+
+  float r[W];
+#pragma unroll
+  for (int w = 0; w < W; ++w) {
+    if (MODE == EN_MEAN) {
+      if (cnt[w] > 0)
+        r[w] = acc0[w] / (float)cnt[w];
+      else {
+        r[w] = undef;
+        nundef += 1;
+      }
+    } else if (MODE == EN_STDDEV) {
+      if (cnt[w] > 0)
+        r[w] = sqrtf(acc1[w] / (float)cnt[w]); // == float(sqrt(double(m2/n))): double rounding is innocuous for sqrt
+      else {
+        r[w] = undef;
+        nundef += 1;
+      }
+    } else if (MODE == EN_EXTREME) {
+      r[w] = (a.compute >= 3) ? acc1[w] : acc0[w];
+      if (r[w] == undef)
+        nundef += 1;
+    } else {
+      // nfields_defined is a property of the time step (member FIELD flags), not of the point
+      if (a.meta[time].b == 0.f) {
+        r[w] = undef;
+        nundef += 1;
+      } else if (a.compute < 4)
+        r[w] = (float)((double)acc0[w] / a.prob_div[time]);
+      else
+        r[w] = acc0[w];
+    }
+  }
+  if constexpr (W == 4)
+    *reinterpret_cast<float4*>(out + base) = make_float4(r[0], r[1], r[2], r[3]);
+  else
+    out[base] = r[0];
+}
+
+template <int MODE, int W>
+__global__ void __launch_bounds__(EN_THREADS) ensemble_kernel(const EnsArgs a)
+{
+  extern __shared__ unsigned char smem_raw[];
+  const float** mptr = reinterpret_cast<const float**>(smem_raw);
+  int* mflag = reinterpret_cast<int*>(smem_raw + sizeof(float*) * a.nmembers);
+
+  const int time = blockIdx.x / a.chunks;
+  const int chunk = blockIdx.x - time * a.chunks;
+  const int M = a.nmembers;
+  const long long n = a.n;
+  for (int j = threadIdx.x; j < M; j += EN_THREADS) {
+    mptr[j] = a.members[j] + (long long)time * n;
+    mflag[j] = a.member_flags[(long long)time * M + j];
+  }
+  __syncthreads();
+
+  // per-time peel so that the float4 groups are 16-byte aligned (see elementwise.cuh)
+  const int head = (W == 4) ? ((4 - ((a.align0 + (int)(((long long)time * n) & 3)) & 3)) & 3) : 0;
+  const long long groups = (n - head) / W;
+  float* out = a.out + (long long)time * n;
+  const bool in_all = a.meta[time].all != 0;
+  unsigned nundef = 0;
+
+  const long long g = (long long)chunk * EN_THREADS + threadIdx.x;
+  if (g < groups)
+    ensemble_points<MODE, W>(a, mptr, mflag, time, head + g * W, out, in_all, nundef);
+
+  if (W == 4 && chunk == 0) {
+    const long long tail0 = head + groups * 4;
+    const int ntail = (int)(n - tail0);
+    long long idx = -1;
+    if ((int)threadIdx.x < head)
+      idx = threadIdx.x;
+    else if (threadIdx.x >= 32 && (int)threadIdx.x - 32 < ntail)
+      idx = tail0 + (threadIdx.x - 32);
+    if (idx >= 0)
+      ensemble_points<MODE, 1>(a, mptr, mflag, time, idx, out, in_all, nundef);
+  }
+
+  dev::block_add_counter(nundef, a.counters + time);
+}
+
+struct EnsHost
+{
+  int mode, compute;
+  int nx, ny, ntimes, nmembers;
+  const float* const* fields;
+  const int* fDefinedIn; // [ntimes][nmembers] or nullptr (extremeValue)
+  const float* limits;
+  int nlimits;
+  float* fres;
+  int* fDefinedOut; // [ntimes]; for extremeValue also the input flag
+  float undef;
+};
+
+int run_ensemble(const EnsHost& h)
+{
+  if (h.nx <= 0 || h.ny <= 0 || h.ntimes <= 0 || (long long)h.nx * h.ny >= 0x7fffffffLL) {
+    set_error("fcb200: invalid grid or batch size (nx=%d ny=%d ntimes=%d)", h.nx, h.ny, h.ntimes);
+    return -1;
+  }
+  const int M = h.nmembers > 0 ? h.nmembers : 0;
+  if (M > 4096) {
+    set_error("fcb200: at most 4096 ensemble members per call (got %d)", M);
+    return -1;
+  }
+  const long long n = (long long)h.nx * h.ny;
+  Call call;
+
+  EnsArgs a;
+  a.compute = h.compute;
+  a.check_above = a.check_below = 0;
+  a.v_above = a.v_below = 0.f;
+  a.prob_div = nullptr;
+  if (h.mode == EN_PROB) { // FC.cc:2821-2825
+    const bool between = (h.nlimits >= 2) && (h.compute == 3 || h.compute == 6);
+    a.check_above = (h.nlimits >= 1) && (h.compute == 1 || h.compute == 4 || between);
+    a.check_below = (h.nlimits >= 1) && (h.compute == 2 || h.compute == 5 || between);
+    if (a.check_above || a.check_below) {
+      a.v_above = h.limits[0];
+      a.v_below = between ? h.limits[1] : h.limits[0];
+    }
+  }
+
+  std::vector<const float*> dptr(M > 0 ? M : 1, nullptr);
+  for (int j = 0; j < M; ++j)
+    dptr[j] = call.in(h.fields[j], (size_t)(n * h.ntimes));
+  float* d_out = call.out(h.fres, (size_t)(n * h.ntimes));
+  if (!call.ok())
+    return -1;
+
+  std::vector<int> mflags((size_t)h.ntimes * (M > 0 ? M : 1), 0);
+  std::vector<double> pdiv(h.ntimes, 1.0);
+  FieldMeta* meta = call.meta_host(h.ntimes);
+  if (!call.ok())
+    return -1;
+  for (int t = 0; t < h.ntimes; ++t) {
+    int counted = 0;
+    for (int j = 0; j < M; ++j) {
+      int f = 0;
+      if (h.fDefinedIn) {
+        const int fd = h.fDefinedIn[(size_t)t * M + j];
+        if (fd == ALL_DEFINED)
+          f |= MF_ALL;
+        if (fd != NONE_DEFINED) {
+          f |= MF_NOT_NONE;
+          counted += 1;
+        }
+      }
+      mflags[(size_t)t * M + j] = f;
+    }
+    meta[t].all = (h.mode == EN_EXTREME && h.fDefinedOut[t] == ALL_DEFINED) ? 1 : 0;
+    meta[t].a = 0.f;
+    meta[t].b = (float)counted;
+    meta[t].c = 0.f;
+    pdiv[t] = counted / 100.0; // FC.cc:2855
+  }
+  a.members = static_cast<const float* const*>(call.upload_small(dptr.data(), sizeof(float*) * dptr.size()));
+  a.member_flags = static_cast<const int*>(call.upload_small(mflags.data(), sizeof(int) * mflags.size()));
+  if (h.mode == EN_PROB)
+    a.prob_div = static_cast<const double*>(call.upload_small(pdiv.data(), sizeof(double) * pdiv.size()));
+  a.meta = call.upload_meta();
+  a.counters = call.counters(h.ntimes);
+  if (!call.ok())
+    return -1;
+
+  a.out = d_out;
+  a.n = n;
+  a.nmembers = M;
+  a.ntimes = h.ntimes;
+  a.undef = h.undef;
+
+  bool vec = n >= 16;
+  const uintptr_t a0 = reinterpret_cast<uintptr_t>(d_out) & 15;
+  if (a0 & 3)
+    vec = false;
+  for (int j = 0; j < M; ++j)
+    if ((reinterpret_cast<uintptr_t>(dptr[j]) & 15) != a0)
+      vec = false;
+  a.align0 = (int)(a0 >> 2);
+  const int width = vec ? 4 : 1;
+  const long long per_cta = (long long)EN_THREADS * width;
+  a.chunks = (int)((n + per_cta - 1) / per_cta);
+  const long long grid = (long long)a.chunks * h.ntimes;
+  if (grid > 0x7fffffffLL) {
+    set_error("fcb200: batch too large for one launch (%lld CTAs)", grid);
+    return -1;
+  }
+  const size_t smem = (sizeof(float*) + sizeof(int)) * (size_t)(M > 0 ? M : 1);
+
+#define FCB_LAUNCH_ENS(MODE)                                                                                                                         \
+  do {                                                                                                                                               \
+    if (vec)                                                                                                                                         \
+      ensemble_kernel<MODE, 4><<<(unsigned)grid, EN_THREADS, smem, call.stream()>>>(a);                                                             \
+    else                                                                                                                                             \
+      ensemble_kernel<MODE, 1><<<(unsigned)grid, EN_THREADS, smem, call.stream()>>>(a);                                                             \
+  } while (0)
+  switch (h.mode) {
+  case EN_MEAN:
+    FCB_LAUNCH_ENS(EN_MEAN);
+    break;
+  case EN_STDDEV:
+    FCB_LAUNCH_ENS(EN_STDDEV);
+    break;
+  case EN_EXTREME:
+    FCB_LAUNCH_ENS(EN_EXTREME);
+    break;
+  default:
+    FCB_LAUNCH_ENS(EN_PROB);
+    break;
+  }
+#undef FCB_LAUNCH_ENS
+  count_launch();
+
+  int* flags = h.fDefinedOut;
+  const int ntimes = h.ntimes;
+  return call.finish([=](const unsigned long long* cnt) {
+    for (int t = 0; t < ntimes; ++t)
+      flags[t] = check_defined(cnt[t], (unsigned long long)n);
+  });
+}
+
+} // namespace
+} // namespace fcb200
+
+// =========================================================================================== C-ABI
+using namespace fcb200;
+
+extern "C" {
+
+int fcb200_meanValue_batched(int nx, int ny, int ntimes, const float* const* fields, int nmembers, const int* fDefinedIn, float* fres,
+                             int* fDefinedOut, float undef)
+{ // FC.cc:2696-2724
+  EnsHost h{EN_MEAN, 0, nx, ny, ntimes, nmembers, fields, fDefinedIn, nullptr, 0, fres, fDefinedOut, undef};
+  return run_ensemble(h);
+}
+int fcb200_meanValue(int nx, int ny, const float* const* fields, int nfields, const int* fDefinedIn, float* fres, int* fDefinedOut, float undef)
+{
+  return fcb200_meanValue_batched(nx, ny, 1, fields, nfields, fDefinedIn, fres, fDefinedOut, undef);
+}
+
+int fcb200_stddevValue_batched(int nx, int ny, int ntimes, const float* const* fields, int nmembers, const int* fDefinedIn, float* fres,
+                               int* fDefinedOut, float undef)
+{ // FC.cc:2726-2757
+  EnsHost h{EN_STDDEV, 0, nx, ny, ntimes, nmembers, fields, fDefinedIn, nullptr, 0, fres, fDefinedOut, undef};
+  return run_ensemble(h);
+}
+int fcb200_stddevValue(int nx, int ny, const float* const* fields, int nfields, const int* fDefinedIn, float* fres, int* fDefinedOut, float undef)
+{
+  return fcb200_stddevValue_batched(nx, ny, 1, fields, nfields, fDefinedIn, fres, fDefinedOut, undef);
+}
+
+int fcb200_extremeValue_batched(int compute, int nx, int ny, int ntimes, const float* const* fields, int nmembers, float* fres, int* fDefined,
+                                float undef)
+{ // FC.cc:2759-2805
+  if (nmembers <= 0)
+    return 0;
+  if (compute < 1 || compute > 4) {
+    // the reference computes nothing, leaves fres untouched, sets ALL_DEFINED and returns true (:2774-2804)
+    for (int t = 0; t < ntimes; ++t)
+      fDefined[t] = ALL_DEFINED;
+    return 1;
+  }
+  EnsHost h{EN_EXTREME, compute, nx, ny, ntimes, nmembers, fields, nullptr, nullptr, 0, fres, fDefined, undef};
+  return run_ensemble(h);
+}
+int fcb200_extremeValue(int compute, int nx, int ny, const float* const* fields, int nfields, float* fres, int* fDefined, float undef)
+{
+  return fcb200_extremeValue_batched(compute, nx, ny, 1, fields, nfields, fres, fDefined, undef);
+}
+
+int fcb200_probability_batched(int compute, int nx, int ny, int ntimes, const float* const* fields, int nmembers, const int* fDefinedIn,
+                               const float* limits, int nlimits, float* fres, int* fDefinedOut, float undef)
+{ // FC.cc:2807-2860
+  const bool between = (nlimits >= 2) && (compute == 3 || compute == 6);
+  const bool above = (nlimits >= 1) && (compute == 1 || compute == 4 || between);
+  const bool below = (nlimits >= 1) && (compute == 2 || compute == 5 || between);
+  EnsHost h{EN_PROB, compute, nx, ny, ntimes, nmembers, fields, fDefinedIn, limits, nlimits, fres, fDefinedOut, undef};
+  if (!(above || below)) {
+    // fill undef, NONE_DEFINED, return false (:2827-2833): run the kernel with no member counted
+    EnsHost f = h;
+    f.nmembers = 0;
+    f.compute = 4;
+    const int r = run_ensemble(f);
+    if (r < 0)
+      return r;
+    return 0;
+  }
+  return run_ensemble(h);
+}
+int fcb200_probability(int compute, int nx, int ny, const float* const* fields, int nfields, const int* fDefinedIn, const float* limits, int nlimits,
+                       float* fres, int* fDefinedOut, float undef)
+{
+  return fcb200_probability_batched(compute, nx, ny, 1, fields, nfields, fDefinedIn, limits, nlimits, fres, fDefinedOut, undef);
+}
+
+} // extern "C"

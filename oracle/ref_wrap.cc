@@ -1,0 +1,281 @@
+// oracle/ref_wrap.cc -- TEST INFRASTRUCTURE, not product code.
+//
+// extern "C" adapter around the UNMODIFIED reference (mi-fieldcalc, compiled in place from
+// /root/reference/src/mi_fieldcalc/*.cc by oracle/Makefile into oracle/_ref/). It exposes every
+// entry of include/fcb200_api.inc with the prefix `fcref_` so that tests can drive the real
+// reference, the C restatement (fco_*) and the CUDA product (fcb200_*) through one signature.
+// Nothing here computes anything: each function forwards to miutil::fieldcalc::<name>
+// (src/mi_fieldcalc/FieldCalculations.h) and converts `ValuesDefined&` <-> `int*`.
+//
+// Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs
+// may load the resulting library.
+
+#include "mi_fieldcalc/FieldCalculations.h"
+
+#include <string>
+#include <vector>
+
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+namespace fc = miutil::fieldcalc;
+using miutil::ValuesDefined;
+
+namespace {
+struct Flag
+{
+  int* p;
+  ValuesDefined v;
+  explicit Flag(int* fp)
+      : p(fp)
+      , v(static_cast<ValuesDefined>(*fp))
+  {
+  }
+  ~Flag() { *p = static_cast<int>(v); }
+  operator ValuesDefined&() { return v; }
+};
+
+std::vector<float*> as_vector(const float* const* fields, int n)
+{
+  std::vector<float*> v(n > 0 ? n : 0);
+  for (int i = 0; i < n; ++i)
+    v[i] = const_cast<float*>(fields[i]);
+  return v;
+}
+
+std::vector<ValuesDefined> as_flags(const int* f, int n)
+{
+  std::vector<ValuesDefined> v(n > 0 ? n : 0);
+  for (int i = 0; i < n; ++i)
+    v[i] = static_cast<ValuesDefined>(f[i]);
+  return v;
+}
+} // namespace
+
+extern "C" {
+
+int fcref_openmp_threads()
+{
+#ifdef _OPENMP
+  return omp_get_max_threads();
+#else
+  return 1;
+#endif
+}
+
+int fcref_pleveltemp(int nx, int ny, const float* tinp, float p, const char* unit, int compute, float* tout, int* fDefined, float undef)
+{
+  Flag f(fDefined);
+  return fc::pleveltemp(nx, ny, tinp, p, unit, compute, tout, f, undef);
+}
+
+int fcref_plevelhum(int nx, int ny, const float* t, const float* huminp, float p, const char* unit, int compute, float* humout, int* fDefined, float undef)
+{
+  Flag f(fDefined);
+  return fc::plevelhum(nx, ny, t, huminp, p, unit, compute, humout, f, undef);
+}
+
+int fcref_hleveltemp(int nx, int ny, const float* tinp, const float* ps, float alevel, float blevel, const char* unit, int compute, float* tout,
+                     int* fDefined, float undef)
+{
+  Flag f(fDefined);
+  return fc::hleveltemp(nx, ny, tinp, ps, alevel, blevel, unit, compute, tout, f, undef);
+}
+
+int fcref_hlevelthe(int nx, int ny, const float* t, const float* q, const float* ps, float alevel, float blevel, int compute, float* the, int* fDefined,
+                    float undef)
+{
+  Flag f(fDefined);
+  return fc::hlevelthe(nx, ny, t, q, ps, alevel, blevel, compute, the, f, undef);
+}
+
+int fcref_hlevelhum(int nx, int ny, const float* t, const float* huminp, const float* ps, float alevel, float blevel, const char* unit, int compute,
+                    float* humout, int* fDefined, float undef)
+{
+  Flag f(fDefined);
+  return fc::hlevelhum(nx, ny, t, huminp, ps, alevel, blevel, unit, compute, humout, f, undef);
+}
+
+int fcref_hlevelducting(int nx, int ny, const float* t, const float* h, const float* ps, float alevel, float blevel, int compute, float* duct,
+                        int* fDefined, float undef)
+{
+  Flag f(fDefined);
+  return fc::hlevelducting(nx, ny, t, h, ps, alevel, blevel, compute, duct, f, undef);
+}
+
+int fcref_hlevelpressure(int nx, int ny, const float* ps, float alevel, float blevel, float* p, int* fDefined, float undef)
+{
+  Flag f(fDefined);
+  return fc::hlevelpressure(nx, ny, ps, alevel, blevel, p, f, undef);
+}
+
+int fcref_aleveltemp(int nx, int ny, const float* tinp, const float* p, const char* unit, int compute, float* tout, int* fDefined, float undef)
+{
+  Flag f(fDefined);
+  return fc::aleveltemp(nx, ny, tinp, p, unit, compute, tout, f, undef);
+}
+
+int fcref_alevelthe(int nx, int ny, const float* t, const float* q, const float* p, int compute, float* the, int* fDefined, float undef)
+{
+  Flag f(fDefined);
+  return fc::alevelthe(nx, ny, t, q, p, compute, the, f, undef);
+}
+
+int fcref_alevelhum(int nx, int ny, const float* t, const float* huminp, const float* p, const char* unit, int compute, float* humout, int* fDefined,
+                    float undef)
+{
+  Flag f(fDefined);
+  return fc::alevelhum(nx, ny, t, huminp, p, unit, compute, humout, f, undef);
+}
+
+int fcref_alevelducting(int nx, int ny, const float* t, const float* h, const float* p, int compute, float* duct, int* fDefined, float undef)
+{
+  Flag f(fDefined);
+  return fc::alevelducting(nx, ny, t, h, p, compute, duct, f, undef);
+}
+
+int fcref_ilevelgwind(int nx, int ny, const float* mpot, const float* xmapr, const float* ymapr, const float* fcoriolis, float* ug, float* vg,
+                      int* fDefined, float undef)
+{
+  Flag f(fDefined);
+  return fc::ilevelgwind(nx, ny, mpot, xmapr, ymapr, fcoriolis, ug, vg, f, undef);
+}
+
+int fcref_relvort(int nx, int ny, const float* u, const float* v, const float* xmapr, const float* ymapr, float* rvort, int* fDefined, float undef)
+{
+  Flag f(fDefined);
+  return fc::relvort(nx, ny, u, v, xmapr, ymapr, rvort, f, undef);
+}
+
+int fcref_absvort(int nx, int ny, const float* u, const float* v, const float* xmapr, const float* ymapr, const float* fcoriolis, float* avort,
+                  int* fDefined, float undef)
+{
+  Flag f(fDefined);
+  return fc::absvort(nx, ny, u, v, xmapr, ymapr, fcoriolis, avort, f, undef);
+}
+
+int fcref_divergence(int nx, int ny, const float* u, const float* v, const float* xmapr, const float* ymapr, float* diverg, int* fDefined, float undef)
+{
+  Flag f(fDefined);
+  return fc::divergence(nx, ny, u, v, xmapr, ymapr, diverg, f, undef);
+}
+
+int fcref_advection(int nx, int ny, const float* fld, const float* u, const float* v, const float* xmapr, const float* ymapr, float hours, float* advec,
+                    int* fDefined, float undef)
+{
+  Flag f(fDefined);
+  return fc::advection(nx, ny, fld, u, v, xmapr, ymapr, hours, advec, f, undef);
+}
+
+int fcref_gradient(int nx, int ny, const float* field, const float* xmapr, const float* ymapr, int compute, float* fgrad, int* fDefined, float undef)
+{
+  Flag f(fDefined);
+  return fc::gradient(nx, ny, field, xmapr, ymapr, compute, fgrad, f, undef);
+}
+
+int fcref_shapiro2_filter(int nx, int ny, float* field, float* fsmooth, int* fDefined, float undef)
+{
+  Flag f(fDefined);
+  return fc::shapiro2_filter(nx, ny, field, fsmooth, f, undef);
+}
+
+int fcref_windCooling(int nx, int ny, const float* t, const float* u, const float* v, int compute, float* dtcool, int* fDefined, float undef)
+{
+  Flag f(fDefined);
+  return fc::windCooling(nx, ny, t, u, v, compute, dtcool, f, undef);
+}
+
+int fcref_thermalFrontParameter(int nx, int ny, const float* t, const float* xmapr, const float* ymapr, float* tfp, int* fDefined, float undef)
+{
+  Flag f(fDefined);
+  return fc::thermalFrontParameter(nx, ny, t, xmapr, ymapr, tfp, f, undef);
+}
+
+int fcref_momentumXcoordinate(int nx, int ny, const float* v, const float* xmapr, const float* fcoriolis, float fcoriolisMin, float* mxy, int* fDefined,
+                              float undef)
+{
+  Flag f(fDefined);
+  return fc::momentumXcoordinate(nx, ny, v, xmapr, fcoriolis, fcoriolisMin, mxy, f, undef);
+}
+
+int fcref_momentumYcoordinate(int nx, int ny, const float* u, const float* ymapr, const float* fcoriolis, float fcoriolisMin, float* nxy, int* fDefined,
+                              float undef)
+{
+  Flag f(fDefined);
+  return fc::momentumYcoordinate(nx, ny, u, ymapr, fcoriolis, fcoriolisMin, nxy, f, undef);
+}
+
+int fcref_jacobian(int nx, int ny, const float* field1, const float* field2, const float* xmapr, const float* ymapr, float* fjacobian, int* fDefined,
+                   float undef)
+{
+  Flag f(fDefined);
+  return fc::jacobian(nx, ny, field1, field2, xmapr, ymapr, fjacobian, f, undef);
+}
+
+int fcref_vesselIcingOverland(int nx, int ny, const float* airtemp, const float* seatemp, const float* u, const float* v, const float* sal,
+                              const float* aice, float* icing, int* fDefined, float undef)
+{
+  Flag f(fDefined);
+  return fc::vesselIcingOverland(nx, ny, airtemp, seatemp, u, v, sal, aice, icing, f, undef);
+}
+
+int fcref_vesselIcingMertins(int nx, int ny, const float* airtemp, const float* seatemp, const float* u, const float* v, const float* sal,
+                             const float* aice, float* icing, int* fDefined, float undef)
+{
+  Flag f(fDefined);
+  return fc::vesselIcingMertins(nx, ny, airtemp, seatemp, u, v, sal, aice, icing, f, undef);
+}
+
+int fcref_vesselIcingModStall(int nx, int ny, const float* sal, const float* wave, const float* x_wind, const float* y_wind, const float* airtemp,
+                              const float* rh, const float* sst, const float* p, const float* Pw, const float* aice, const float* depth, float vs,
+                              float alpha, float zmin, float zmax, float* icing, int* fDefined, float undef)
+{
+  Flag f(fDefined);
+  return fc::vesselIcingModStall(nx, ny, sal, wave, x_wind, y_wind, airtemp, rh, sst, p, Pw, aice, depth, vs, alpha, zmin, zmax, icing, f, undef);
+}
+
+int fcref_vesselIcingMincog(int nx, int ny, const float* sal, const float* wave, const float* x_wind, const float* y_wind, const float* airtemp,
+                            const float* rh, const float* sst, const float* p, const float* Pw, const float* aice, const float* depth, float vs,
+                            float alpha, float zmin, float zmax, int alt, float* icing, int* fDefined, float undef)
+{
+  Flag f(fDefined);
+  return fc::vesselIcingMincog(nx, ny, sal, wave, x_wind, y_wind, airtemp, rh, sst, p, Pw, aice, depth, vs, alpha, zmin, zmax, alt, icing, f, undef);
+}
+
+int fcref_fieldOPERfield(int compute, int nx, int ny, const float* field1, const float* field2, float* fres, int* fDefined, float undef)
+{
+  Flag f(fDefined);
+  return fc::fieldOPERfield(compute, nx, ny, field1, field2, fres, f, undef);
+}
+
+int fcref_meanValue(int nx, int ny, const float* const* fields, int nfields, const int* fDefinedIn, float* fres, int* fDefinedOut, float undef)
+{
+  Flag f(fDefinedOut);
+  return fc::meanValue(nx, ny, as_vector(fields, nfields), as_flags(fDefinedIn, nfields), fres, f, undef);
+}
+
+int fcref_stddevValue(int nx, int ny, const float* const* fields, int nfields, const int* fDefinedIn, float* fres, int* fDefinedOut, float undef)
+{
+  Flag f(fDefinedOut);
+  return fc::stddevValue(nx, ny, as_vector(fields, nfields), as_flags(fDefinedIn, nfields), fres, f, undef);
+}
+
+int fcref_extremeValue(int compute, int nx, int ny, const float* const* fields, int nfields, float* fres, int* fDefined, float undef)
+{
+  Flag f(fDefined);
+  return fc::extremeValue(compute, nx, ny, as_vector(fields, nfields), fres, f, undef);
+}
+
+int fcref_probability(int compute, int nx, int ny, const float* const* fields, int nfields, const int* fDefinedIn, const float* limits, int nlimits,
+                      float* fres, int* fDefinedOut, float undef)
+{
+  Flag f(fDefinedOut);
+  // the reference reads limits[0] before validating the size (FieldCalculations.cc:2824);
+  // keep one readable element so that the nlimits == 0 rejection path can be driven safely
+  std::vector<float> lim(limits, limits + (nlimits > 0 ? nlimits : 0));
+  lim.reserve(2);
+  return fc::probability(compute, nx, ny, as_vector(fields, nfields), as_flags(fDefinedIn, nfields), lim, fres, f, undef);
+}
+
+} // extern "C"

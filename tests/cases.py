@@ -1,0 +1,295 @@
+"""Seeded synthetic inputs and the operator case table shared by the CPU and GPU parity suites.
+
+A *case* is a list of arguments in the exact order of include/fcb200_api.inc, with
+  - input fields as float32 numpy arrays (shape (ny, nx), nx fastest -- the reference's i = y*nx + x),
+  - output fields pre-filled with a sentinel so that "left untouched" is observable,
+  - the in/out ValuesDefined flag as a 1-element int32 array.
+`run(api, case)` copies the arguments, calls `<prefix><op>` and returns (ret, outputs, flag).
+
+Synthetic fields follow SURVEY.md 8(d): smooth sums of sinusoids plus a little white noise, in
+physically plausible ranges (so that the saturation table stays in range unless a test wants
+otherwise), with optional undefined-value patterns.
+"""
+from __future__ import annotations
+
+import copy
+
+import numpy as np
+
+ALL, NONE, SOME = 0, 1, 2
+SENTINEL = np.float32(-777.25)
+UNDEF = np.float32(1.0e35)
+
+
+# ----------------------------------------------------------------------------------------- fields
+def smooth(rng, nx, ny, lo, hi, noise=0.01):
+    """smooth field in [lo, hi]: a few sinusoids + white noise, float32 (ny, nx)"""
+    y, x = np.mgrid[0:ny, 0:nx]
+    f = np.zeros((ny, nx))
+    for _ in range(3):
+        kx, ky = rng.uniform(0.5, 4.0, 2)
+        ph = rng.uniform(0, 2 * np.pi, 2)
+        f += rng.uniform(0.3, 1.0) * np.sin(2 * np.pi * kx * x / max(nx, 2) + ph[0]) * np.cos(2 * np.pi * ky * y / max(ny, 2) + ph[1])
+    f += noise * rng.standard_normal((ny, nx)) * 3
+    f = (f - f.min()) / max(f.max() - f.min(), 1e-12)
+    return (lo + (hi - lo) * f).astype(np.float32)
+
+
+def uniform(rng, nx, ny, lo, hi):
+    return rng.uniform(lo, hi, (ny, nx)).astype(np.float32)
+
+
+FIELD_RANGES = {
+    "tk": (215.0, 310.0),      # temperature, K
+    "tc": (-25.0, 5.0),        # air temperature, deg C (icing)
+    "th": (260.0, 330.0),      # potential temperature, K
+    "q": (1e-6, 2e-2),         # specific humidity, kg/kg
+    "rh": (1.0, 100.0),        # relative humidity, %
+    "rh01": (0.4, 1.0),        # relative humidity, fraction (icing)
+    "p": (150.0, 1040.0),      # pressure field, hPa
+    "ps": (950.0, 1050.0),     # surface pressure, hPa
+    "pmsl": (960.0, 1030.0),
+    "wind": (-30.0, 30.0),
+    "z": (4800.0, 5900.0),     # geopotential height / Montgomery-like
+    "sst": (-1.0, 8.0),
+    "sal": (30.0, 35.0),
+    "aice": (0.0, 0.6),
+    "wave": (0.0, 8.0),
+    "pw": (3.0, 12.0),
+    "depth": (20.0, 3000.0),
+    "any": (-50.0, 50.0),
+}
+
+
+def field(rng, kind, nx, ny):
+    if kind == "xm" or kind == "ym":
+        return (smooth(rng, nx, ny, 0.97, 1.03, noise=0.0) / np.float32(2 * 2500.0)).astype(np.float32)
+    if kind == "fc":
+        return smooth(rng, nx, ny, 1.1e-4, 1.4e-4, noise=0.0)
+    if kind == "fc0":  # Coriolis field crossing zero (momentum coordinates clamp)
+        return smooth(rng, nx, ny, -3e-5, 1.4e-4, noise=0.0)
+    lo, hi = FIELD_RANGES[kind]
+    if kind in ("aice", "wave", "pw", "depth", "sal"):
+        return uniform(rng, nx, ny, lo, hi)
+    return smooth(rng, nx, ny, lo, hi)
+
+
+def apply_mask(rng, a, mask, undef):
+    """in-place undefined pattern"""
+    ny, nx = a.shape
+    if mask == "none":
+        return a
+    if mask == "bernoulli":
+        a[rng.random(a.shape) < 0.3] = undef
+    elif mask == "sparse":
+        a[rng.random(a.shape) < 0.02] = undef
+    elif mask == "nan":
+        a[rng.random(a.shape) < 0.05] = np.nan
+        a[rng.random(a.shape) < 0.05] = undef
+    elif mask == "blobs":
+        y, x = np.mgrid[0:ny, 0:nx]
+        for _ in range(4):
+            cx, cy = rng.uniform(0, nx), rng.uniform(0, ny)
+            r = rng.uniform(0.05, 0.25) * max(nx, ny)
+            a[(x - cx) ** 2 + (y - cy) ** 2 < r * r] = undef
+    elif mask == "edge":  # only row 0, column 0 and the last column: the wrap-around flag quirk
+        a[0, :: max(1, nx // 7)] = undef
+        a[:: max(1, ny // 5), 0] = undef
+        a[1:: max(1, ny // 3), nx - 1] = undef
+    elif mask == "corner":
+        a[0, 0] = undef
+    elif mask == "all":
+        a[:] = undef
+    else:
+        raise ValueError(mask)
+    return a
+
+
+# ----------------------------------------------------------------------------------------- case table
+# Each spec: list of argument descriptors, in API order.
+#   "nx", "ny", "undef", "flag", "out"
+#   ("in", kind)            input field of a FIELD_RANGES kind (masked by the case's mask)
+#   ("in!", kind)           input field that is never masked (map ratios, Coriolis)
+#   ("f", name, default)    float scalar, overridable by params[name]
+#   ("i", name, default)    int scalar
+#   ("s", name, default)    string
+#   ("members", kind)       ensemble member list + count (two C arguments)
+#   "flags_in"              per-member int32 flags
+#   ("limits", default)     float list + count (two C arguments)
+#   "inout"                 shapiro2_filter's `field`
+SPECS = {
+    "pleveltemp": ["nx", "ny", ("in", "tk"), ("f", "p", 500.0), ("s", "unit", "kelvin"), ("i", "compute", 3), "out", "flag", "undef"],
+    "plevelhum": ["nx", "ny", ("in", "tk"), ("in", "q"), ("f", "p", 850.0), ("s", "unit", "celsius"), ("i", "compute", 1), "out", "flag", "undef"],
+    "hleveltemp": ["nx", "ny", ("in", "tk"), ("in", "ps"), ("f", "alevel", 50.0), ("f", "blevel", 0.7), ("s", "unit", "kelvin"), ("i", "compute", 3),
+                   "out", "flag", "undef"],
+    "hlevelthe": ["nx", "ny", ("in", "tk"), ("in", "q"), ("in", "ps"), ("f", "alevel", 50.0), ("f", "blevel", 0.7), ("i", "compute", 1), "out", "flag",
+                  "undef"],
+    "hlevelhum": ["nx", "ny", ("in", "tk"), ("in", "q"), ("in", "ps"), ("f", "alevel", 50.0), ("f", "blevel", 0.7), ("s", "unit", "celsius"),
+                  ("i", "compute", 1), "out", "flag", "undef"],
+    "hlevelducting": ["nx", "ny", ("in", "tk"), ("in", "q"), ("in", "ps"), ("f", "alevel", 50.0), ("f", "blevel", 0.7), ("i", "compute", 1), "out",
+                      "flag", "undef"],
+    "hlevelpressure": ["nx", "ny", ("in", "ps"), ("f", "alevel", 50.0), ("f", "blevel", 0.7), "out", "flag", "undef"],
+    "aleveltemp": ["nx", "ny", ("in", "tk"), ("in", "p"), ("s", "unit", "kelvin"), ("i", "compute", 3), "out", "flag", "undef"],
+    "alevelthe": ["nx", "ny", ("in", "tk"), ("in", "q"), ("in", "p"), ("i", "compute", 1), "out", "flag", "undef"],
+    "alevelhum": ["nx", "ny", ("in", "tk"), ("in", "q"), ("in", "p"), ("s", "unit", "celsius"), ("i", "compute", 1), "out", "flag", "undef"],
+    "alevelducting": ["nx", "ny", ("in", "tk"), ("in", "q"), ("in", "p"), ("i", "compute", 1), "out", "flag", "undef"],
+    "ilevelgwind": ["nx", "ny", ("in", "z"), ("in!", "xm"), ("in!", "ym"), ("in!", "fc"), "out", "out", "flag", "undef"],
+    "relvort": ["nx", "ny", ("in", "wind"), ("in", "wind"), ("in!", "xm"), ("in!", "ym"), "out", "flag", "undef"],
+    "absvort": ["nx", "ny", ("in", "wind"), ("in", "wind"), ("in!", "xm"), ("in!", "ym"), ("in!", "fc"), "out", "flag", "undef"],
+    "divergence": ["nx", "ny", ("in", "wind"), ("in", "wind"), ("in!", "xm"), ("in!", "ym"), "out", "flag", "undef"],
+    "advection": ["nx", "ny", ("in", "tk"), ("in", "wind"), ("in", "wind"), ("in!", "xm"), ("in!", "ym"), ("f", "hours", 1.0), "out", "flag", "undef"],
+    "gradient": ["nx", "ny", ("in", "tk"), ("in!", "xm"), ("in!", "ym"), ("i", "compute", 1), "out", "flag", "undef"],
+    "shapiro2_filter": ["nx", "ny", ("inout", "tk"), "out", "flag", "undef"],
+    "windCooling": ["nx", "ny", ("in", "tk"), ("in", "wind"), ("in", "wind"), ("i", "compute", 1), "out", "flag", "undef"],
+    "thermalFrontParameter": ["nx", "ny", ("in", "tk"), ("in!", "xm"), ("in!", "ym"), "out", "flag", "undef"],
+    "momentumXcoordinate": ["nx", "ny", ("in", "wind"), ("in!", "xm"), ("in!", "fc0"), ("f", "fcoriolisMin", 5e-5), "out", "flag", "undef"],
+    "momentumYcoordinate": ["nx", "ny", ("in", "wind"), ("in!", "ym"), ("in!", "fc0"), ("f", "fcoriolisMin", 5e-5), "out", "flag", "undef"],
+    "jacobian": ["nx", "ny", ("in", "tk"), ("in", "z"), ("in!", "xm"), ("in!", "ym"), "out", "flag", "undef"],
+    "vesselIcingOverland": ["nx", "ny", ("in", "tc"), ("in", "sst"), ("in", "wind"), ("in", "wind"), ("in", "sal"), ("in", "aice"), "out", "flag",
+                            "undef"],
+    "vesselIcingMertins": ["nx", "ny", ("in", "tc"), ("in", "sst"), ("in", "wind"), ("in", "wind"), ("in", "sal"), ("in", "aice"), "out", "flag",
+                           "undef"],
+    "vesselIcingModStall": ["nx", "ny", ("in", "sal"), ("in", "wave"), ("in", "wind"), ("in", "wind"), ("in", "tc"), ("in", "rh01"), ("in", "sst"),
+                            ("in", "pmsl"), ("in", "pw"), ("in", "aice"), ("in", "depth"), ("f", "vs", 5.0), ("f", "alpha", 2.6), ("f", "zmin", 4.0),
+                            ("f", "zmax", 4.0), "out", "flag", "undef"],
+    "vesselIcingMincog": ["nx", "ny", ("in", "sal"), ("in", "wave"), ("in", "wind"), ("in", "wind"), ("in", "tc"), ("in", "rh01"), ("in", "sst"),
+                          ("in", "pmsl"), ("in", "pw"), ("in", "aice"), ("in", "depth"), ("f", "vs", 5.0), ("f", "alpha", 2.6), ("f", "zmin", 4.0),
+                          ("f", "zmax", 4.0), ("i", "alt", 1), "out", "flag", "undef"],
+    "fieldOPERfield": [("i", "compute", 1), "nx", "ny", ("in", "any"), ("in", "any"), "out", "flag", "undef"],
+    "meanValue": ["nx", "ny", ("members", "tk"), "flags_in", "out", "flag", "undef"],
+    "stddevValue": ["nx", "ny", ("members", "tk"), "flags_in", "out", "flag", "undef"],
+    "extremeValue": [("i", "compute", 1), "nx", "ny", ("members", "tk"), "out", "flag", "undef"],
+    "probability": [("i", "compute", 1), "nx", "ny", ("members", "tk"), "flags_in", ("limits", (262.0, 280.0)), "out", "flag", "undef"],
+}
+
+# operators whose device result may differ from the CPU by transcendental ulps (powf/expf/exp/pow/tanh);
+# everything else must be bit-identical.  Values are relative tolerances on defined points.
+TRANSCENDENTAL = {
+    "hleveltemp": 1e-5, "hlevelthe": 1e-5, "hlevelhum": 1e-5, "hlevelducting": 1e-5,
+    "aleveltemp": 1e-5, "alevelthe": 1e-5, "alevelhum": 1e-5, "alevelducting": 1e-5,
+    "windCooling": 1e-5, "vesselIcingModStall": 1e-5, "vesselIcingMincog": 1e-4,
+}
+
+
+class Case:
+    def __init__(self, name, args, out_idx, flag_idx, undef, params):
+        self.name, self.args, self.out_idx, self.flag_idx, self.undef, self.params = name, args, out_idx, flag_idx, undef, params
+
+    def __repr__(self):
+        return "Case(%s, %s)" % (self.name, self.params)
+
+
+def build(name, nx, ny, seed=0, undef=UNDEF, flag_in=SOME, mask="none", nmembers=5, member_flags=None, alias=False, **params):
+    """Build one case.  `params` override scalar defaults (compute=..., unit=..., p=...)."""
+    rng = np.random.default_rng(seed)
+    undef = np.float32(undef)
+    args, out_idx, flag_idx = [], [], None
+    fields_for_alias = []
+    for d in SPECS[name]:
+        if d == "nx":
+            args.append(nx)
+        elif d == "ny":
+            args.append(ny)
+        elif d == "undef":
+            args.append(float(undef))
+        elif d == "flag":
+            flag_idx = len(args)
+            args.append(np.array([flag_in], dtype=np.int32))
+        elif d == "out":
+            out_idx.append(len(args))
+            args.append(np.full((ny, nx), SENTINEL, dtype=np.float32))
+        elif d == "flags_in":
+            mf = member_flags if member_flags is not None else [flag_in] * nmembers
+            args.append(np.array(mf, dtype=np.int32))
+        elif d[0] in ("in", "in!", "inout"):
+            a = field(rng, d[1], nx, ny)
+            if d[0] != "in!":
+                apply_mask(rng, a, mask, undef)
+            fields_for_alias.append(len(args))
+            args.append(a)
+        elif d[0] in ("f", "i", "s"):
+            v = params.get(d[1], d[2])
+            args.append(v)
+        elif d[0] == "members":
+            base = field(rng, d[1], nx, ny)
+            members = []
+            for _ in range(nmembers):
+                m = (base + rng.standard_normal((ny, nx)).astype(np.float32) * np.float32(3.0)).astype(np.float32)
+                apply_mask(rng, m, mask, undef)
+                members.append(m)
+            args.append(members)
+            args.append(nmembers)
+        elif d[0] == "limits":
+            lim = list(params.get("limits", d[1]))
+            args.append(np.array(lim if lim else [0.0], dtype=np.float32))
+            args.append(len(lim))
+        else:
+            raise ValueError(d)
+    case = Case(name, args, out_idx, flag_idx, undef, dict(params, nx=nx, ny=ny, seed=seed, flag_in=flag_in, mask=mask))
+    if alias:  # output aliases the first input field (allowed for elementwise operators and shapiro2_filter)
+        case.alias = (fields_for_alias[0], out_idx[0])
+    return case
+
+
+def run(api, case, to_device=None):
+    """Call `<prefix><op>` on a private copy of the case.  `to_device(arr) -> tensor` moves field
+    arguments to the GPU first (device-pointer path); outputs come back as numpy arrays."""
+    args = copy.deepcopy(case.args)
+    alias = getattr(case, "alias", None)
+    if alias:
+        args[alias[1]] = args[alias[0]]
+    moved = {}
+    if to_device is not None:
+        for k, a in enumerate(args):
+            if isinstance(a, np.ndarray) and a.dtype == np.float32 and a.ndim == 2:
+                if alias and k == alias[1]:
+                    continue
+                moved[k] = to_device(a)
+            elif isinstance(a, list):
+                moved[k] = [to_device(m) for m in a]
+        if alias:
+            moved[alias[1]] = moved[alias[0]]
+    call_args = [moved.get(k, a) for k, a in enumerate(args)]
+    ret = api.call(case.name, *call_args)
+    outs = []
+    for k in case.out_idx:
+        o = call_args[k]
+        outs.append(o.cpu().numpy() if hasattr(o, "cpu") else o)
+    return ret, outs, int(args[case.flag_idx][0])
+
+
+def undefined_mask(a, undef):
+    return (a == undef) | np.isnan(a)
+
+
+def compare(case, got, want, rtol=0.0):
+    """Returns a list of human-readable mismatches (empty = parity).  `got`/`want` = (ret, outs, flag).
+    The undefined mask and the flag must be bit-exact; values are compared bit-for-bit when rtol == 0,
+    otherwise by relative error on the defined points."""
+    problems = []
+    if got[0] != want[0]:
+        problems.append("return value %r != %r" % (got[0], want[0]))
+    if got[2] != want[2]:
+        problems.append("fDefined %r != %r" % (got[2], want[2]))
+    for k, (g, w) in enumerate(zip(got[1], want[1])):
+        mg, mw = undefined_mask(g, case.undef), undefined_mask(w, case.undef)
+        if not np.array_equal(mg, mw):
+            problems.append("output %d: undefined mask differs at %d points" % (k, int((mg != mw).sum())))
+            continue
+        if rtol == 0.0:
+            same = (g.view(np.uint32) == w.view(np.uint32)) | (np.isnan(g) & np.isnan(w)) | (g == w)
+            if not same.all():
+                bad = np.argwhere(~same)
+                y, x = bad[0]
+                problems.append("output %d: %d points differ bitwise, first at (y=%d,x=%d): %r vs %r" % (k, len(bad), y, x, g[y, x], w[y, x]))
+        else:
+            d = ~mw
+            with np.errstate(all="ignore"):
+                err = np.abs(g[d].astype(np.float64) - w[d].astype(np.float64))
+                scale = np.maximum(np.abs(w[d].astype(np.float64)), 1e-30)
+                rel = np.where(err == 0, 0.0, err / scale)
+                # both infinite with the same sign counts as equal
+                rel = np.where(np.isinf(g[d]) & (g[d] == w[d]), 0.0, rel)
+            if rel.size and np.nanmax(rel) > rtol:
+                problems.append("output %d: max relative error %.3g > %.1g" % (k, float(np.nanmax(rel)), rtol))
+    return problems
