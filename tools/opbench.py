@@ -1,0 +1,188 @@
+#!/usr/bin/env python
+"""Per-operator device-resident throughput against the HBM roofline (run on a B200 via gpurun).
+
+    python tools/opbench.py [--ops relvort,advection,...] [--reps 10] [--json out.json]
+
+Every operator runs on a batch sized so that one launch streams >= ~1 GB (far beyond the 126 MB
+L2); inputs alternate between two batches; time = CUDA events on the launching stream around
+`reps` deferred launches.  Algorithmic bytes per point follow SURVEY.md 8(a) ("batched" figures:
+grid-constant map arrays are counted once per batch, i.e. ~0 per point).
+"""
+import argparse
+import importlib
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+MEPS = (949, 1069)
+ECMWF = (3600, 1801)
+UNDEF = 1.0e35
+
+
+def main():
+    import torch
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--ops", default="")
+    ap.add_argument("--reps", type=int, default=10)
+    ap.add_argument("--json", default="")
+    ap.add_argument("--mask", type=float, default=0.0, help="fraction of undefined points in every maskable input (flag SOME_DEFINED)")
+    args = ap.parse_args()
+    pkg = importlib.import_module("mi-fieldcalc_b200")
+    gpu = pkg.load()
+    dev = torch.device("cuda", 0)
+    peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"] if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
+    stream = torch.cuda.current_stream()
+    gpu.set_stream(stream.cuda_stream, True)
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(1234)
+
+    def rnd(shape, lo, hi, maskable=True):
+        a = torch.rand(shape, device=dev, generator=gen, dtype=torch.float32) * (hi - lo) + lo
+        if maskable and args.mask > 0:
+            a[torch.rand(shape, device=dev, generator=gen) < args.mask] = UNDEF
+        return a
+
+    flag_in = 2 if args.mask > 0 else 0
+
+    def batch(grid, nf):
+        nx, ny = grid
+        return (nf, ny, nx)
+
+    # name -> (grid, nfields, bytes/pt, builder(nf, grid) -> (callname, args-with-out-and-flags))
+    def mk_stencil(name, nin, extra=()):
+        def build(grid, nf):
+            nx, ny = grid
+            fields = [rnd(batch(grid, nf), 250, 300) if k == 0 else rnd(batch(grid, nf), -30, 30) for k in range(nin)]
+            xm = rnd((ny, nx), 1.9e-4, 2.1e-4, False)
+            ym = rnd((ny, nx), 1.9e-4, 2.1e-4, False)
+            out = torch.empty(batch(grid, nf), device=dev)
+            flags = np.full(nf, flag_in, np.int32)
+            return [nx, ny, nf] + fields + [xm, ym] + list(extra) + [out, flags, UNDEF]
+        return build
+
+    def b_absvort(grid, nf):
+        nx, ny = grid
+        a = mk_stencil("absvort", 2)(grid, nf)
+        fc = rnd((ny, nx), 1.1e-4, 1.4e-4, False)
+        return a[:7] + [fc] + a[7:]
+
+    def b_gwind(grid, nf):
+        nx, ny = grid
+        m = rnd(batch(grid, nf), 4800, 5900)
+        xm, ym, fc = rnd((ny, nx), 1.9e-4, 2.1e-4, False), rnd((ny, nx), 1.9e-4, 2.1e-4, False), rnd((ny, nx), 1.1e-4, 1.4e-4, False)
+        return [nx, ny, nf, m, xm, ym, fc, torch.empty(batch(grid, nf), device=dev), torch.empty(batch(grid, nf), device=dev), np.full(nf, flag_in, np.int32), UNDEF]
+
+    def b_shapiro(grid, nf):
+        nx, ny = grid
+        return [nx, ny, nf, rnd(batch(grid, nf), 250, 300), torch.empty(batch(grid, nf), device=dev), np.full(nf, flag_in, np.int32), UNDEF]
+
+    def b_ew(kinds, scalars_before_out=(), lead=()):
+        def build(grid, nf):
+            nx, ny = grid
+            rng = {"t": (215, 305), "q": (1e-6, 2e-2), "p": (300, 1040), "w": (-30, 30), "any": (-50, 50), "tc": (-25, 5), "sst": (-1, 8), "sal": (30, 35),
+                   "aice": (0, 0.6), "wave": (0, 8), "rh01": (0.4, 1), "pmsl": (960, 1030), "pw": (3, 12), "depth": (20, 3000)}
+            fields = [rnd(batch(grid, nf), *rng[k]) for k in kinds]
+            return list(lead) + [nx, ny, nf] + fields + list(scalars_before_out) + [torch.empty(batch(grid, nf), device=dev), np.full(nf, flag_in, np.int32), UNDEF]
+        return build
+
+    def b_pleveltemp(compute):
+        def build(grid, nf):
+            nx, ny = grid
+            return [nx, ny, nf, rnd(batch(grid, nf), 215, 305), np.full(nf, 500.0, np.float32), "kelvin", compute, torch.empty(batch(grid, nf), device=dev),
+                    np.full(nf, flag_in, np.int32), UNDEF]
+        return build
+
+    def b_plevelhum(compute):
+        def build(grid, nf):
+            nx, ny = grid
+            return [nx, ny, nf, rnd(batch(grid, nf), 215, 305), rnd(batch(grid, nf), 1e-6, 2e-2), np.full(nf, 850.0, np.float32), "celsius", compute,
+                    torch.empty(batch(grid, nf), device=dev), np.full(nf, flag_in, np.int32), UNDEF]
+        return build
+
+    def b_ens(name, M=30, lead=(), limits=None):
+        def build(grid, nt):
+            nx, ny = grid
+            members = [rnd(batch(grid, nt), 250, 300) for _ in range(M)]
+            a = list(lead) + [nx, ny, nt, members, M]
+            if name != "extremeValue":
+                a.append(np.full(nt * M, flag_in, np.int32))
+            if limits is not None:
+                a += [np.array(limits, np.float32), len(limits)]
+            return a + [torch.empty(batch(grid, nt), device=dev), np.full(nt, flag_in, np.int32), UNDEF]
+        return build
+
+    icing6 = ["tc", "sst", "w", "w", "sal", "aice"]
+    icing11 = ["sal", "wave", "w", "w", "tc", "rh01", "sst", "pmsl", "pw", "aice", "depth"]
+    OPS = {
+        # stencils (batched B/pt: maps amortised)
+        "relvort": ("relvort_batched", MEPS, 64, 12, mk_stencil("relvort", 2)),
+        "absvort": ("absvort_batched", MEPS, 64, 12, b_absvort),
+        "divergence": ("divergence_batched", MEPS, 64, 12, mk_stencil("divergence", 2)),
+        "advection": ("advection_batched", ECMWF, 12, 16, mk_stencil("advection", 3, extra=(1.0,))),
+        "gradient_c3": ("gradient_batched", ECMWF, 16, 8, mk_stencil("gradient", 1, extra=(3,))),
+        "jacobian": ("jacobian_batched", MEPS, 64, 12, mk_stencil("jacobian", 2)),
+        "ilevelgwind": ("ilevelgwind_batched", MEPS, 64, 12, b_gwind),
+        "thermalFrontParameter": ("thermalFrontParameter_batched", ECMWF, 16, 8, mk_stencil("tfp", 1)),
+        "shapiro2_filter": ("shapiro2_filter_batched", ECMWF, 16, 8, b_shapiro),
+        # elementwise
+        "pleveltemp_c3": ("pleveltemp_batched", MEPS, 128, 8, b_pleveltemp(3)),
+        "pleveltemp_c4": ("pleveltemp_batched", MEPS, 128, 8, b_pleveltemp(4)),
+        "plevelhum_c1": ("plevelhum_batched", MEPS, 96, 12, b_plevelhum(1)),
+        "plevelhum_c7": ("plevelhum_batched", MEPS, 96, 12, b_plevelhum(7)),
+        "aleveltemp_c3": ("aleveltemp_batched", MEPS, 96, 12, b_ew(["t", "p"], ("kelvin", 3))),
+        "alevelhum_c1": ("alevelhum_batched", MEPS, 65, 16, b_ew(["t", "q", "p"], ("celsius", 1))),
+        "alevelhum_c5": ("alevelhum_batched", MEPS, 65, 16, b_ew(["t", "q", "p"], ("celsius", 5))),
+        "alevelthe_c1": ("alevelthe_batched", MEPS, 65, 16, b_ew(["t", "q", "p"], (1,))),
+        "alevelducting_c1": ("alevelducting_batched", MEPS, 65, 16, b_ew(["t", "q", "p"], (1,))),
+        "windCooling": ("windCooling_batched", MEPS, 65, 16, b_ew(["t", "w", "w"], (1,))),
+        "fieldOPERfield_add": ("fieldOPERfield_batched", MEPS, 96, 12, b_ew(["any", "any"], (), lead=(1,))),
+        "fieldOPERfield_div": ("fieldOPERfield_batched", MEPS, 96, 12, b_ew(["any", "any"], (), lead=(4,))),
+        "vesselIcingOverland": ("vesselIcingOverland_batched", MEPS, 40, 28, b_ew(icing6)),
+        "vesselIcingMertins": ("vesselIcingMertins_batched", MEPS, 40, 28, b_ew(icing6)),
+        "vesselIcingModStall": ("vesselIcingModStall_batched", MEPS, 4, 48, b_ew(icing11, (5.0, 2.6, 4.0, 4.0))),
+        "vesselIcingMincog": ("vesselIcingMincog_batched", MEPS, 4, 48, b_ew(icing11, (5.0, 2.6, 4.0, 4.0, 1))),
+        # ensemble, 30 members: bytes per OUTPUT point = 4*(M+1)
+        "meanValue": ("meanValue_batched", MEPS, 8, 124, b_ens("meanValue")),
+        "stddevValue": ("stddevValue_batched", MEPS, 8, 124, b_ens("stddevValue")),
+        "extremeValue_max": ("extremeValue_batched", MEPS, 8, 124, b_ens("extremeValue", lead=(1,))),
+        "probability_above": ("probability_batched", MEPS, 8, 124, b_ens("probability", lead=(1,), limits=[275.0])),
+    }
+    wanted = [o for o in args.ops.split(",") if o] or list(OPS)
+    results = []
+    print("%-24s %-10s %7s %9s %9s %8s %6s" % ("operator", "grid", "fields", "ms", "Gpt/s", "GB/s", "frac"))
+    for name in wanted:
+        call, grid, nf, bpp, build = OPS[name]
+        sets = [build(grid, nf), build(grid, nf)]
+        pts = grid[0] * grid[1] * nf
+        for s in sets:  # warm-up (also checks the call is accepted)
+            r = gpu.call(call, *s)
+            assert r == 1, (name, r)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        gpu.begin_deferred()
+        e0.record(stream)
+        for k in range(args.reps):
+            gpu.call(call, *sets[k % 2])
+        e1.record(stream)
+        gpu.end_deferred()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / args.reps
+        gbs = bpp * pts / (ms * 1e-3) / 1e9
+        res = {"operator": name, "grid": list(grid), "fields": nf, "ms": ms, "gpts": pts / (ms * 1e-3) / 1e9, "gbs": gbs, "frac": gbs / peak, "bytes_per_point": bpp,
+               "mask": args.mask}
+        results.append(res)
+        print("%-24s %-10s %7d %9.4f %9.2f %8.1f %6.3f" % (name, "%dx%d" % grid, nf, ms, res["gpts"], gbs, res["frac"]))
+        del sets
+        torch.cuda.empty_cache()
+    if args.json:
+        json.dump({"peak_gbs": peak, "results": results}, open(args.json, "w"), indent=1)
+
+
+if __name__ == "__main__":
+    main()
