@@ -41,6 +41,9 @@ WORKLOAD = "meps65_alevel_chain"
 # (12 + 16 + 16 + 16), fused = t, q, p read once + four outputs
 BYTES_UNFUSED = {"aleveltemp": 12, "alevelhum_rh": 16, "alevelhum_td": 16, "alevelthe": 16}
 BYTES_FUSED = 28
+# dram__bytes_read.sum + dram__bytes_write.sum of one fused-chain launch (65 levels), from the ncu --set full
+# capture committed under profiles/ (None until captured)
+TRAFFIC_NCU = None
 
 
 def peaks():
@@ -263,65 +266,72 @@ def run_product(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- device-resident timing: K steps, CUDA events on the launching stream
+    # ---- device-resident timing: K steps, CUDA events on the launching stream.
+    # One step = ONE launch of the fused chain kernel (fcb200_alevel_chain_batched): t, q, p read once,
+    # theta / RH / Td / theta_e written -- the same values, masks and flags as the four reference calls.
+    fin = np.zeros(nlev, np.int32)            # ALL_DEFINED: what the reference call sequence would be given
+    fout = np.full((4, nlev), -1, np.int32)
+
+    def fused_step(t, q, p):
+        gpu.call("alevel_chain_batched", NX, NY, nlev, t, q, p, "celsius", outs[0], outs[1], outs[2], outs[3], fin, fout, UNDEF)
+
     gpu.begin_deferred()
     for w in range(args.warmup):
-        chain_calls(gpu, *sets[w % 2], outs, flags)
+        fused_step(*sets[w % 2])
     gpu.end_deferred()
     barrier()
     sampler = ClockSampler(local) if rank == 0 else None
-    n_ev = 5
-    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(n_ev)] for _ in range(args.steps)]
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(2)] for _ in range(args.steps)]
     launches0 = gpu.launch_count()
     wall0 = time.time()
     gpu.begin_deferred()
     for k in range(args.steps):
-        t, q, p = sets[k % 2]
-        flags[:] = 0
         evs[k][0].record(stream)
-        gpu.call("aleveltemp_batched", NX, NY, nlev, t, p, "kelvin", 3, outs[0], flags[0], UNDEF)
+        fused_step(*sets[k % 2])
         evs[k][1].record(stream)
-        gpu.call("alevelhum_batched", NX, NY, nlev, t, q, p, "celsius", 1, outs[1], flags[1], UNDEF)
-        evs[k][2].record(stream)
-        gpu.call("alevelhum_batched", NX, NY, nlev, t, q, p, "celsius", 5, outs[2], flags[2], UNDEF)
-        evs[k][3].record(stream)
-        gpu.call("alevelthe_batched", NX, NY, nlev, t, q, p, 1, outs[3], flags[3], UNDEF)
-        evs[k][4].record(stream)
     gpu.end_deferred()
     barrier()
     wall1 = time.time()
     launches = gpu.launch_count() - launches0
-    total_ms = evs[0][0].elapsed_time(evs[-1][4])
+    total_ms = evs[0][0].elapsed_time(evs[-1][1])
     if world > 1:
         tt = torch.tensor([total_ms], device=dev)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         total_ms = float(tt.item())
-    assert (flags == 0).all(), "synthetic input is fully defined: every output flag must be ALL_DEFINED"
+    assert (fout == 0).all(), "synthetic input is fully defined: every output flag must be ALL_DEFINED"
     clocks = sampler.stop(wall0, wall1) if sampler else None
-    names = ["aleveltemp", "alevelhum_rh", "alevelhum_td", "alevelthe"]
-    kern_ms = {nme: float(np.mean([evs[k][i].elapsed_time(evs[k][i + 1]) for k in range(args.steps)])) for i, nme in enumerate(names)}
+    kern_ms = float(np.mean([evs[k][0].elapsed_time(evs[k][1]) for k in range(args.steps)]))
     points_per_step = nlev * N
     value = world * points_per_step * args.steps / (total_ms * 1e-3)
+    achieved = BYTES_FUSED * points_per_step / (kern_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": "ew_kernel<AlevelChainOp, 4> (fused chain)", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": TRAFFIC_NCU, "peak_source": peak_src, "algorithmic_bytes_per_point": BYTES_FUSED,
+                "kernel_ms": kern_ms, "note": "issue-bound, not HBM-bound: ~155 instructions per point (ncu, profiles/)"}
 
-    # roofline of the dominant kernel of the step
-    dom = max(kern_ms, key=kern_ms.get)
-    achieved = BYTES_UNFUSED[dom] * points_per_step / (kern_ms[dom] * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                "peak_source": peak_src, "algorithmic_bytes_per_point": BYTES_UNFUSED[dom],
-                "all_kernels": {nme: {"ms": kern_ms[nme], "GB/s": BYTES_UNFUSED[nme] * points_per_step / (kern_ms[nme] * 1e-3) / 1e9} for nme in names}}
+    # for the record: the same step as the UNFUSED reference call sequence (four batched launches, 60 B/point)
+    gpu.begin_deferred()
+    chain_calls(gpu, *sets[0], outs, flags)
+    gpu.end_deferred()
+    barrier()
+    u0, u1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    gpu.begin_deferred()
+    u0.record(stream)
+    for k in range(3):
+        chain_calls(gpu, *sets[k % 2], outs, flags)
+    u1.record(stream)
+    gpu.end_deferred()
+    barrier()
+    unfused_ms = u0.elapsed_time(u1) / 3
 
     # ---- end to end: host (pinned) buffers through the C-ABI, copies inside the timed region
     e2e_lev = min(nlev, args.e2e_levels)
     hin = [torch.from_numpy(a[:e2e_lev].copy()).pin_memory() for a in synth_level_set(np.random.default_rng(3000 + rank), e2e_lev)]
     hout = [torch.empty((e2e_lev, NY, NX), dtype=torch.float32).pin_memory() for _ in range(4)]
-    hflags = np.zeros((4, e2e_lev), np.int32)
+    hfin = np.zeros(e2e_lev, np.int32)
+    hfout = np.full((4, e2e_lev), -1, np.int32)
 
     def e2e_step():
-        hflags[:] = 0
-        gpu.call("aleveltemp_batched", NX, NY, e2e_lev, hin[0], hin[2], "kelvin", 3, hout[0], hflags[0], UNDEF)
-        gpu.call("alevelhum_batched", NX, NY, e2e_lev, hin[0], hin[1], hin[2], "celsius", 1, hout[1], hflags[1], UNDEF)
-        gpu.call("alevelhum_batched", NX, NY, e2e_lev, hin[0], hin[1], hin[2], "celsius", 5, hout[2], hflags[2], UNDEF)
-        gpu.call("alevelthe_batched", NX, NY, e2e_lev, hin[0], hin[1], hin[2], 1, hout[3], hflags[3], UNDEF)
+        gpu.call("alevel_chain_batched", NX, NY, e2e_lev, hin[0], hin[1], hin[2], "celsius", hout[0], hout[1], hout[2], hout[3], hfin, hfout, UNDEF)
 
     for _ in range(min(3, max(1, args.warmup))):
         e2e_step()
@@ -335,10 +345,11 @@ def run_product(args):
         tt = torch.tensor([e2e_dt], device=dev)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         e2e_dt = float(tt.item())
+    assert (hfout == 0).all()
     e2e_value = world * e2e_lev * N * args.e2e_steps / e2e_dt
-    # bytes actually copied per step by the four calls: inputs (2 + 3 + 3 + 3 arrays) and 4 outputs
-    e2e = {"value": e2e_value, "unit": "grid points/s", "h2d_bytes_per_step": 11 * 4 * e2e_lev * N, "d2h_bytes_per_step": 4 * 4 * e2e_lev * N,
-           "levels_per_step": e2e_lev, "api": "4 x fcb200_*_batched with pinned host buffers"}
+    e2e = {"value": e2e_value, "unit": "grid points/s", "h2d_bytes_per_step": 3 * 4 * e2e_lev * N, "d2h_bytes_per_step": 4 * 4 * e2e_lev * N,
+           "levels_per_step": e2e_lev, "ms_per_step": 1e3 * e2e_dt / args.e2e_steps,
+           "api": "fcb200_alevel_chain_batched with pinned host buffers (chunked, copy-in / kernel / copy-out pipelined over 3 streams)"}
 
     cpu = cpu_baseline_sample() if (rank == 0 and world == 1 and not args.no_cpu) else None
 
@@ -347,7 +358,8 @@ def run_product(args):
             "metric": METRIC, "value": value, "unit": "grid points/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "grid": [NX, NY], "levels_per_step": nlev, "points_per_step_per_gpu": points_per_step,
-                       "chain": "aleveltemp c3 + alevelhum c1 + alevelhum c5 + alevelthe c1 (unfused: one batched launch per reference call)",
+                       "chain": "aleveltemp c3 + alevelhum c1 + alevelhum c5 + alevelthe c1, fused into one launch per step (t, q, p read once)",
+                       "unfused_ms_per_step": unfused_ms,
                        "cache": "inputs larger than L2 (>= 790 MB streamed per step, two alternating input sets)", "sharding": "by field batch, no collective"},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
         }
@@ -364,7 +376,7 @@ def main():
     ap.add_argument("--impl", default="product", choices=["product", "reference"])
     ap.add_argument("--levels", type=int, default=NLEV, help="levels per step (default: the full 65)")
     ap.add_argument("--e2e-levels", type=int, default=NLEV)
-    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--ref-levels", type=int, default=4, help="levels per step of the bounded CPU sample (--impl reference)")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()

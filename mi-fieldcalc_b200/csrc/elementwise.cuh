@@ -5,10 +5,17 @@
 // of the same shape.
 //
 // Layout: a batch is `nfields` dense fields of `n = nx*ny` floats, field k at base + k*stride
-// (stride = n, or 0 for an array shared by the whole batch).  One CTA works on one chunk of one
-// field, so the per-field metadata is CTA-uniform and the undefined counter needs one atomic per
-// CTA.  Every thread first issues ALL its loads (UNROLL x NIN vectors of 16 B), then computes, then
-// stores: the kernels are HBM-bound, bytes in flight are what matters.
+// (stride = n, or 0 for an array shared by the whole batch).  The work is cut into items of
+// EW_THREADS * U * W consecutive points of one field; the grid is PERSISTENT (a multiple of the SM
+// count) and the items are dealt round-robin to the CTAs, so that
+//   * the saturation / pow tables are staged in shared memory once per CTA, not once per item;
+//   * the per-field metadata is CTA-uniform per item and the ALL_DEFINED fast path (no undefined
+//     tests at all, exactly like the reference's `allDefined` short-circuit, FC.h:47-98) is chosen by
+//     a uniform branch into code specialised at compile time;
+//   * undefined points are counted in registers and flushed with one warp reduction + one atomic
+//     per warp only when the CTA moves on to another field -- no block barriers in the loop.
+// Every thread first issues ALL its loads (U x NIN vectors of 16 B), then computes, then stores:
+// the kernels are HBM- or issue-bound, never latency-bound.
 //
 // Vector path (W = 4): fields of a batch are only 4-byte aligned in general (n = 949*1069 is odd),
 // so every field is peeled: `head` scalar points up to the first 16-byte boundary, float4 groups,
@@ -27,45 +34,42 @@ struct EwArgs
   const float* in[NIN];
   long long in_stride[NIN];
   float* out[NOUT];
-  long long n;  // points per field
+  long long n;      // points per field
+  long long items;  // nfields * chunks
   int nfields;
-  int chunks;   // CTAs per field
-  int align0;   // (address of field 0, element 0) / 4 mod 4 -- identical for every array (W = 4 only)
+  int chunks;       // items per field
+  int align0;       // (address of field 0, element 0) / 4 mod 4 -- identical for every array (W = 4 only)
   int nx;
   float undef;
   const FieldMeta* meta;
-  unsigned long long* counters; // one per field, or nullptr when the operator never counts
+  unsigned long long* counters; // Op::NCOUNT per field, or nullptr when the operator never counts
 };
 
 struct PointCtx
 {
   const dev::EwtTable& tab;
+  const dev::PowTable& pw;
   FieldMeta m;
   float undef;
   int nx;
 };
 
 // An operator type provides:
-//   static constexpr int NIN, NOUT, UNROLL;  static constexpr bool USES_EWT, COUNTS;
-//   __device__ void point(const float* in, float* out, const PointCtx& c, long long idx, unsigned& nundef) const;
+//   static constexpr int NIN, NOUT, UNROLL, NCOUNT, MIN_BLOCKS;  static constexpr bool USES_EWT, USES_POW;
+//   static constexpr bool HEAVY;   // hundreds of instructions per point: one CTA per item, hardware load balancing
+//   (MIN_BLOCKS = CTAs per SM the register allocation must allow)
+//   template <bool ALL>
+//   __device__ void point(const float* in, float* out, const PointCtx& c, long long idx, unsigned* nundef) const;
 // `in`/`out` hold the NIN inputs / NOUT outputs of ONE grid point, `idx` is the point's flat index
-// inside its field.
+// inside its field, `nundef` are the thread's NCOUNT private undefined-point counts (field k's
+// counters live at counters[k*NCOUNT ...]).  ALL = the field's input flag is ALL_DEFINED: the
+// operator must then skip every is_defined test (NaN / undef flow through the arithmetic).
 
-template <class Op, int W>
-__global__ void __launch_bounds__(EW_THREADS) ew_kernel(const Op op, const EwArgs<Op::NIN, Op::NOUT> a)
+template <class Op, int W, bool ALL>
+__device__ __forceinline__ void ew_item(const Op& op, const EwArgs<Op::NIN, Op::NOUT>& a, const PointCtx& c, int field, int chunk, unsigned* nundef)
 {
   constexpr int NIN = Op::NIN, NOUT = Op::NOUT;
   constexpr int U = (W == 4) ? Op::UNROLL : Op::UNROLL * 2;
-
-  __shared__ dev::EwtTable tab;
-  if (Op::USES_EWT) {
-    tab.load();
-    __syncthreads();
-  }
-
-  const int field = blockIdx.x / a.chunks;
-  const int chunk = blockIdx.x - field * a.chunks;
-  const PointCtx c{tab, a.meta[field], a.undef, a.nx};
 
   const float* in[NIN];
   float* out[NOUT];
@@ -79,7 +83,6 @@ __global__ void __launch_bounds__(EW_THREADS) ew_kernel(const Op op, const EwArg
   const long long n = a.n;
   const int head = (W == 4) ? ((4 - ((a.align0 + (int)(((long long)field * n) & 3)) & 3)) & 3) : 0;
   const long long groups = (n - head) / W;
-  unsigned nundef = 0;
 
   // ---- body: all loads first, then compute + store
   float v[U][NIN][W];
@@ -113,7 +116,7 @@ __global__ void __launch_bounds__(EW_THREADS) ew_kernel(const Op op, const EwArg
 #pragma unroll
         for (int k = 0; k < NIN; ++k)
           pin[k] = v[u][k][w];
-        op.point(pin, pout, c, head + g * W + w, nundef);
+        op.template point<ALL>(pin, pout, c, head + g * W + w, nundef);
 #pragma unroll
         for (int k = 0; k < NOUT; ++k)
           r[k][w] = pout[k];
@@ -128,7 +131,7 @@ __global__ void __launch_bounds__(EW_THREADS) ew_kernel(const Op op, const EwArg
     }
   }
 
-  // ---- peel: < 4 head points and < 4 tail points of the field, done by its first CTA
+  // ---- peel: < 4 head points and < 4 tail points of the field, done with its first item
   if (W == 4 && chunk == 0) {
     const long long tail0 = head + groups * 4;
     const int ntail = (int)(n - tail0);
@@ -142,18 +145,100 @@ __global__ void __launch_bounds__(EW_THREADS) ew_kernel(const Op op, const EwArg
 #pragma unroll
       for (int k = 0; k < NIN; ++k)
         pin[k] = in[k][idx];
-      op.point(pin, pout, c, idx, nundef);
+      op.template point<ALL>(pin, pout, c, idx, nundef);
 #pragma unroll
       for (int k = 0; k < NOUT; ++k)
         out[k][idx] = pout[k];
     }
   }
-
-  if (Op::COUNTS)
-    dev::block_add_counter(nundef, a.counters + field);
 }
 
-// Host side: pick the vector width, size the grid, launch.  `in`/`out` are DEVICE pointers.
+template <int NCOUNT>
+__device__ __forceinline__ void ew_flush(unsigned* nundef, unsigned long long* counters, int field)
+{
+#pragma unroll
+  for (int k = 0; k < NCOUNT; ++k) {
+    const unsigned total = __reduce_add_sync(0xffffffffu, nundef[k]);
+    if ((threadIdx.x & 31) == 0 && total)
+      atomicAdd(counters + (long long)field * NCOUNT + k, (unsigned long long)total);
+    nundef[k] = 0;
+  }
+}
+
+template <class Op, int W>
+__global__ void __launch_bounds__(EW_THREADS, Op::MIN_BLOCKS) ew_kernel(const Op op, const EwArgs<Op::NIN, Op::NOUT> a)
+{
+  __shared__ dev::EwtTable tab;
+  __shared__ dev::PowTable pw;
+  if (Op::USES_EWT)
+    tab.load();
+  if (Op::USES_POW)
+    pw.load();
+  if (Op::USES_EWT || Op::USES_POW)
+    __syncthreads();
+
+  // Items are dealt round-robin: at any moment the resident CTAs stream one compact window of the
+  // batch (good DRAM page locality), exactly like a non-persistent grid would.  (field, chunk) are
+  // advanced incrementally -- no division in the loop -- and the next item's metadata is fetched
+  // before the current item is processed, so its latency is hidden.
+  constexpr int NC = Op::NCOUNT > 0 ? Op::NCOUNT : 1;
+  unsigned nundef[NC] = {};
+  const unsigned items = (unsigned)a.items, grid = gridDim.x, chunks = (unsigned)a.chunks;
+  const unsigned step_f = grid / chunks, step_c = grid - step_f * chunks;
+  unsigned item = blockIdx.x;
+  unsigned field = item / chunks, chunk = item - field * chunks;
+  FieldMeta m = a.meta[field < (unsigned)a.nfields ? field : 0];
+  while (item < items) {
+    const unsigned nitem = item + grid;
+    unsigned nfield = field + step_f, nchunk = chunk + step_c;
+    if (nchunk >= chunks) {
+      nchunk -= chunks;
+      nfield += 1;
+    }
+    FieldMeta mn = m;
+    if (nitem < items && nfield != field)
+      mn = a.meta[nfield];
+    const PointCtx c{tab, pw, m, a.undef, a.nx};
+    if (m.all == 1)
+      ew_item<Op, W, true>(op, a, c, (int)field, (int)chunk, nundef);
+    else
+      ew_item<Op, W, false>(op, a, c, (int)field, (int)chunk, nundef);
+    if (Op::NCOUNT > 0 && (nfield != field || nitem >= items))
+      ew_flush<Op::NCOUNT>(nundef, a.counters, (int)field);
+    item = nitem;
+    field = nfield;
+    chunk = nchunk;
+    m = mn;
+  }
+}
+
+// One CTA per item: used for operators without shared-memory tables (pure streaming: every register
+// goes to loads in flight) and for compute-heavy ones (the hardware scheduler balances the load).
+template <class Op, int W>
+__global__ void __launch_bounds__(EW_THREADS, Op::MIN_BLOCKS) ew_kernel_once(const Op op, const EwArgs<Op::NIN, Op::NOUT> a)
+{
+  __shared__ dev::EwtTable tab;
+  __shared__ dev::PowTable pw;
+  if (Op::USES_EWT)
+    tab.load();
+  if (Op::USES_POW)
+    pw.load();
+  if (Op::USES_EWT || Op::USES_POW)
+    __syncthreads();
+  constexpr int NC = Op::NCOUNT > 0 ? Op::NCOUNT : 1;
+  unsigned nundef[NC] = {};
+  const unsigned chunks = (unsigned)a.chunks;
+  const unsigned field = blockIdx.x / chunks, chunk = blockIdx.x - field * chunks;
+  const PointCtx c{tab, pw, a.meta[field], a.undef, a.nx};
+  if (c.m.all == 1)
+    ew_item<Op, W, true>(op, a, c, (int)field, (int)chunk, nundef);
+  else
+    ew_item<Op, W, false>(op, a, c, (int)field, (int)chunk, nundef);
+  if (Op::NCOUNT > 0)
+    ew_flush<Op::NCOUNT>(nundef, a.counters, (int)field);
+}
+
+// Host side: pick the vector width, size the persistent grid, launch.  `in`/`out` are DEVICE pointers.
 template <class Op>
 bool launch_elementwise(Call& call, const Op& op, const float* const* in, const long long* in_stride, float* const* out, long long n, int nfields,
                         int nx, float undef, const FieldMeta* meta, unsigned long long* counters)
@@ -184,13 +269,38 @@ bool launch_elementwise(Call& call, const Op& op, const float* const* in, const 
   a.counters = counters;
   const int width = vec ? 4 : 1;
   const int unroll = vec ? Op::UNROLL : Op::UNROLL * 2;
-  const long long per_cta = (long long)EW_THREADS * unroll * width;
-  a.chunks = (int)((n + per_cta - 1) / per_cta);
-  const long long grid = (long long)a.chunks * nfields;
-  if (grid <= 0 || grid > 0x7fffffffLL) {
-    set_error("fcb200: batch too large for one launch (%lld CTAs)", grid);
+  const long long per_item = (long long)EW_THREADS * unroll * width;
+  a.chunks = (int)((n + per_item - 1) / per_item);
+  a.items = (long long)a.chunks * nfields;
+
+  if (a.items > 0x7fffffffLL) {
+    set_error("fcb200: batch too large for one launch (%lld work items)", a.items);
     return false;
   }
+  // Operators that stage tables in shared memory run a persistent grid (as many CTAs as stay
+  // resident: occupancy x SM count) so that the staging is paid once per CTA; pure streaming and
+  // compute-heavy operators get one CTA per item and leave load balancing to the hardware scheduler.
+  const bool persistent = (Op::USES_EWT || Op::USES_POW) && !Op::HEAVY;
+  if (!persistent) {
+    if (vec)
+      ew_kernel_once<Op, 4><<<(unsigned)a.items, EW_THREADS, 0, call.stream()>>>(op, a);
+    else
+      ew_kernel_once<Op, 1><<<(unsigned)a.items, EW_THREADS, 0, call.stream()>>>(op, a);
+    count_launch();
+    return true;
+  }
+  int occ = 0;
+  cudaError_t e = vec ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ew_kernel<Op, 4>, EW_THREADS, 0)
+                      : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ew_kernel<Op, 1>, EW_THREADS, 0);
+  if (e != cudaSuccess || occ < 1) {
+    cudaGetLastError();
+    occ = 2;
+  }
+  long long grid = (long long)occ * sm_count();
+  if (grid > a.items)
+    grid = a.items;
+  if (grid < 1)
+    grid = 1;
   if (vec)
     ew_kernel<Op, 4><<<(unsigned)grid, EW_THREADS, 0, call.stream()>>>(op, a);
   else

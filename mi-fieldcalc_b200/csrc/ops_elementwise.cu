@@ -5,7 +5,7 @@
 // `compute` / `unit` and validates arguments with the reference's exact early-return rules, then
 // launches one kernel for the whole batch.  Citations: FC.cc = the reference's
 // src/mi_fieldcalc/FieldCalculations.cc.
-#include "elementwise.cuh"
+#include "ew_driver.cuh"
 
 #include "../../include/fcb200.h"
 
@@ -68,12 +68,16 @@ int hum_compute(int compute, const char* unit)
 struct PTempStreamOp
 {
   static constexpr int NIN = 1, NOUT = 1, UNROLL = 4;
-  static constexpr bool USES_EWT = false, COUNTS = false;
+  static constexpr int NCOUNT = 0;
+  static constexpr int MIN_BLOCKS = 5;
+  static constexpr bool HEAVY = false;
+  static constexpr bool USES_EWT = false, USES_POW = false;
   int compute;
-  __device__ __forceinline__ void point(const float* in, float* out, const PointCtx& c, long long, unsigned&) const
+  template <bool ALL>
+  __device__ __forceinline__ void point(const float* in, float* out, const PointCtx& c, long long, unsigned*) const
   {
     const float f = in[0], pidcp = c.m.a;
-    if (c.m.all || is_def(f, c.undef))
+    if (ALL || is_def(f, c.undef))
       out[0] = (compute == 1) ? (f * pidcp - K_T0) : (compute == 2) ? (f * pidcp) : (f / pidcp);
     else
       out[0] = c.undef;
@@ -86,14 +90,18 @@ template <int KIND>
 struct TempOp
 {
   static constexpr int NIN = (KIND == PLEVEL) ? 1 : 2, NOUT = 1, UNROLL = 2;
-  static constexpr bool USES_EWT = true, COUNTS = true;
+  static constexpr int NCOUNT = 1;
+  static constexpr int MIN_BLOCKS = 4;
+  static constexpr bool HEAVY = false;
+  static constexpr bool USES_EWT = true, USES_POW = true;
   int compute;
-  __device__ __forceinline__ void point(const float* in, float* out, const PointCtx& c, long long, unsigned& nundef) const
+  template <bool ALL>
+  __device__ __forceinline__ void point(const float* in, float* out, const PointCtx& c, long long, unsigned* nundef) const
   {
     const float t = in[0];
-    bool ok = c.m.all || is_def(t, c.undef);
+    bool ok = ALL || is_def(t, c.undef);
     if (KIND != PLEVEL)
-      ok = c.m.all || (ok && is_def(in[NIN - 1], c.undef));
+      ok = ALL || (ok && is_def(in[NIN - 1], c.undef));
     float r = c.undef;
     if (ok) {
       float p, pi, pidcp = 0.f;
@@ -102,7 +110,7 @@ struct TempOp
         pi = c.m.b;
       } else {
         p = (KIND == HLEVEL) ? dev::p_hlevel(in[1], c.m.a, c.m.b) : in[1];
-        pidcp = dev::pidcp_from_p(p);
+        pidcp = dev::pidcp_from_p(c.pw, p);
         pi = K_CP * pidcp;
       }
       if (compute == 1)
@@ -118,7 +126,7 @@ struct TempOp
     }
     if (!ok) {
       r = c.undef;
-      nundef += 1;
+      nundef[0] += 1;
     }
     out[0] = r;
   }
@@ -129,18 +137,22 @@ template <int KIND>
 struct TheOp
 {
   static constexpr int NIN = 3, NOUT = 1, UNROLL = 2;
-  static constexpr bool USES_EWT = false, COUNTS = true;
+  static constexpr int NCOUNT = 1;
+  static constexpr int MIN_BLOCKS = 4;
+  static constexpr bool HEAVY = false;
+  static constexpr bool USES_EWT = false, USES_POW = true;
   int compute;
-  __device__ __forceinline__ void point(const float* in, float* out, const PointCtx& c, long long, unsigned& nundef) const
+  template <bool ALL>
+  __device__ __forceinline__ void point(const float* in, float* out, const PointCtx& c, long long, unsigned* nundef) const
   {
     const float t = in[0], q = in[1];
-    if (c.m.all || (is_def(t, c.undef) && is_def(q, c.undef) && is_def(in[2], c.undef))) {
+    if (ALL || (is_def(t, c.undef) && is_def(q, c.undef) && is_def(in[2], c.undef))) {
       const float p = (KIND == HLEVEL) ? dev::p_hlevel(in[2], c.m.a, c.m.b) : in[2];
-      const float pi = K_CP * dev::pidcp_from_p(p);
+      const float pi = K_CP * dev::pidcp_from_p(c.pw, p);
       out[0] = (compute == 1) ? ((t * K_CP + q * K_XLH) / pi) : (t + q * K_XLH / pi);
     } else {
       out[0] = c.undef;
-      nundef += 1;
+      nundef[0] += 1;
     }
   }
 };
@@ -152,14 +164,18 @@ template <int KIND>
 struct HumOp
 {
   static constexpr int NIN = (KIND == PLEVEL) ? 2 : 3, NOUT = 1, UNROLL = 2;
-  static constexpr bool USES_EWT = true, COUNTS = true;
+  static constexpr int NCOUNT = 1;
+  static constexpr int MIN_BLOCKS = 4;
+  static constexpr bool HEAVY = false;
+  static constexpr bool USES_EWT = true, USES_POW = true;
   int compute;
   int pcheck; // test `pin != undef` (no NaN test): HLEVEL when p is needed (FC.cc:1187), ALEVEL when it is NOT (FC.cc:1429)
   float tdconv;
-  __device__ __forceinline__ void point(const float* in, float* out, const PointCtx& c, long long, unsigned& nundef) const
+  template <bool ALL>
+  __device__ __forceinline__ void point(const float* in, float* out, const PointCtx& c, long long, unsigned* nundef) const
   {
     const float t = in[0], h = in[1];
-    const bool all = (c.m.all & 1) != 0;
+    const bool all = ALL || (c.m.all & 1) != 0;
     bool ok = all || (is_def(t, c.undef) && is_def(h, c.undef));
     if (KIND == PLEVEL) {
       if (c.m.all & 2)
@@ -178,11 +194,11 @@ struct HumOp
         const bool need_p = !(compute == 7 || compute == 11);
         p = need_p ? dev::p_hlevel(in[2], c.m.a, c.m.b) : 0.f;
         if (even)
-          tk = t * dev::pidcp_from_p(p);
+          tk = t * dev::pidcp_from_p(c.pw, p);
       } else {
         p = in[2];
         if (even)
-          tk = t * dev::pidcp_from_p(p);
+          tk = t * dev::pidcp_from_p(c.pw, p);
       }
       switch (compute) {
       case 1:
@@ -206,7 +222,7 @@ struct HumOp
     }
     if (!ok) {
       r = c.undef;
-      nundef += 1;
+      nundef[0] += 1;
     }
     out[0] = r;
   }
@@ -217,17 +233,21 @@ template <int KIND>
 struct DuctOp
 {
   static constexpr int NIN = 3, NOUT = 1, UNROLL = 2;
-  static constexpr bool USES_EWT = true, COUNTS = true;
+  static constexpr int NCOUNT = 1;
+  static constexpr int MIN_BLOCKS = 4;
+  static constexpr bool HEAVY = false;
+  static constexpr bool USES_EWT = true, USES_POW = true;
   int compute;
-  __device__ __forceinline__ void point(const float* in, float* out, const PointCtx& c, long long, unsigned& nundef) const
+  template <bool ALL>
+  __device__ __forceinline__ void point(const float* in, float* out, const PointCtx& c, long long, unsigned* nundef) const
   {
-    bool ok = c.m.all || (is_def(in[0], c.undef) && is_def(in[1], c.undef) && is_def(in[2], c.undef));
+    bool ok = ALL || (is_def(in[0], c.undef) && is_def(in[1], c.undef) && is_def(in[2], c.undef));
     float r = c.undef;
     if (ok) {
       const float p = (KIND == HLEVEL) ? dev::p_hlevel(in[2], c.m.a, c.m.b) : in[2];
       float tk = in[0];
       if ((compute & 1) == 0)
-        tk *= dev::pidcp_from_p(p);
+        tk *= dev::pidcp_from_p(c.pw, p);
       if (compute <= 2)
         r = dev::tk_q_duct(tk, in[1], p);
       else
@@ -235,7 +255,7 @@ struct DuctOp
     }
     if (!ok) {
       r = c.undef;
-      nundef += 1;
+      nundef[0] += 1;
     }
     out[0] = r;
   }
@@ -248,18 +268,22 @@ template <int NCHK>
 struct KeepOrUndefOp
 {
   static constexpr int NIN = NCHK + 1, NOUT = 1, UNROLL = 2;
-  static constexpr bool USES_EWT = false, COUNTS = true;
-  __device__ __forceinline__ void point(const float* in, float* out, const PointCtx& c, long long, unsigned& nundef) const
+  static constexpr int NCOUNT = 1;
+  static constexpr int MIN_BLOCKS = 5;
+  static constexpr bool HEAVY = false;
+  static constexpr bool USES_EWT = false, USES_POW = false;
+  template <bool ALL>
+  __device__ __forceinline__ void point(const float* in, float* out, const PointCtx& c, long long, unsigned* nundef) const
   {
     bool ok = true;
 #pragma unroll
     for (int k = 0; k < NCHK; ++k)
       ok = ok && is_def(in[k], c.undef);
-    if (c.m.all || ok)
+    if (ALL || ok)
       out[0] = in[NCHK];
     else {
       out[0] = c.undef;
-      nundef += 1;
+      nundef[0] += 1;
     }
   }
 };
@@ -268,14 +292,18 @@ struct KeepOrUndefOp
 struct HPressureOp
 {
   static constexpr int NIN = 1, NOUT = 1, UNROLL = 4;
-  static constexpr bool USES_EWT = false, COUNTS = true;
-  __device__ __forceinline__ void point(const float* in, float* out, const PointCtx& c, long long, unsigned& nundef) const
+  static constexpr int NCOUNT = 1;
+  static constexpr int MIN_BLOCKS = 5;
+  static constexpr bool HEAVY = false;
+  static constexpr bool USES_EWT = false, USES_POW = false;
+  template <bool ALL>
+  __device__ __forceinline__ void point(const float* in, float* out, const PointCtx& c, long long, unsigned* nundef) const
   {
-    if (c.m.all || is_def(in[0], c.undef))
+    if (ALL || is_def(in[0], c.undef))
       out[0] = dev::p_hlevel(in[0], c.m.a, c.m.b);
     else {
       out[0] = c.undef;
-      nundef += 1;
+      nundef[0] += 1;
     }
   }
 };
@@ -284,14 +312,18 @@ struct HPressureOp
 struct WindCoolingOp
 {
   static constexpr int NIN = 3, NOUT = 1, UNROLL = 2;
-  static constexpr bool USES_EWT = false, COUNTS = false;
+  static constexpr int NCOUNT = 0;
+  static constexpr int MIN_BLOCKS = 4;
+  static constexpr bool HEAVY = false;
+  static constexpr bool USES_EWT = false, USES_POW = true;
   float tconv;
-  __device__ __forceinline__ void point(const float* in, float* out, const PointCtx& c, long long, unsigned&) const
+  template <bool ALL>
+  __device__ __forceinline__ void point(const float* in, float* out, const PointCtx& c, long long, unsigned*) const
   {
-    if (c.m.all || (is_def(in[0], c.undef) && is_def(in[1], c.undef) && is_def(in[2], c.undef))) {
+    if (ALL || (is_def(in[0], c.undef) && is_def(in[1], c.undef) && is_def(in[2], c.undef))) {
       const float tc = in[0] - tconv;
       const float ff = (float)((double)dev::absval(in[1], in[2]) * 3.6);
-      const float ffpow = powf(ff, (float)0.16);
+      const float ffpow = c.pw.pow(ff, (double)(float)0.16);
       float d = (float)(13.12 + 0.6215 * (double)tc - 11.37 * (double)ffpow + 0.3965 * (double)tc * (double)ffpow);
       if ((double)d > 0.)
         d = 0.f;
@@ -305,13 +337,17 @@ struct WindCoolingOp
 struct FieldOperOp
 {
   static constexpr int NIN = 2, NOUT = 1, UNROLL = 4;
-  static constexpr bool USES_EWT = false, COUNTS = true;
+  static constexpr int NCOUNT = 1;
+  static constexpr int MIN_BLOCKS = 5;
+  static constexpr bool HEAVY = false;
+  static constexpr bool USES_EWT = false, USES_POW = false;
   int compute;
-  __device__ __forceinline__ void point(const float* in, float* out, const PointCtx& c, long long, unsigned& nundef) const
+  template <bool ALL>
+  __device__ __forceinline__ void point(const float* in, float* out, const PointCtx& c, long long, unsigned* nundef) const
   {
     const float a = in[0], b = in[1];
     float r = c.undef;
-    bool ok = c.m.all || (is_def(a, c.undef) && is_def(b, c.undef));
+    bool ok = ALL || (is_def(a, c.undef) && is_def(b, c.undef));
     if (ok) {
       if (compute == 1)
         r = a + b;
@@ -326,7 +362,7 @@ struct FieldOperOp
     }
     if (!ok) {
       r = c.undef;
-      nundef += 1;
+      nundef[0] += 1;
     }
     out[0] = r;
   }
@@ -337,11 +373,15 @@ template <bool XDIR>
 struct MomentumOp
 {
   static constexpr int NIN = 3, NOUT = 1, UNROLL = 2;
-  static constexpr bool USES_EWT = false, COUNTS = true;
+  static constexpr int NCOUNT = 1;
+  static constexpr int MIN_BLOCKS = 5;
+  static constexpr bool HEAVY = false;
+  static constexpr bool USES_EWT = false, USES_POW = false;
   float fcormin;
-  __device__ __forceinline__ void point(const float* in, float* out, const PointCtx& c, long long idx, unsigned& nundef) const
+  template <bool ALL>
+  __device__ __forceinline__ void point(const float* in, float* out, const PointCtx& c, long long idx, unsigned* nundef) const
   {
-    if (c.m.all || is_def(in[0], c.undef)) {
+    if (ALL || is_def(in[0], c.undef)) {
       float fcor = in[2];
       const float fcormax = -fcormin;
       if (fcor >= 0.f && fcor < fcormin)
@@ -355,8 +395,62 @@ struct MomentumOp
         out[0] = (float)(i / c.nx) - in[0] * in[1] / fcor;
     } else {
       out[0] = c.undef;
-      nundef += 1;
+      nundef[0] += 1;
     }
+  }
+};
+
+
+// The MEPS alevel chain (BASELINE.json configs[1]) fused: one read of t, q, p produces what the
+// reference computes with four calls that each re-read their inputs (12 + 16 + 16 + 16 = 60 B/point
+// -> 28 B/point):
+//   out[0] theta   = aleveltemp(c=3)          t / pidcp(p)                         test t, p     FC.cc:1334-1340
+//   out[1] RH (%)  = alevelhum(c=1)           tk_q_rh(t, q, p)                     test t, q     FC.cc:1429-1431
+//   out[2] Td      = alevelhum(c=5 or 9)      tk_q_td(t, q, p, tdconv)             test t, q     FC.cc:1440-1441
+//   out[3] theta_e = alevelthe(c=1)           (t*cp + q*xlh) / (cp*pidcp(p))       test t, q, p  FC.cc:1379-1382
+// Each output keeps its own definedness test and its own undefined counter, so values, masks and
+// the four flags are exactly those of the four separate calls.  The Exner function and the
+// saturation-table lookup are evaluated once per point instead of three / two times.
+struct AlevelChainOp
+{
+  static constexpr int NIN = 3, NOUT = 4, UNROLL = 1;
+  static constexpr int NCOUNT = 4;
+  static constexpr int MIN_BLOCKS = 4;
+  static constexpr bool HEAVY = false;
+  static constexpr bool USES_EWT = true, USES_POW = true;
+  float tdconv;
+  // Straight-line code: every value is computed unconditionally (the helpers are safe on any bit
+  // pattern) and the definedness tests only select between value and undef at the end, so the
+  // ALL_DEFINED instantiation contains no test at all and the other one no divergent branch.
+  template <bool ALL>
+  __device__ __forceinline__ void point(const float* in, float* out, const PointCtx& c, long long, unsigned* nundef) const
+  {
+    const float t = in[0], q = in[1], p = in[2];
+    const float undef = c.undef;
+    const bool dt = ALL || is_def(t, undef), dq = ALL || is_def(q, undef), dp = ALL || is_def(p, undef);
+
+    const float pidcp = dev::pidcp_from_p(c.pw, p);
+    const float theta = t / pidcp;
+    const float the = (t * K_CP + q * K_XLH) / (K_CP * pidcp);
+
+    const dev::Ewt e(t - K_T0);
+    const float et = e.value(c.tab);
+    const float qsat = dev::K_EPS * et / p;
+    const float rh = (float)(100. * (double)q / (double)qsat);
+    const float rhc = dev::clamp_rh(q / qsat);
+    const float td = e.inverse(c.tab, rhc * et) + tdconv;
+
+    const bool ok_theta = dt && dp;        // aleveltemp tests t, p
+    const bool ok_hum = dt && dq && e.defined; // alevelhum c1/c5 test t, q only; an undefined p flows into the arithmetic
+    const bool ok_the = dt && dq && dp;    // alevelthe tests t, q, p
+    out[0] = ok_theta ? theta : undef;
+    out[1] = ok_hum ? rh : undef;
+    out[2] = ok_hum ? td : undef;
+    out[3] = ok_the ? the : undef;
+    nundef[0] += ok_theta ? 0u : 1u;
+    nundef[1] += ok_hum ? 0u : 1u;
+    nundef[2] += ok_hum ? 0u : 1u;
+    nundef[3] += ok_the ? 0u : 1u;
   }
 };
 
@@ -383,44 +477,25 @@ enum FlagRule { FLAG_FROM_COUNT, FLAG_UNCHANGED };
 
 // Runs one elementwise operator over a batch.  `stride[k]` = 1 for per-field arrays, 0 for arrays shared
 // by the batch.  `fill_meta(k, meta)` sets the per-field scalars.  The output may alias an input.
+// Adapter from the argument lists of the entry points to an EwJob (single output, one counter).
 template <class Op, class FillMeta>
 int run_elementwise(const Batch& b, const Op& op, const float* const* host_in, const int* per_field, float* host_out, int* fDefined, float undef,
                     FlagRule rule, FillMeta fill_meta)
 {
-  if (!b.valid()) {
-    set_error("fcb200: invalid grid or batch size (nx=%d ny=%d nfields=%d)", b.nx, b.ny, b.nfields);
-    return -1;
-  }
-  Call call;
-  const float* in[Op::NIN];
-  long long stride[Op::NIN];
+  EwJob<Op> job;
+  job.nx = b.nx;
+  job.ny = b.ny;
+  job.nfields = b.nfields;
   for (int k = 0; k < Op::NIN; ++k) {
-    stride[k] = per_field[k] ? b.n : 0;
-    in[k] = call.in(host_in[k], (size_t)(per_field[k] ? b.n * b.nfields : b.n));
+    job.in[k] = host_in[k];
+    job.per_field[k] = per_field[k] != 0;
   }
-  float* out[1] = {call.out(host_out, (size_t)(b.n * b.nfields))};
-  FieldMeta* meta = call.meta_host(b.nfields);
-  if (!call.ok())
-    return -1;
-  for (int k = 0; k < b.nfields; ++k) {
-    meta[k].all = (fDefined[k] == ALL_DEFINED) ? 1 : 0;
-    meta[k].a = meta[k].b = meta[k].c = 0.f;
-    fill_meta(k, meta[k]);
-  }
-  const FieldMeta* dmeta = call.upload_meta();
-  unsigned long long* counters = Op::COUNTS ? call.counters(b.nfields) : nullptr;
-  if (!call.ok())
-    return -1;
-  if (!launch_elementwise(call, op, in, stride, out, b.n, b.nfields, b.nx, undef, dmeta, counters))
-    return -1;
-  const int nfields = b.nfields;
-  const unsigned long long n = (unsigned long long)b.n;
-  if (rule == FLAG_FROM_COUNT && Op::COUNTS)
-    return call.finish([=](const unsigned long long* cnt) {
-      for (int k = 0; k < nfields; ++k)
-        fDefined[k] = check_defined(cnt[k], n);
-    });
-  return call.finish(Finalizer());
+  job.out[0] = host_out;
+  job.flags_in = fDefined;
+  job.flags_out[0] = (rule == FLAG_FROM_COUNT && Op::NCOUNT) ? fDefined : nullptr;
+  job.undef = undef;
+  job.fill_meta = fill_meta;
+  return run_ew_job(op, job);
 }
 
 struct NoMeta
@@ -786,6 +861,31 @@ int fcb200_momentumYcoordinate(int nx, int ny, const float* u, const float* ymap
                                int* fDefined, float undef)
 {
   return fcb200_momentumYcoordinate_batched(nx, ny, 1, u, ymapr, fcoriolis, fcoriolisMin, nxy, fDefined, undef);
+}
+
+int fcb200_alevel_chain_batched(int nx, int ny, int nfields, const float* t, const float* q, const float* p, const char* td_unit, float* theta,
+                                float* rh, float* td, float* thetae, const int* fDefinedIn, int* fDefinedOut, float undef)
+{ // = aleveltemp(c=3) + alevelhum(c=1) + alevelhum(c=5, unit) + alevelthe(c=1) on the same inputs
+  const int td_compute = hum_compute(5, td_unit); // 5 (Celsius) or 9 (Kelvin), FC.cc:1417-1420
+  AlevelChainOp op{(td_compute >= 9) ? H_T0 : 0.f};
+  EwJob<AlevelChainOp> job;
+  job.nx = nx;
+  job.ny = ny;
+  job.nfields = nfields;
+  job.in[0] = t;
+  job.in[1] = q;
+  job.in[2] = p;
+  for (int k = 0; k < 3; ++k)
+    job.per_field[k] = true;
+  job.out[0] = theta;
+  job.out[1] = rh;
+  job.out[2] = td;
+  job.out[3] = thetae;
+  job.flags_in = fDefinedIn;
+  for (int o = 0; o < 4; ++o)
+    job.flags_out[o] = fDefinedOut + (size_t)o * (nfields > 0 ? nfields : 0);
+  job.undef = undef;
+  return run_ew_job(op, job);
 }
 
 } // extern "C"

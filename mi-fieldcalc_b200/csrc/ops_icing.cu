@@ -8,7 +8,7 @@
 //
 // Everything that depends only on the call's scalars (vs, alpha, zmin, zmax) is evaluated ONCE on the
 // host with the same libm the reference uses and passed to the kernel, so those terms are bit-exact.
-#include "elementwise.cuh"
+#include "ew_driver.cuh"
 
 #include "../../include/fcb200.h"
 
@@ -38,12 +38,16 @@ __device__ __forceinline__ double freezing_point(float sal)
 // in: airtemp, seatemp, u, v, sal, aice
 struct OverlandOp
 { // VI.cc:77-112
-  static constexpr int NIN = 6, NOUT = 1, UNROLL = 1;
-  static constexpr bool USES_EWT = false, COUNTS = true;
-  __device__ __forceinline__ void point(const float* in, float* out, const PointCtx& c, long long, unsigned& nundef) const
+  static constexpr int NIN = 6, NOUT = 1, UNROLL = 2;
+  static constexpr int NCOUNT = 1;
+  static constexpr int MIN_BLOCKS = 3;
+  static constexpr bool HEAVY = false;
+  static constexpr bool USES_EWT = false, USES_POW = false;
+  template <bool ALL>
+  __device__ __forceinline__ void point(const float* in, float* out, const PointCtx& c, long long, unsigned* nundef) const
   {
     const float airtemp = in[0], seatemp = in[1], sal = in[4], aice = in[5];
-    bool ok = def6(c.m.all, in, c.undef) && ((double)aice < 0.4);
+    bool ok = def6(ALL, in, c.undef) && ((double)aice < 0.4);
     float r = c.undef;
     if (ok) {
       const double Tf = freezing_point(sal);
@@ -57,7 +61,7 @@ struct OverlandOp
     }
     if (!ok) {
       r = c.undef;
-      nundef += 1;
+      nundef[0] += 1;
     }
     out[0] = r;
   }
@@ -65,12 +69,16 @@ struct OverlandOp
 
 struct MertinsOp
 { // VI.cc:114-180
-  static constexpr int NIN = 6, NOUT = 1, UNROLL = 1;
-  static constexpr bool USES_EWT = false, COUNTS = true;
-  __device__ __forceinline__ void point(const float* in, float* out, const PointCtx& c, long long, unsigned& nundef) const
+  static constexpr int NIN = 6, NOUT = 1, UNROLL = 2;
+  static constexpr int NCOUNT = 1;
+  static constexpr int MIN_BLOCKS = 3;
+  static constexpr bool HEAVY = false;
+  static constexpr bool USES_EWT = false, USES_POW = false;
+  template <bool ALL>
+  __device__ __forceinline__ void point(const float* in, float* out, const PointCtx& c, long long, unsigned* nundef) const
   {
     const float sal = in[4], aice = in[5];
-    bool ok = def6(c.m.all, in, c.undef) && ((double)aice < 0.4);
+    bool ok = def6(ALL, in, c.undef) && ((double)aice < 0.4);
     float r = c.undef;
     if (ok) {
       const double Tf = freezing_point(sal);
@@ -115,7 +123,7 @@ struct MertinsOp
     }
     if (!ok) {
       r = c.undef;
-      nundef += 1;
+      nundef[0] += 1;
     }
     out[0] = r;
   }
@@ -153,16 +161,20 @@ __device__ __forceinline__ bool def10_no_pw(bool all, const float* in, float und
 struct ModStallOp
 { // VI.cc:182-337 -- everything in double
   static constexpr int NIN = 11, NOUT = 1, UNROLL = 1;
-  static constexpr bool USES_EWT = false, COUNTS = true;
+  static constexpr int NCOUNT = 1;
+  static constexpr int MIN_BLOCKS = 2;
+  static constexpr bool HEAVY = true;
+  static constexpr bool USES_EWT = false, USES_POW = false;
   double vs_cos_alpha; // vs * cos(alpha), host libm
   float zmin;
   int number;
-  __device__ __forceinline__ void point(const float* in, float* out, const PointCtx& c, long long, unsigned& nundef) const
+  template <bool ALL>
+  __device__ __forceinline__ void point(const float* in, float* out, const PointCtx& c, long long, unsigned* nundef) const
   {
     const float sal = in[0], wave = in[1], airtemp = in[4], rh = in[5], sst = in[6], p = in[7], Pw = in[8], aice = in[9], depth = in[10];
-    if (!(def10_no_pw(c.m.all, in, c.undef) && ((double)aice < 0.4))) {
+    if (!(def10_no_pw(ALL, in, c.undef) && ((double)aice < 0.4))) {
       out[0] = c.undef;
-      nundef += 1;
+      nundef[0] += 1;
       return;
     }
     // deep-water wave speed, then the shallow-water fixed point (:218-237)
@@ -293,7 +305,10 @@ __device__ __forceinline__ float f10mk(float t, float M, float K)
 struct MincogOp
 { // VI.cc:465-705
   static constexpr int NIN = 11, NOUT = 1, UNROLL = 1;
-  static constexpr bool USES_EWT = false, COUNTS = true;
+  static constexpr int NCOUNT = 1;
+  static constexpr int MIN_BLOCKS = 2;
+  static constexpr bool HEAVY = true;
+  static constexpr bool USES_EWT = false, USES_POW = false;
   // call constants, evaluated on the host exactly as the reference's expressions
   float vs, cos_alpha, sin_beta, drag, Vf, zmin;
   double cos_beta_d; // cos((double)beta)
@@ -418,14 +433,15 @@ struct MincogOp
     return fabsf(icing / number) * (float)(3600.0 * 100.0 / 890.0);
   }
 
-  __device__ __forceinline__ void point(const float* in, float* out, const PointCtx& c, long long, unsigned& nundef) const
+  template <bool ALL>
+  __device__ __forceinline__ void point(const float* in, float* out, const PointCtx& c, long long, unsigned* nundef) const
   {
     const float sal = in[0], sst = in[6], aice = in[9];
-    if (def10_no_pw(c.m.all, in, c.undef) && ((double)aice < 0.4) && ((double)sst > (-54.1126 * (double)sal / (double)(1000 - sal)))) {
+    if (def10_no_pw(ALL, in, c.undef) && ((double)aice < 0.4) && ((double)sst > (-54.1126 * (double)sal / (double)(1000 - sal)))) {
       out[0] = model(sal, in[1], in[2], in[3], in[4], in[5], sst, in[7], in[8], in[10]);
     } else {
       out[0] = c.undef;
-      nundef += 1;
+      nundef[0] += 1;
     }
   }
 };
@@ -433,36 +449,19 @@ struct MincogOp
 template <class Op>
 int run_icing(const Op& op, int nx, int ny, int nfields, const float* const* host_in, float* host_out, int* fDefined, float undef)
 {
-  if (nx <= 0 || ny <= 0 || nfields <= 0 || (long long)nx * ny >= 0x7fffffffLL) {
-    set_error("fcb200: invalid grid or batch size (nx=%d ny=%d nfields=%d)", nx, ny, nfields);
-    return -1;
-  }
-  const long long n = (long long)nx * ny;
-  Call call;
-  const float* in[Op::NIN];
-  long long stride[Op::NIN];
+  EwJob<Op> job;
+  job.nx = nx;
+  job.ny = ny;
+  job.nfields = nfields;
   for (int k = 0; k < Op::NIN; ++k) {
-    stride[k] = n;
-    in[k] = call.in(host_in[k], (size_t)(n * nfields));
+    job.in[k] = host_in[k];
+    job.per_field[k] = true;
   }
-  float* out[1] = {call.out(host_out, (size_t)(n * nfields))};
-  FieldMeta* meta = call.meta_host(nfields);
-  if (!call.ok())
-    return -1;
-  for (int k = 0; k < nfields; ++k) {
-    meta[k].all = (fDefined[k] == ALL_DEFINED) ? 1 : 0;
-    meta[k].a = meta[k].b = meta[k].c = 0.f;
-  }
-  const FieldMeta* dmeta = call.upload_meta();
-  unsigned long long* counters = call.counters(nfields);
-  if (!call.ok())
-    return -1;
-  if (!launch_elementwise(call, op, in, stride, out, n, nfields, nx, undef, dmeta, counters))
-    return -1;
-  return call.finish([=](const unsigned long long* cnt) {
-    for (int k = 0; k < nfields; ++k)
-      fDefined[k] = check_defined(cnt[k], (unsigned long long)n);
-  });
+  job.out[0] = host_out;
+  job.flags_in = fDefined;
+  job.flags_out[0] = fDefined;
+  job.undef = undef;
+  return run_ew_job(op, job);
 }
 
 } // namespace

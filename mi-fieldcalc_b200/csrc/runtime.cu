@@ -97,9 +97,22 @@ std::atomic<unsigned long long> g_launches{0};
 
 } // namespace
 
+struct Slot
+{
+  cudaStream_t stream = nullptr;
+  cudaEvent_t done = nullptr; // recorded after the last chunk that used this slot
+  bool busy = false;
+  Arena dev;
+  Arena pin;
+  Slot() { pin.pinned = true; }
+};
+
 struct ThreadState
 {
   int device = -1;
+  Slot slots[PIPE_SLOTS];
+  cudaEvent_t fork_event = nullptr;
+  bool pipe_used = false;
   cudaStream_t own_stream = nullptr;
   cudaStream_t user_stream = nullptr;
   bool use_user_stream = false;
@@ -117,7 +130,39 @@ struct ThreadState
       cudaStreamDestroy(own_stream);
     dev.release_all();
     pin.release_all();
+    release_slots();
     cudaGetLastError();
+  }
+
+  void release_slots()
+  {
+    for (auto& s : slots) {
+      if (s.stream)
+        cudaStreamDestroy(s.stream);
+      if (s.done)
+        cudaEventDestroy(s.done);
+      s.stream = nullptr;
+      s.done = nullptr;
+      s.busy = false;
+      s.dev.release_all();
+      s.pin.release_all();
+    }
+    if (fork_event)
+      cudaEventDestroy(fork_event);
+    fork_event = nullptr;
+  }
+
+  bool init_slots()
+  {
+    for (auto& s : slots) {
+      if (!s.stream && !cuda_ok(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking), "cudaStreamCreate(pipeline)"))
+        return false;
+      if (!s.done && !cuda_ok(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming), "cudaEventCreate(pipeline)"))
+        return false;
+    }
+    if (!fork_event && !cuda_ok(cudaEventCreateWithFlags(&fork_event, cudaEventDisableTiming), "cudaEventCreate(fork)"))
+      return false;
+    return true;
   }
 
   bool init()
@@ -133,6 +178,7 @@ struct ThreadState
           cudaStreamDestroy(own_stream);
         dev.release_all();
         pin.release_all();
+        release_slots();
         own_stream = nullptr;
         cudaSetDevice(d);
       }
@@ -159,6 +205,8 @@ struct ThreadState
     in_flight = false;
     dev.reset();
     pin.reset();
+    for (auto& s : slots)
+      s.busy = false; // the main stream waited for every slot before it drained
     return ok;
   }
 };
@@ -212,17 +260,33 @@ int sm_count()
 
 // ------------------------------------------------------------------------------------------- Call
 
-Call::Call()
+Call::Call(int slot)
 {
   ts_ = &thread_state();
+  slot_ = slot;
   ok_ = ts_->init();
   if (!ok_)
     return;
-  stream_ = ts_->stream();
-  if (!ts_->in_flight) {
-    ts_->dev.reset();
-    ts_->pin.reset();
+  if (slot == 0) {
+    stream_ = ts_->stream();
+    if (!ts_->in_flight) {
+      ts_->dev.reset();
+      ts_->pin.reset();
+    }
+    return;
   }
+  // pipeline slot: wait until the chunk that used this slot last is completely done (that is the
+  // pipeline's back pressure), then recycle the slot's arenas
+  Slot& s = ts_->slots[slot - 1];
+  stream_ = s.stream;
+  if (s.busy) {
+    ok_ = cuda_ok(cudaEventSynchronize(s.done), "cudaEventSynchronize(pipeline slot)");
+    s.busy = false;
+  }
+  for (auto& c : s.dev.chunks)
+    c.used = 0;
+  for (auto& c : s.pin.chunks)
+    c.used = 0;
 }
 
 Call::~Call() {}
@@ -231,7 +295,7 @@ void* Call::arena_alloc(size_t bytes)
 {
   if (!ok_)
     return nullptr;
-  void* p = ts_->dev.alloc(bytes);
+  void* p = (slot_ == 0 ? ts_->dev : ts_->slots[slot_ - 1].dev).alloc(bytes);
   if (!p)
     ok_ = false;
   return p;
@@ -241,7 +305,7 @@ void* Call::pinned_alloc(size_t bytes)
 {
   if (!ok_)
     return nullptr;
-  void* p = ts_->pin.alloc(bytes);
+  void* p = (slot_ == 0 ? ts_->pin : ts_->slots[slot_ - 1].pin).alloc(bytes);
   if (!p)
     ok_ = false;
   return p;
@@ -298,6 +362,7 @@ const float* Call::in(const float* p, size_t count)
     return nullptr;
   }
   pending_.push_back({p, d, count * sizeof(float), false});
+  staged_ += count * sizeof(float);
   return static_cast<const float*>(d);
 }
 
@@ -322,6 +387,7 @@ float* Call::out(float* p, size_t count)
   if (!d)
     return nullptr;
   pending_.push_back({p, d, count * sizeof(float), true});
+  staged_ += count * sizeof(float);
   return static_cast<float*>(d);
 }
 
@@ -406,7 +472,9 @@ int Call::finish(const Finalizer& fin)
   }
   const unsigned long long* host_counters = nullptr;
   if (counters_n_ > 0) {
-    void* pin = pinned_alloc(sizeof(unsigned long long) * (size_t)counters_n_);
+    // counters are read by the finaliser when the whole call drains: they live in the main pinned
+    // arena, which is not recycled while work is in flight
+    void* pin = ts_->pin.alloc(sizeof(unsigned long long) * (size_t)counters_n_);
     if (!pin)
       return -1;
     if (!cuda_ok(cudaMemcpyAsync(pin, counters_dev_, sizeof(unsigned long long) * (size_t)counters_n_, cudaMemcpyDeviceToHost, stream_),
@@ -416,9 +484,43 @@ int Call::finish(const Finalizer& fin)
   }
   ts_->queue.push_back({fin, host_counters});
   ts_->in_flight = true;
+  if (slot_ > 0) { // a chunk of a pipelined call: pipeline_join() drains
+    Slot& s = ts_->slots[slot_ - 1];
+    if (!cuda_ok(cudaEventRecord(s.done, s.stream), "cudaEventRecord(pipeline slot)"))
+      return -1;
+    s.busy = true;
+    return 1;
+  }
   if (ts_->deferred)
     return 1;
   return ts_->drain() ? 1 : -1;
+}
+
+bool pipeline_fork()
+{
+  ThreadState& ts = thread_state();
+  if (!ts.init() || !ts.init_slots())
+    return false;
+  // everything already queued on the main stream happens before the chunks
+  if (!cuda_ok(cudaEventRecord(ts.fork_event, ts.stream()), "cudaEventRecord(fork)"))
+    return false;
+  for (auto& s : ts.slots)
+    if (!cuda_ok(cudaStreamWaitEvent(s.stream, ts.fork_event, 0), "cudaStreamWaitEvent(fork)"))
+      return false;
+  ts.in_flight = true; // keep the main pinned arena (counters) alive until the join
+  return true;
+}
+
+int pipeline_join()
+{
+  ThreadState& ts = thread_state();
+  for (auto& s : ts.slots) {
+    if (s.busy && !cuda_ok(cudaStreamWaitEvent(ts.stream(), s.done, 0), "cudaStreamWaitEvent(join)"))
+      return -1;
+  }
+  if (ts.deferred)
+    return 1;
+  return ts.drain() ? 1 : -1;
 }
 
 } // namespace fcb200

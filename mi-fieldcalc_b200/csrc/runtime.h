@@ -51,11 +51,21 @@ int sm_count();
 // the ValuesDefined flags (and nothing else) into caller memory.
 typedef std::function<void(const unsigned long long* counters)> Finalizer;
 
-// One Call object lives for the duration of one fcb200_* entry point.
+// Chunked host-pointer calls are software-pipelined over PIPE_SLOTS extra streams: while chunk c
+// computes, chunk c+1 is copied in and chunk c-1 is copied out (PCIe is full duplex and the copy
+// engines run beside the SMs).  Each slot owns a stream and a device arena.
+constexpr int PIPE_SLOTS = 3;
+
+// fork the calling thread's pipeline streams off its main stream / join them back and drain.
+bool pipeline_fork();
+int pipeline_join();
+
+// One Call object lives for the duration of one fcb200_* entry point (slot 0, the thread's main
+// stream) or of one chunk of a pipelined entry point (slot 1..PIPE_SLOTS).
 class Call
 {
 public:
-  Call();
+  explicit Call(int slot = 0);
   ~Call();
 
   bool ok() const { return ok_; }
@@ -86,6 +96,8 @@ public:
   // copy host outputs back, fetch the counters, synchronise and run `fin` -- or, in deferred mode,
   // queue all of that for fcb200_end_deferred().  Returns 1 on success, -1 on a runtime error.
   int finish(const Finalizer& fin);
+  // bytes of host memory this call staged so far (0 = everything was device resident)
+  size_t staged_bytes() const { return staged_; }
 
 private:
   struct Pending
@@ -100,6 +112,8 @@ private:
   bool classify(const void* p, bool* is_dev);
 
   struct ThreadState* ts_ = nullptr;
+  int slot_ = 0;
+  size_t staged_ = 0;
   cudaStream_t stream_ = nullptr;
   bool ok_ = true;
   std::vector<Pending> pending_;

@@ -103,3 +103,41 @@ def test_full_size_fields(gpu, name, grid):
         case = cases.build(name, nx, ny, seed=1000, flag_in=flag, mask=mask, nmembers=30 if name in matrix.ENSEMBLE else 5, **params)
         problems = cases.compare(case, cases.run(gpu, case, to_device=_to_device), cases.run(arb, case), rtol=cases.TRANSCENDENTAL.get(name, 0.0))
         assert not problems, "%s %s: %s" % (name, mask, "\n".join(problems))
+
+
+@pytest.mark.parametrize("mask,flag", [("none", cases.ALL), ("none", cases.SOME), ("bernoulli", cases.SOME), ("nan", cases.SOME), ("nan", cases.ALL), ("all", cases.SOME)])
+@pytest.mark.parametrize("unit", ["celsius", "kelvin"])
+def test_fused_alevel_chain_equals_four_reference_calls(gpu, mask, flag, unit):
+    """fcb200_alevel_chain_batched == aleveltemp(c3) + alevelhum(c1) + alevelhum(c5/9) + alevelthe(c1), field by field"""
+    arb = _arbiter()
+    nx, ny, nf = 949, 23, 5
+    rng = np.random.default_rng(42)
+    t = np.stack([cases.field(rng, "tk", nx, ny) for _ in range(nf)])
+    q = np.stack([cases.field(rng, "q", nx, ny) for _ in range(nf)])
+    p = np.stack([cases.field(rng, "p", nx, ny) for _ in range(nf)])
+    for a in (t, q, p):
+        for k in range(nf):
+            cases.apply_mask(rng, a[k], mask, cases.UNDEF)
+    outs = [np.full((nf, ny, nx), cases.SENTINEL, np.float32) for _ in range(4)]
+    fin = np.full(nf, flag, np.int32)
+    fout = np.full((4, nf), -1, np.int32)
+    for device in (False, True):
+        args = [t, q, p] + outs
+        if device:
+            args = [_to_device(a) for a in args]
+        r = gpu.call("alevel_chain_batched", nx, ny, nf, args[0], args[1], args[2], unit, args[3], args[4], args[5], args[6], fin, fout, float(cases.UNDEF))
+        assert r == 1
+        got = [a.cpu().numpy() if device else a for a in args[3:]]
+        calls = [("aleveltemp", lambda k, o, f: (nx, ny, t[k], p[k], "kelvin", 3, o, f, float(cases.UNDEF)), 1e-5, 0.0),
+                 ("alevelhum", lambda k, o, f: (nx, ny, t[k], q[k], p[k], unit, 1, o, f, float(cases.UNDEF)), 0.0, 0.0),
+                 ("alevelhum", lambda k, o, f: (nx, ny, t[k], q[k], p[k], unit, 5, o, f, float(cases.UNDEF)), 0.0, 273.15),
+                 ("alevelthe", lambda k, o, f: (nx, ny, t[k], q[k], p[k], 1, o, f, float(cases.UNDEF)), 1e-5, 0.0)]
+        for oi, (name, mk, rtol, floor) in enumerate(calls):
+            for k in range(nf):
+                o = np.full((ny, nx), cases.SENTINEL, np.float32)
+                f = np.array([flag], np.int32)
+                assert arb.call(name, *mk(k, o, f)) == 1
+                case = cases.Case(name, [], [], None, cases.UNDEF, {})
+                case.floor = floor
+                problems = cases.compare(case, (1, [got[oi][k]], int(fout[oi, k])), (1, [o], int(f[0])), rtol=rtol)
+                assert not problems, "output %d (%s) field %d device=%s: %s" % (oi, name, k, device, problems)

@@ -117,6 +117,11 @@ def main():
             return a + [torch.empty(batch(grid, nt), device=dev), np.full(nt, flag_in, np.int32), UNDEF]
         return build
 
+    def b_chain(grid, nf):
+        nx, ny = grid
+        return [nx, ny, nf, rnd(batch(grid, nf), 215, 305), rnd(batch(grid, nf), 1e-6, 2e-2), rnd(batch(grid, nf), 300, 1040), "celsius"] + \
+               [torch.empty(batch(grid, nf), device=dev) for _ in range(4)] + [np.full(nf, flag_in, np.int32), np.zeros(4 * nf, np.int32), UNDEF]
+
     icing6 = ["tc", "sst", "w", "w", "sal", "aice"]
     icing11 = ["sal", "wave", "w", "w", "tc", "rh01", "sst", "pmsl", "pw", "aice", "depth"]
     OPS = {
@@ -140,6 +145,7 @@ def main():
         "alevelhum_c5": ("alevelhum_batched", MEPS, 65, 16, b_ew(["t", "q", "p"], ("celsius", 5))),
         "alevelthe_c1": ("alevelthe_batched", MEPS, 65, 16, b_ew(["t", "q", "p"], (1,))),
         "alevelducting_c1": ("alevelducting_batched", MEPS, 65, 16, b_ew(["t", "q", "p"], (1,))),
+        "alevel_chain": ("alevel_chain_batched", MEPS, 65, 28, b_chain),
         "windCooling": ("windCooling_batched", MEPS, 65, 16, b_ew(["t", "w", "w"], (1,))),
         "fieldOPERfield_add": ("fieldOPERfield_batched", MEPS, 96, 12, b_ew(["any", "any"], (), lead=(1,))),
         "fieldOPERfield_div": ("fieldOPERfield_batched", MEPS, 96, 12, b_ew(["any", "any"], (), lead=(4,))),
