@@ -1,0 +1,319 @@
+// shim.cc -- libmi-fieldcalc.so.0 drop-in: the reference's C++ free-function API
+// (namespace miutil::fieldcalc, src/mi_fieldcalc/FieldCalculations.h:113-303 of the reference) on top
+// of the C-ABI of include/fcb200.h.  Nothing is computed here: every function converts
+// `ValuesDefined&` <-> `int*`, `std::string` -> `const char*`, `std::vector` -> pointer + count and
+// forwards to fcb200_<name>.  The exported (mangled) symbols are exactly the reference's, so an
+// application linked against mi-fieldcalc picks this library up unchanged.
+//
+// Error policy: the reference cannot fail at run time.  A runtime failure here (no CUDA device,
+// CUDA error) must not look like "arguments rejected", so it throws std::runtime_error; with
+// FCB200_ON_ERROR=return in the environment it prints the message and returns false instead.
+#include "mi_fieldcalc/FieldCalculations.h"
+
+#include "fcb200.h"
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <stdexcept>
+
+const float fieldUndef = 1.0e35f;
+
+namespace miutil {
+
+const float UNDEF = 1.0e35f;
+
+ValuesDefined checkDefined(const float* data, size_t n)
+{ // reference FieldDefined.cc:36-60: defined means `value < UNDEF` (NaN is therefore undefined)
+  bool some_defined = false, some_undefined = false;
+  for (size_t i = 0; i < n && !(some_defined && some_undefined); ++i) {
+    if (data[i] < UNDEF)
+      some_defined = true;
+    else
+      some_undefined = true;
+  }
+  if (some_defined && some_undefined)
+    return SOME_DEFINED;
+  return some_defined ? ALL_DEFINED : NONE_DEFINED;
+}
+
+ValuesDefined checkDefined(size_t n_undefined, size_t n)
+{ // reference FieldDefined.cc:62-70
+  if (n_undefined == 0)
+    return ALL_DEFINED;
+  return (n_undefined == n) ? NONE_DEFINED : SOME_DEFINED;
+}
+
+ValuesDefined combineDefined(ValuesDefined a, ValuesDefined b)
+{ // reference FieldDefined.cc:72-83
+  if (a == ALL_DEFINED)
+    return b;
+  if (a == NONE_DEFINED)
+    return NONE_DEFINED;
+  return (b != ALL_DEFINED) ? b : SOME_DEFINED;
+}
+
+namespace fieldcalc {
+
+namespace {
+
+// result of a C-ABI call -> the reference's bool, flag copied back
+bool done(int rc, int flag, ValuesDefined& fDefined)
+{
+  if (rc < 0) {
+    const char* msg = fcb200_last_error();
+    const char* mode = std::getenv("FCB200_ON_ERROR");
+    if (mode && std::strcmp(mode, "return") == 0) {
+      std::fprintf(stderr, "mi-fieldcalc (B200): %s\n", msg && *msg ? msg : "runtime error");
+      return false;
+    }
+    throw std::runtime_error(msg && *msg ? msg : "mi-fieldcalc (B200): runtime error");
+  }
+  fDefined = static_cast<ValuesDefined>(flag);
+  return rc == 1;
+}
+
+std::vector<int> to_ints(const std::vector<ValuesDefined>& v)
+{
+  std::vector<int> r(v.size());
+  for (size_t i = 0; i < v.size(); ++i)
+    r[i] = static_cast<int>(v[i]);
+  return r;
+}
+
+} // namespace
+
+void copy_field(float* fout, const float* fin, size_t fsize)
+{ // host helper of the reference (FieldCalculations.cc:318-322)
+  if (fout != fin)
+    std::memcpy(fout, fin, sizeof(float) * fsize);
+}
+
+#define FCB_FLAG int f = static_cast<int>(fDefined)
+
+bool pleveltemp(int nx, int ny, const float* tinp, float p, const std::string& unit, int compute, float* tout, ValuesDefined& fDefined, float undef)
+{
+  FCB_FLAG;
+  return done(fcb200_pleveltemp(nx, ny, tinp, p, unit.c_str(), compute, tout, &f, undef), f, fDefined);
+}
+
+bool plevelhum(int nx, int ny, const float* t, const float* huminp, float p, const std::string& unit, int compute, float* humout,
+               ValuesDefined& fDefined, float undef)
+{
+  FCB_FLAG;
+  return done(fcb200_plevelhum(nx, ny, t, huminp, p, unit.c_str(), compute, humout, &f, undef), f, fDefined);
+}
+
+bool hleveltemp(int nx, int ny, const float* tinp, const float* ps, float alevel, float blevel, const std::string& unit, int compute, float* tout,
+                ValuesDefined& fDefined, float undef)
+{
+  FCB_FLAG;
+  return done(fcb200_hleveltemp(nx, ny, tinp, ps, alevel, blevel, unit.c_str(), compute, tout, &f, undef), f, fDefined);
+}
+
+bool hlevelthe(int nx, int ny, const float* t, const float* q, const float* ps, float alevel, float blevel, int compute, float* the,
+               ValuesDefined& fDefined, float undef)
+{
+  FCB_FLAG;
+  return done(fcb200_hlevelthe(nx, ny, t, q, ps, alevel, blevel, compute, the, &f, undef), f, fDefined);
+}
+
+bool hlevelhum(int nx, int ny, const float* t, const float* huminp, const float* ps, float alevel, float blevel, const std::string& unit, int compute,
+               float* humout, ValuesDefined& fDefined, float undef)
+{
+  FCB_FLAG;
+  return done(fcb200_hlevelhum(nx, ny, t, huminp, ps, alevel, blevel, unit.c_str(), compute, humout, &f, undef), f, fDefined);
+}
+
+bool hlevelducting(int nx, int ny, const float* t, const float* h, const float* ps, float alevel, float blevel, int compute, float* duct,
+                   ValuesDefined& fDefined, float undef)
+{
+  FCB_FLAG;
+  return done(fcb200_hlevelducting(nx, ny, t, h, ps, alevel, blevel, compute, duct, &f, undef), f, fDefined);
+}
+
+bool hlevelpressure(int nx, int ny, const float* ps, float alevel, float blevel, float* p, ValuesDefined& fDefined, float undef)
+{
+  FCB_FLAG;
+  return done(fcb200_hlevelpressure(nx, ny, ps, alevel, blevel, p, &f, undef), f, fDefined);
+}
+
+bool aleveltemp(int nx, int ny, const float* tinp, const float* p, const std::string& unit, int compute, float* tout, ValuesDefined& fDefined,
+                float undef)
+{
+  FCB_FLAG;
+  return done(fcb200_aleveltemp(nx, ny, tinp, p, unit.c_str(), compute, tout, &f, undef), f, fDefined);
+}
+
+bool alevelthe(int nx, int ny, const float* t, const float* q, const float* p, int compute, float* the, ValuesDefined& fDefined, float undef)
+{
+  FCB_FLAG;
+  return done(fcb200_alevelthe(nx, ny, t, q, p, compute, the, &f, undef), f, fDefined);
+}
+
+bool alevelhum(int nx, int ny, const float* t, const float* huminp, const float* p, const std::string& unit, int compute, float* humout,
+               ValuesDefined& fDefined, float undef)
+{
+  FCB_FLAG;
+  return done(fcb200_alevelhum(nx, ny, t, huminp, p, unit.c_str(), compute, humout, &f, undef), f, fDefined);
+}
+
+bool alevelducting(int nx, int ny, const float* t, const float* h, const float* p, int compute, float* duct, ValuesDefined& fDefined, float undef)
+{
+  FCB_FLAG;
+  return done(fcb200_alevelducting(nx, ny, t, h, p, compute, duct, &f, undef), f, fDefined);
+}
+
+bool ilevelgwind(int nx, int ny, const float* mpot, const float* xmapr, const float* ymapr, const float* fcoriolis, float* ug, float* vg,
+                 ValuesDefined& fDefined, float undef)
+{
+  FCB_FLAG;
+  return done(fcb200_ilevelgwind(nx, ny, mpot, xmapr, ymapr, fcoriolis, ug, vg, &f, undef), f, fDefined);
+}
+
+bool relvort(int nx, int ny, const float* u, const float* v, const float* xmapr, const float* ymapr, float* rvort, ValuesDefined& fDefined,
+             float undef)
+{
+  FCB_FLAG;
+  return done(fcb200_relvort(nx, ny, u, v, xmapr, ymapr, rvort, &f, undef), f, fDefined);
+}
+
+bool absvort(int nx, int ny, const float* u, const float* v, const float* xmapr, const float* ymapr, const float* fcoriolis, float* avort,
+             ValuesDefined& fDefined, float undef)
+{
+  FCB_FLAG;
+  return done(fcb200_absvort(nx, ny, u, v, xmapr, ymapr, fcoriolis, avort, &f, undef), f, fDefined);
+}
+
+bool divergence(int nx, int ny, const float* u, const float* v, const float* xmapr, const float* ymapr, float* diverg, ValuesDefined& fDefined,
+                float undef)
+{
+  FCB_FLAG;
+  return done(fcb200_divergence(nx, ny, u, v, xmapr, ymapr, diverg, &f, undef), f, fDefined);
+}
+
+bool advection(int nx, int ny, const float* fld, const float* u, const float* v, const float* xmapr, const float* ymapr, float hours, float* advec,
+               ValuesDefined& fDefined, float undef)
+{
+  FCB_FLAG;
+  return done(fcb200_advection(nx, ny, fld, u, v, xmapr, ymapr, hours, advec, &f, undef), f, fDefined);
+}
+
+bool gradient(int nx, int ny, const float* field, const float* xmapr, const float* ymapr, int compute, float* fgrad, ValuesDefined& fDefined,
+              float undef)
+{
+  FCB_FLAG;
+  return done(fcb200_gradient(nx, ny, field, xmapr, ymapr, compute, fgrad, &f, undef), f, fDefined);
+}
+
+bool shapiro2_filter(int nx, int ny, float* field, float* fsmooth, ValuesDefined& fDefined, float undef)
+{
+  FCB_FLAG;
+  return done(fcb200_shapiro2_filter(nx, ny, field, fsmooth, &f, undef), f, fDefined);
+}
+
+bool windCooling(int nx, int ny, const float* t, const float* u, const float* v, int compute, float* dtcool, ValuesDefined& fDefined, float undef)
+{
+  FCB_FLAG;
+  return done(fcb200_windCooling(nx, ny, t, u, v, compute, dtcool, &f, undef), f, fDefined);
+}
+
+bool thermalFrontParameter(int nx, int ny, const float* t, const float* xmapr, const float* ymapr, float* tfp, ValuesDefined& fDefined, float undef)
+{
+  FCB_FLAG;
+  return done(fcb200_thermalFrontParameter(nx, ny, t, xmapr, ymapr, tfp, &f, undef), f, fDefined);
+}
+
+bool momentumXcoordinate(int nx, int ny, const float* v, const float* xmapr, const float* fcoriolis, float fcoriolisMin, float* mxy,
+                         ValuesDefined& fDefined, float undef)
+{
+  FCB_FLAG;
+  return done(fcb200_momentumXcoordinate(nx, ny, v, xmapr, fcoriolis, fcoriolisMin, mxy, &f, undef), f, fDefined);
+}
+
+bool momentumYcoordinate(int nx, int ny, const float* u, const float* ymapr, const float* fcoriolis, float fcoriolisMin, float* nxy,
+                         ValuesDefined& fDefined, float undef)
+{
+  FCB_FLAG;
+  return done(fcb200_momentumYcoordinate(nx, ny, u, ymapr, fcoriolis, fcoriolisMin, nxy, &f, undef), f, fDefined);
+}
+
+bool jacobian(int nx, int ny, const float* field1, const float* field2, const float* xmapr, const float* ymapr, float* fjacobian,
+              ValuesDefined& fDefined, float undef)
+{
+  FCB_FLAG;
+  return done(fcb200_jacobian(nx, ny, field1, field2, xmapr, ymapr, fjacobian, &f, undef), f, fDefined);
+}
+
+bool vesselIcingOverland(int nx, int ny, const float* airtemp, const float* seatemp, const float* u, const float* v, const float* sal,
+                         const float* aice, float* icing, ValuesDefined& fDefined, float undef)
+{
+  FCB_FLAG;
+  return done(fcb200_vesselIcingOverland(nx, ny, airtemp, seatemp, u, v, sal, aice, icing, &f, undef), f, fDefined);
+}
+
+bool vesselIcingMertins(int nx, int ny, const float* airtemp, const float* seatemp, const float* u, const float* v, const float* sal,
+                        const float* aice, float* icing, ValuesDefined& fDefined, float undef)
+{
+  FCB_FLAG;
+  return done(fcb200_vesselIcingMertins(nx, ny, airtemp, seatemp, u, v, sal, aice, icing, &f, undef), f, fDefined);
+}
+
+bool vesselIcingModStall(int nx, int ny, const float* sal, const float* wave, const float* x_wind, const float* y_wind, const float* airtemp,
+                         const float* rh, const float* sst, const float* p, const float* Pw, const float* aice, const float* depth, const float vs,
+                         const float alpha, const float zmin, const float zmax, float* icing, ValuesDefined& fDefined, float undef)
+{
+  FCB_FLAG;
+  return done(fcb200_vesselIcingModStall(nx, ny, sal, wave, x_wind, y_wind, airtemp, rh, sst, p, Pw, aice, depth, vs, alpha, zmin, zmax, icing, &f, undef),
+              f, fDefined);
+}
+
+bool vesselIcingMincog(int nx, int ny, const float* sal, const float* wave, const float* x_wind, const float* y_wind, const float* airtemp,
+                       const float* rh, const float* sst, const float* p, const float* Pw, const float* aice, const float* depth, const float vs,
+                       const float alpha, const float zmin, const float zmax, const int alt, float* icing, ValuesDefined& fDefined, float undef)
+{
+  FCB_FLAG;
+  return done(
+      fcb200_vesselIcingMincog(nx, ny, sal, wave, x_wind, y_wind, airtemp, rh, sst, p, Pw, aice, depth, vs, alpha, zmin, zmax, alt, icing, &f, undef), f,
+      fDefined);
+}
+
+bool fieldOPERfield(int compute, int nx, int ny, const float* field1, const float* field2, float* fres, ValuesDefined& fDefined, float undef)
+{
+  FCB_FLAG;
+  return done(fcb200_fieldOPERfield(compute, nx, ny, field1, field2, fres, &f, undef), f, fDefined);
+}
+
+bool meanValue(int nx, int ny, const std::vector<float*>& fields, const std::vector<ValuesDefined>& fDefinedIn, float* fres,
+               ValuesDefined& fDefinedOut, float undef)
+{
+  int f = static_cast<int>(fDefinedOut);
+  const std::vector<int> fin = to_ints(fDefinedIn);
+  return done(fcb200_meanValue(nx, ny, fields.data(), (int)fields.size(), fin.data(), fres, &f, undef), f, fDefinedOut);
+}
+
+bool stddevValue(int nx, int ny, const std::vector<float*>& fields, const std::vector<ValuesDefined>& fDefinedIn, float* fres,
+                 ValuesDefined& fDefinedOut, float undef)
+{
+  int f = static_cast<int>(fDefinedOut);
+  const std::vector<int> fin = to_ints(fDefinedIn);
+  return done(fcb200_stddevValue(nx, ny, fields.data(), (int)fields.size(), fin.data(), fres, &f, undef), f, fDefinedOut);
+}
+
+bool extremeValue(int compute, int nx, int ny, const std::vector<float*>& fields, float* fres, ValuesDefined& fDefined, float undef)
+{
+  FCB_FLAG;
+  return done(fcb200_extremeValue(compute, nx, ny, fields.data(), (int)fields.size(), fres, &f, undef), f, fDefined);
+}
+
+bool probability(int compute, int nx, int ny, const std::vector<float*>& fields, const std::vector<ValuesDefined>& fDefinedIn,
+                 const std::vector<float>& limits, float* fres, ValuesDefined& fDefinedOut, float undef)
+{
+  int f = static_cast<int>(fDefinedOut);
+  const std::vector<int> fin = to_ints(fDefinedIn);
+  return done(fcb200_probability(compute, nx, ny, fields.data(), (int)fields.size(), fin.data(), limits.data(), (int)limits.size(), fres, &f, undef), f,
+              fDefinedOut);
+}
+
+} // namespace fieldcalc
+} // namespace miutil
