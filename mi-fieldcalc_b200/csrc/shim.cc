@@ -58,7 +58,7 @@ namespace fieldcalc {
 namespace {
 
 // result of a C-ABI call -> the reference's bool, flag copied back
-bool done(int rc, int flag, ValuesDefined& fDefined)
+bool done(int rc, const int& flag, ValuesDefined& fDefined) // `flag` by reference: it is written by the call that produces `rc`
 {
   if (rc < 0) {
     const char* msg = fcb200_last_error();
