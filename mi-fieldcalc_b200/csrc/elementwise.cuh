@@ -165,6 +165,26 @@ __device__ __forceinline__ void ew_flush(unsigned* nundef, unsigned long long* c
   }
 }
 
+// CTA-level flush for the one-item-per-CTA kernel: every CTA in flight works on the same one or two
+// fields, and one atomic per WARP on a single address serialises in L2 when many points are undefined.
+template <int NCOUNT>
+__device__ __forceinline__ void ew_flush_block(unsigned* nundef, unsigned long long* counters, int field)
+{
+  __shared__ unsigned s_count[NCOUNT > 0 ? NCOUNT : 1];
+  if (threadIdx.x < NCOUNT)
+    s_count[threadIdx.x] = 0;
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < NCOUNT; ++k) {
+    const unsigned total = __reduce_add_sync(0xffffffffu, nundef[k]);
+    if ((threadIdx.x & 31) == 0 && total)
+      atomicAdd(&s_count[k], total);
+  }
+  __syncthreads();
+  if (threadIdx.x < NCOUNT && s_count[threadIdx.x])
+    atomicAdd(counters + (long long)field * NCOUNT + threadIdx.x, (unsigned long long)s_count[threadIdx.x]);
+}
+
 template <class Op, int W>
 __global__ void __launch_bounds__(EW_THREADS, Op::MIN_BLOCKS) ew_kernel(const Op op, const EwArgs<Op::NIN, Op::NOUT> a)
 {
@@ -235,7 +255,7 @@ __global__ void __launch_bounds__(EW_THREADS, Op::MIN_BLOCKS) ew_kernel_once(con
   else
     ew_item<Op, W, false>(op, a, c, (int)field, (int)chunk, nundef);
   if (Op::NCOUNT > 0)
-    ew_flush<Op::NCOUNT>(nundef, a.counters, (int)field);
+    ew_flush_block<Op::NCOUNT>(nundef, a.counters, (int)field);
 }
 
 // Host side: pick the vector width, size the persistent grid, launch.  `in`/`out` are DEVICE pointers.

@@ -15,6 +15,7 @@
 #include "../../include/fcb200.h"
 
 #include <cmath>
+#include <cstdlib>
 
 namespace fcb200 {
 namespace {
@@ -30,78 +31,142 @@ struct StencilGeom
   int n; // nx*ny < 2^31 (the reference's `int fsize`)
   int nfields;
   int chunks;
+  int group;      // fields per grid group (gridDim.x)
+  int chunk_base; // first chunk of this launch (a range of more than 65535 chunks takes several launches)
+  int lo, hi; // the reference's flat loop range [lo, hi): [nx, N-nx), or [1, N-1) for gradient c=1
   float undef;
   const FieldMeta* meta;
   unsigned long long* counters;
 };
 
-__device__ __forceinline__ void store_with_edges(float* out, int i, int x, int y, int nx, int ny, float v)
+// Op interface (every member is evaluated per thread; pointers are per-field after at()):
+//   static constexpr int NOUT;
+//   static constexpr bool TESTS_WHEN_ALL;        // eval() can fail even when allDefined (TFP's absdelt != 0)
+//   __device__ bool all_defined(int field, bool in_all) const;   // the allDefined of this pass
+//   __device__ Op at(int field, int n) const;                    // the same operator with its field pointers advanced
+//   template <bool ALL> struct In;                               // the operands of ONE point, in registers
+//   template <bool ALL> __device__ In<ALL> load(int i, int nx) const;
+//   template <bool ALL> __device__ bool eval(const In<ALL>&, float undef, float* val) const;
+//   __device__ float* out(int k) const;
+//
+// The main kernel is the reference's flat loop and nothing else: a thread owns ST_UNROLL points one
+// CTA-width apart (every warp access is a contiguous 128 B run), issues ALL its loads, then computes
+// and stores.  No (x, y) is ever computed; edge-column points are evaluated with their wrapped
+// neighbours exactly like the reference does, and fill_edges_kernel overwrites the border ring
+// afterwards (stream order), exactly like fillEdges.  Undefined points are counted in a register and
+// flushed with one warp reduction + one atomic per warp.
+template <class Op, bool ALL>
+__device__ __forceinline__ unsigned stencil_point(const Op& op, const typename Op::template In<ALL>& in, int i, float undef)
 {
-  out[i] = v;
-  const bool l = (x == 1), r = (x == nx - 2), t = (y == 1), b = (y == ny - 2);
-  if (l)
-    out[i - 1] = v;
-  if (r)
-    out[i + 1] = v;
-  if (t) {
-    out[i - nx] = v;
-    if (l)
-      out[i - nx - 1] = v;
-    if (r)
-      out[i - nx + 1] = v;
+  float val[Op::NOUT];
+  const bool ok = op.template eval<ALL>(in, undef, val);
+#pragma unroll
+  for (int k = 0; k < Op::NOUT; ++k)
+    op.out(k)[i] = ok ? val[k] : undef;
+  return ok ? 0u : 1u;
+}
+
+template <class Op, bool ALL>
+__device__ __forceinline__ void stencil_body(const Op& op, const StencilGeom& g, int chunk, unsigned long long* counter)
+{
+  typedef typename Op::template In<ALL> In;
+  const int nx = g.nx, hi = g.hi;
+  const int c0 = g.lo + chunk * (ST_THREADS * ST_UNROLL);
+  const int i0 = c0 + (int)threadIdx.x;
+  unsigned nundef = 0;
+  if (c0 + ST_THREADS * ST_UNROLL <= hi) {
+    // full chunk (all but the last of a field): no guards, every address is a constant offset from i0
+    In in[ST_UNROLL];
+#pragma unroll
+    for (int u = 0; u < ST_UNROLL; ++u)
+      in[u] = op.template load<ALL>(i0 + u * ST_THREADS, nx);
+#pragma unroll
+    for (int u = 0; u < ST_UNROLL; ++u)
+      nundef += stencil_point<Op, ALL>(op, in[u], i0 + u * ST_THREADS, g.undef);
+  } else {
+#pragma unroll 1
+    for (int i = i0; i < hi; i += ST_THREADS)
+      nundef += stencil_point<Op, ALL>(op, op.template load<ALL>(i, nx), i, g.undef);
   }
-  if (b) {
-    out[i + nx] = v;
-    if (l)
-      out[i + nx - 1] = v;
-    if (r)
-      out[i + nx + 1] = v;
+  // one global atomic per CTA: all CTAs in flight belong to one or two fields, and per-warp atomics on
+  // a single address serialise in L2 (measured: 2.3x slower with 30 % undefined points)
+  if (!ALL || Op::TESTS_WHEN_ALL) {
+    __shared__ unsigned s_count;
+    if (threadIdx.x == 0)
+      s_count = 0;
+    __syncthreads();
+    nundef = __reduce_add_sync(0xffffffffu, nundef);
+    if ((threadIdx.x & 31) == 0 && nundef)
+      atomicAdd(&s_count, nundef);
+    __syncthreads();
+    if (threadIdx.x == 0 && s_count)
+      atomicAdd(counter, (unsigned long long)s_count);
   }
 }
 
-// Op interface:
-//   static constexpr int NOUT;
-//   static constexpr bool TESTS_WHEN_ALL;  // eval() can fail even when allDefined (TFP's absdelt != 0)
-//   bool count_flat;                      // count over [1, N-1) instead of rows 1..ny-2 (gradient c=1)
-//   __device__ bool all_defined(int field, bool in_all) const;       // the allDefined of this pass
-//   __device__ bool eval(int field, int i, int nx, int n, bool all, float undef, bool want, float* val) const;
-//   __device__ float* out(int k, int field, int n) const;
-template <class Op>
-__global__ void __launch_bounds__(ST_THREADS) stencil_kernel(const Op op, const StencilGeom g)
-{
-  const int field = blockIdx.x / g.chunks;
-  const int chunk = blockIdx.x - field * g.chunks;
-  const bool all = op.all_defined(field, g.meta[field].all != 0);
-  const int nx = g.nx, ny = g.ny, n = g.n;
-  unsigned nundef = 0;
+// Grid = (ST_GROUP fields, chunks, field groups), x fastest: the CTAs in flight work on the SAME few
+// chunks of up to ST_GROUP different fields, so a chunk of the grid-constant arrays (xmapr, ymapr,
+// fcoriolis) is fetched from HBM once per group and then hit in L2.  Field-major order thrashes: one
+// ECMWF field streams 26 MB in + 26 MB out + 52 MB of map ratios, more than the L2 keeps (measured
+// 2.9x DRAM read amplification).
+constexpr int ST_GROUP = 16;
 
-#pragma unroll
-  for (int u = 0; u < ST_UNROLL; ++u) {
-    const int i = chunk * (ST_THREADS * ST_UNROLL) + u * ST_THREADS + threadIdx.x;
-    if (i >= n)
-      continue;
-    const int y = i / nx, x = i - y * nx;
-    const bool row_in = (y >= 1 && y <= ny - 2);
-    const bool interior = row_in && x >= 1 && x <= nx - 2;
-    const bool count_here = op.count_flat ? (i >= 1 && i <= n - 2) : row_in;
-    if (!(interior || (count_here && (!all || Op::TESTS_WHEN_ALL))))
-      continue;
-    float val[Op::NOUT];
-    const bool ok = op.eval(field, i, nx, n, all, g.undef, interior, val);
-    if (!ok)
-      nundef += 1;
-    if (interior) {
-#pragma unroll
-      for (int k = 0; k < Op::NOUT; ++k)
-        store_with_edges(op.out(k, field, n), i, x, y, nx, ny, ok ? val[k] : g.undef);
+template <class Op>
+__global__ void __launch_bounds__(ST_THREADS) stencil_kernel(const Op op0, const StencilGeom g)
+{
+  const int field = blockIdx.z * g.group + blockIdx.x, chunk = blockIdx.y + g.chunk_base;
+  if (field >= g.nfields)
+    return;
+  const bool all = op0.all_defined(field, g.meta[field].all != 0);
+  const Op op = op0.at(field, g.n);
+  if (all)
+    stencil_body<Op, true>(op, g, chunk, g.counters + field);
+  else
+    stencil_body<Op, false>(op, g, chunk, g.counters + field);
+}
+
+// fillEdges (FC.cc:59-74): out(x, y) = interior(clamp(x, 1, nx-2), clamp(y, 1, ny-2)) on the border ring.
+// One thread per border cell; the sources are interior cells, which this kernel never writes.
+constexpr int FE_THREADS = 128;
+
+__global__ void __launch_bounds__(FE_THREADS) fill_edges_kernel(float* o0, float* o1, int nx, int ny, int nfields)
+{
+  const int ring = 2 * nx + 2 * (ny - 2);
+  const int b = blockIdx.x * FE_THREADS + threadIdx.x;
+  if (b >= ring)
+    return;
+  int x, y;
+  if (b < nx) {
+    x = b;
+    y = 0;
+  } else if (b < 2 * nx) {
+    x = b - nx;
+    y = ny - 1;
+  } else {
+    const int c = b - 2 * nx;
+    y = 1 + (c >> 1);
+    x = (c & 1) ? nx - 1 : 0;
+  }
+  const int sx = min(max(x, 1), nx - 2), sy = min(max(y, 1), ny - 2);
+  const long long n = (long long)nx * ny;
+  const int dst = y * nx + x, src = sy * nx + sx;
+  for (int field = blockIdx.y; field < nfields; field += gridDim.y) {
+    float* p = o0 + field * n;
+    p[dst] = p[src];
+    if (o1) {
+      float* q = o1 + field * n;
+      q[dst] = q[src];
     }
   }
-  dev::block_add_counter(nundef, g.counters + field);
 }
 
-__device__ __forceinline__ bool def4(bool all, float a, float b, float c, float d, float undef)
+__device__ __forceinline__ bool def2(float a, float b, float undef)
 {
-  return all || (is_def(a, undef) && is_def(b, undef) && is_def(c, undef) && is_def(d, undef));
+  return is_def(a, undef) && is_def(b, undef);
+}
+__device__ __forceinline__ bool def4(float a, float b, float c, float d, float undef)
+{
+  return is_def(a, undef) && is_def(b, undef) && is_def(c, undef) && is_def(d, undef);
 }
 
 // centred difference times map ratio, evaluated like `0.5 * mapr[i] * (f[i+d] - f[i-d])`:
@@ -111,34 +176,192 @@ __device__ __forceinline__ double half_map_diff(float mapr, float hi, float lo)
   return 0.5 * (double)mapr * (double)(hi - lo);
 }
 
-// relvort / absvort / divergence (FC.cc:1843-1940)
+// ---- vector loads for the float4 path ------------------------------------------------------------------
+// A lane of the vector kernel owns "group" gi = 4 consecutive flat points i0 .. i0+3 whose address is
+// 16-byte aligned in every per-field array; the 32 lanes of a warp own 32 consecutive groups.  Every
+// global access is ONE aligned LDG.128 per lane and array row; what a lane needs beyond its own 16
+// bytes comes from the adjacent lanes by warp shuffle:
+//   * x neighbours: point i0-1 is lane-1's .w, point i0+4 is lane+1's .x;
+//   * a neighbour row (i0 +- nx) or a grid-constant array starts SH = 0..3 elements past a 16-byte
+//     boundary (SH is uniform per CTA, a template parameter): the lane loads the aligned block that
+//     holds its first 4-SH values and takes the other SH from lane+1's block.
+// Lanes 0 and 31 therefore only serve as halo: a warp produces 30 groups (120 points) per step.
+// (Loading two blocks per lane instead was measured L1-bound: 72 % l1tex throughput, 50 B/point.)
+// A block is only loaded when it holds at least one element some lane needs, so no access leaves the
+// arrays: groups -1 and ngroups (the range's unaligned head and tail) exist for the halo only.
+constexpr unsigned FULL = 0xffffffffu;
+
+// Loads are unconditional: a lane whose group lies outside [first, last] loads the nearest group that
+// some lane needs instead (an L1 hit, result unused).  first/last per kind of array:
+//   x-neighbour arrays: [-1, ngroups]; rows / maps with SH > 0: [0, ngroups]; with SH == 0: [0, ngroups-1].
+__device__ __forceinline__ float4 ldx(const float* p_al, int gi, int ngroups)
+{
+  const int g = min(max(gi, -1), ngroups);
+  return *reinterpret_cast<const float4*>(p_al + 4 * g);
+}
+template <int SH>
+__device__ __forceinline__ float4 ldr(const float* p_al, int gi, int ngroups)
+{
+  const int g = min(max(gi, 0), SH ? ngroups : ngroups - 1);
+  return *reinterpret_cast<const float4*>(p_al + 4 * g - SH);
+}
+// o[0] = p[-1], o[1..4] = p[0..3], o[5] = p[4]
+__device__ __forceinline__ void ex6(const float4& a, float (&o)[6])
+{
+  o[0] = __shfl_up_sync(FULL, a.w, 1);
+  o[1] = a.x;
+  o[2] = a.y;
+  o[3] = a.z;
+  o[4] = a.w;
+  o[5] = __shfl_down_sync(FULL, a.x, 1);
+}
+template <int SH>
+__device__ __forceinline__ void ex4(const float4& a, float (&o)[4])
+{
+  float t[8] = {a.x, a.y, a.z, a.w, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int j = 0; j < SH; ++j)
+    t[4 + j] = __shfl_down_sync(FULL, t[j], 1);
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+    o[j] = t[j + SH];
+}
+
+// relvort / absvort / divergence (FC.cc:1843-1940).  MODE: 0 relvort, 1 absvort, 2 divergence
+template <int MODE>
 struct VortDivOp
 {
   static constexpr int NOUT = 1;
   static constexpr bool TESTS_WHEN_ALL = false;
-  bool count_flat;
-  int mode; // 0 relvort, 1 absvort, 2 divergence
   const float *u, *v, *xm, *ym, *fc;
   float* o;
-  __device__ __forceinline__ bool all_defined(int, bool in_all) const { return in_all; }
-  __device__ __forceinline__ float* out(int, int field, int n) const { return o + (long long)field * n; }
-  __device__ __forceinline__ bool eval(int field, int i, int nx, int n, bool all, float undef, bool want, float* val) const
+  // relvort/absvort: a = v[i-1], b = v[i+1], c = u[i-nx], d = u[i+nx] are both the tested and the used
+  // operands.  divergence TESTS the same four (FC.cc:1927) but COMPUTES from u[i+-1], v[i+-nx]
+  // (FC.cc:1928): the masked path loads both sets, the all-defined path only the second.
+  template <bool ALL>
+  struct In
   {
-    const float* uu = u + (long long)field * n;
-    const float* vv = v + (long long)field * n;
-    const float vl = vv[i - 1], vr = vv[i + 1], ud = uu[i - nx], uup = uu[i + nx];
-    // the test of all three operators reads v[i+-1] and u[i+-nx] -- divergence included (FC.cc:1927)
-    if (!def4(all, vl, vr, ud, uup, undef))
-      return false;
-    if (want) {
-      if (mode == 2)
-        val[0] = (float)(half_map_diff(xm[i], uu[i + 1], uu[i - 1]) + half_map_diff(ym[i], vv[i + nx], vv[i - nx]));
-      else if (mode == 1)
-        val[0] = (float)(half_map_diff(xm[i], vr, vl) - half_map_diff(ym[i], uup, ud) + (double)fc[i]);
-      else
-        val[0] = (float)(half_map_diff(xm[i], vr, vl) - half_map_diff(ym[i], uup, ud));
+    float a, b, c, d, xm, ym, fc;
+    float ta, tb, tc, td;
+  };
+  __device__ __forceinline__ bool all_defined(int, bool in_all) const { return in_all; }
+  __device__ __forceinline__ VortDivOp at(int field, int n) const
+  {
+    VortDivOp r = *this;
+    const long long off = (long long)field * n;
+    r.u += off;
+    r.v += off;
+    r.o += off;
+    return r;
+  }
+  __host__ __device__ __forceinline__ float* out(int) const { return o; }
+  template <bool ALL>
+  __device__ __forceinline__ In<ALL> load(int i, int nx) const
+  {
+    In<ALL> r;
+    if (MODE == 2) {
+      r.a = u[i - 1];
+      r.b = u[i + 1];
+      r.c = v[i - nx];
+      r.d = v[i + nx];
+      if (!ALL) {
+        r.ta = v[i - 1];
+        r.tb = v[i + 1];
+        r.tc = u[i - nx];
+        r.td = u[i + nx];
+      }
+    } else {
+      r.a = v[i - 1];
+      r.b = v[i + 1];
+      r.c = u[i - nx];
+      r.d = u[i + nx];
     }
-    return true;
+    r.xm = xm[i];
+    r.ym = ym[i];
+    if (MODE == 1)
+      r.fc = fc[i];
+    return r;
+  }
+  static constexpr int NFIELD_PTRS = 3, NMAP_PTRS = (MODE == 1) ? 3 : 2;
+  __host__ void field_ptrs(const void** p) const { p[0] = u, p[1] = v, p[2] = o; }
+  __host__ void map_ptrs(const void** p) const { p[0] = xm, p[1] = ym, p[2] = fc; }
+  __host__ __device__ __forceinline__ const float* map0() const { return xm; }
+  struct Raw
+  {
+    float4 x, up, dn, m1, m2, m3, tx, tup, tdn;
+  };
+  // p_al = array + i_al: the address of group 0
+  template <bool ALL, int SNX, int SMAP>
+  __device__ __forceinline__ Raw load_raw(int i_al, int nx, int gi, int ng) const
+  {
+    constexpr int SUP = (4 - SNX) & 3, SDN = SNX;
+    const float* fx = (MODE == 2) ? u : v; // the array whose x neighbours are used
+    const float* fy = (MODE == 2) ? v : u; // the array whose y neighbours are used
+    Raw r;
+    r.x = ldx(fx + i_al, gi, ng);
+    r.up = ldr<SUP>(fy + i_al - nx, gi, ng);
+    r.dn = ldr<SDN>(fy + i_al + nx, gi, ng);
+    r.m1 = ldr<SMAP>(xm + i_al, gi, ng);
+    r.m2 = ldr<SMAP>(ym + i_al, gi, ng);
+    if (MODE == 1)
+      r.m3 = ldr<SMAP>(fc + i_al, gi, ng);
+    if (MODE == 2 && !ALL) {
+      r.tx = ldx(v + i_al, gi, ng);
+      r.tup = ldr<SUP>(u + i_al - nx, gi, ng);
+      r.tdn = ldr<SDN>(u + i_al + nx, gi, ng);
+    }
+    return r;
+  }
+  template <bool ALL, int SNX, int SMAP>
+  __device__ __forceinline__ void assemble(const Raw& r, In<ALL> (&in)[4]) const
+  {
+    constexpr int SUP = (4 - SNX) & 3, SDN = SNX;
+    float x6[6], up[4], dn[4], m1[4], m2[4], m3[4], tx6[6], tup[4], tdn[4];
+    ex6(r.x, x6);
+    ex4<SUP>(r.up, up);
+    ex4<SDN>(r.dn, dn);
+    ex4<SMAP>(r.m1, m1);
+    ex4<SMAP>(r.m2, m2);
+    if (MODE == 1)
+      ex4<SMAP>(r.m3, m3);
+    if (MODE == 2 && !ALL) {
+      ex6(r.tx, tx6);
+      ex4<SUP>(r.tup, tup);
+      ex4<SDN>(r.tdn, tdn);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      in[j].a = x6[j];
+      in[j].b = x6[j + 2];
+      in[j].c = up[j];
+      in[j].d = dn[j];
+      in[j].xm = m1[j];
+      in[j].ym = m2[j];
+      if (MODE == 1)
+        in[j].fc = m3[j];
+      if (MODE == 2 && !ALL) {
+        in[j].ta = tx6[j];
+        in[j].tb = tx6[j + 2];
+        in[j].tc = tup[j];
+        in[j].td = tdn[j];
+      }
+    }
+  }
+  template <bool ALL>
+  __device__ __forceinline__ bool eval(const In<ALL>& r, float undef, float* val) const
+  {
+    bool ok = true;
+    if (!ALL)
+      ok = (MODE == 2) ? def4(r.ta, r.tb, r.tc, r.td, undef) : def4(r.a, r.b, r.c, r.d, undef);
+    if (!ok)
+      return false;
+    // 0.5*xm*dx -+ 0.5*ym*dy: the products of two floats are exact in double and so is the scaling by 0.5,
+    // hence RN(0.5*px -+ 0.5*py) = 0.5 * RN(px -+ py) = 0.5 * fma(-+ym, dy, px): three double instructions
+    const double px = (double)r.xm * (double)(r.b - r.a);
+    const double ym = (MODE == 2) ? (double)r.ym : -(double)r.ym;
+    const double h = 0.5 * fma(ym, (double)(r.d - r.c), px);
+    val[0] = (MODE == 1) ? (float)(h + (double)r.fc) : (float)h;
+    return ok;
   }
 };
 
@@ -147,80 +370,227 @@ struct AdvectionOp
 {
   static constexpr int NOUT = 1;
   static constexpr bool TESTS_WHEN_ALL = false;
-  bool count_flat;
   const float *f, *u, *v, *xm, *ym;
   float scale;
   float* o;
-  __device__ __forceinline__ bool all_defined(int, bool in_all) const { return in_all; }
-  __device__ __forceinline__ float* out(int, int field, int n) const { return o + (long long)field * n; }
-  __device__ __forceinline__ bool eval(int field, int i, int nx, int n, bool all, float undef, bool want, float* val) const
+  template <bool ALL>
+  struct In
   {
+    float ui, vi, fd, fl, fr, fu, xm, ym;
+  };
+  __device__ __forceinline__ bool all_defined(int, bool in_all) const { return in_all; }
+  __device__ __forceinline__ AdvectionOp at(int field, int n) const
+  {
+    AdvectionOp r = *this;
     const long long off = (long long)field * n;
-    const float* ff = f + off;
-    const float ui = u[off + i], vi = v[off + i];
-    const float fd = ff[i - nx], fl = ff[i - 1], fr = ff[i + 1], fu = ff[i + nx];
-    if (!(all || (is_def(ui, undef) && is_def(vi, undef) && is_def(fd, undef) && is_def(fl, undef) && is_def(fr, undef) && is_def(fu, undef))))
-      return false;
-    if (want) {
-      const double ax = (double)ui * 0.5 * (double)xm[i] * (double)(fr - fl);
-      const double ay = (double)vi * 0.5 * (double)ym[i] * (double)(fu - fd);
-      val[0] = (float)((ax + ay) * (double)scale);
+    r.f += off;
+    r.u += off;
+    r.v += off;
+    r.o += off;
+    return r;
+  }
+  __host__ __device__ __forceinline__ float* out(int) const { return o; }
+  template <bool ALL>
+  __device__ __forceinline__ In<ALL> load(int i, int nx) const
+  {
+    In<ALL> r;
+    r.ui = u[i];
+    r.vi = v[i];
+    r.fd = f[i - nx];
+    r.fl = f[i - 1];
+    r.fr = f[i + 1];
+    r.fu = f[i + nx];
+    r.xm = xm[i];
+    r.ym = ym[i];
+    return r;
+  }
+  static constexpr int NFIELD_PTRS = 4, NMAP_PTRS = 2;
+  __host__ void field_ptrs(const void** p) const { p[0] = f, p[1] = u, p[2] = v, p[3] = o; }
+  __host__ void map_ptrs(const void** p) const { p[0] = xm, p[1] = ym; }
+  __host__ __device__ __forceinline__ const float* map0() const { return xm; }
+  struct Raw
+  {
+    float4 x, up, dn, uc, vc, m1, m2;
+  };
+  template <bool ALL, int SNX, int SMAP>
+  __device__ __forceinline__ Raw load_raw(int i_al, int nx, int gi, int ng) const
+  {
+    constexpr int SUP = (4 - SNX) & 3, SDN = SNX;
+    Raw r;
+    r.x = ldx(f + i_al, gi, ng);
+    r.up = ldr<SUP>(f + i_al - nx, gi, ng);
+    r.dn = ldr<SDN>(f + i_al + nx, gi, ng);
+    r.uc = ldr<0>(u + i_al, gi, ng);
+    r.vc = ldr<0>(v + i_al, gi, ng);
+    r.m1 = ldr<SMAP>(xm + i_al, gi, ng);
+    r.m2 = ldr<SMAP>(ym + i_al, gi, ng);
+    return r;
+  }
+  template <bool ALL, int SNX, int SMAP>
+  __device__ __forceinline__ void assemble(const Raw& r, In<ALL> (&in)[4]) const
+  {
+    constexpr int SUP = (4 - SNX) & 3, SDN = SNX;
+    float x6[6], up[4], dn[4], uc[4], vc[4], m1[4], m2[4];
+    ex6(r.x, x6);
+    ex4<SUP>(r.up, up);
+    ex4<SDN>(r.dn, dn);
+    ex4<0>(r.uc, uc);
+    ex4<0>(r.vc, vc);
+    ex4<SMAP>(r.m1, m1);
+    ex4<SMAP>(r.m2, m2);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      in[j].ui = uc[j];
+      in[j].vi = vc[j];
+      in[j].fd = up[j];
+      in[j].fl = x6[j];
+      in[j].fr = x6[j + 2];
+      in[j].fu = dn[j];
+      in[j].xm = m1[j];
+      in[j].ym = m2[j];
     }
-    return true;
+  }
+  template <bool ALL>
+  __device__ __forceinline__ bool eval(const In<ALL>& r, float undef, float* val) const
+  {
+    bool ok = true;
+    if (!ALL)
+      ok = def2(r.ui, r.vi, undef) && def4(r.fd, r.fl, r.fr, r.fu, undef);
+    if (!ok)
+      return false;
+    const double ax = (double)r.ui * 0.5 * (double)r.xm * (double)(r.fr - r.fl);
+    const double ay = (double)r.vi * 0.5 * (double)r.ym * (double)(r.fu - r.fd);
+    val[0] = (float)((ax + ay) * (double)scale);
+    return ok;
   }
 };
 
-// gradient (FC.cc:1985-2074)
+// gradient (FC.cc:1985-2074), COMPUTE = 1..4
+template <int COMPUTE>
 struct GradientOp
 {
   static constexpr int NOUT = 1;
   static constexpr bool TESTS_WHEN_ALL = false;
-  bool count_flat; // compute == 1 loops over [1, N-1)
-  int compute;
   const float *f, *xm, *ym;
   float* o;
-  __device__ __forceinline__ bool all_defined(int, bool in_all) const { return in_all; }
-  __device__ __forceinline__ float* out(int, int field, int n) const { return o + (long long)field * n; }
-  __device__ __forceinline__ bool eval(int field, int i, int nx, int n, bool all, float undef, bool want, float* val) const
+  template <bool ALL>
+  struct In
   {
-    const float* ff = f + (long long)field * n;
-    if (compute == 1) {
-      const float fl = ff[i - 1], fr = ff[i + 1];
-      if (!(all || (is_def(fl, undef) && is_def(fr, undef))))
-        return false;
-      if (want)
-        val[0] = (float)half_map_diff(xm[i], fr, fl);
-      return true;
+    float fd, fl, fc, fr, fu, xm, ym;
+  };
+  __device__ __forceinline__ bool all_defined(int, bool in_all) const { return in_all; }
+  __device__ __forceinline__ GradientOp at(int field, int n) const
+  {
+    GradientOp r = *this;
+    const long long off = (long long)field * n;
+    r.f += off;
+    r.o += off;
+    return r;
+  }
+  __host__ __device__ __forceinline__ float* out(int) const { return o; }
+  template <bool ALL>
+  __device__ __forceinline__ In<ALL> load(int i, int nx) const
+  {
+    In<ALL> r;
+    if (COMPUTE != 2) {
+      r.fl = f[i - 1];
+      r.fr = f[i + 1];
+      r.xm = xm[i];
     }
-    const float fd = ff[i - nx], fu = ff[i + nx];
-    if (compute == 2) {
-      if (!(all || (is_def(fd, undef) && is_def(fu, undef))))
-        return false;
-      if (want)
-        val[0] = (float)half_map_diff(ym[i], fu, fd);
-      return true;
+    if (COMPUTE != 1) {
+      r.fd = f[i - nx];
+      r.fu = f[i + nx];
+      r.ym = ym[i];
     }
-    const float fl = ff[i - 1], fr = ff[i + 1];
-    if (!def4(all, fd, fl, fr, fu, undef))
-      return false;
-    if (compute == 3) {
-      if (want) {
-        const float dfdx = (float)half_map_diff(xm[i], fr, fl);
-        const float dfdy = (float)half_map_diff(ym[i], fu, fd);
-        val[0] = dev::absval(dfdx, dfdy);
+    if (COMPUTE == 4)
+      r.fc = f[i];
+    return r;
+  }
+  static constexpr int NFIELD_PTRS = 2, NMAP_PTRS = (COMPUTE <= 2) ? 1 : 2;
+  __host__ void field_ptrs(const void** p) const { p[0] = f, p[1] = o; }
+  __host__ void map_ptrs(const void** p) const { p[0] = (COMPUTE == 2) ? ym : xm, p[1] = ym; }
+  __host__ __device__ __forceinline__ const float* map0() const { return (COMPUTE == 2) ? ym : xm; }
+  struct Raw
+  {
+    float4 x, up, dn, m1, m2;
+  };
+  template <bool ALL, int SNX, int SMAP>
+  __device__ __forceinline__ Raw load_raw(int i_al, int nx, int gi, int ng) const
+  {
+    constexpr int SUP = (4 - SNX) & 3, SDN = SNX;
+    Raw r;
+    if (COMPUTE != 2) {
+      r.x = ldx(f + i_al, gi, ng);
+      r.m1 = ldr<SMAP>(xm + i_al, gi, ng);
+    }
+    if (COMPUTE != 1) {
+      r.up = ldr<SUP>(f + i_al - nx, gi, ng);
+      r.dn = ldr<SDN>(f + i_al + nx, gi, ng);
+      r.m2 = ldr<SMAP>(ym + i_al, gi, ng);
+    }
+    return r;
+  }
+  template <bool ALL, int SNX, int SMAP>
+  __device__ __forceinline__ void assemble(const Raw& r, In<ALL> (&in)[4]) const
+  {
+    constexpr int SUP = (4 - SNX) & 3, SDN = SNX;
+    float x6[6], up[4], dn[4], m1[4], m2[4];
+    if (COMPUTE != 2) {
+      ex6(r.x, x6);
+      ex4<SMAP>(r.m1, m1);
+    }
+    if (COMPUTE != 1) {
+      ex4<SUP>(r.up, up);
+      ex4<SDN>(r.dn, dn);
+      ex4<SMAP>(r.m2, m2);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (COMPUTE != 2) {
+        in[j].fl = x6[j];
+        in[j].fr = x6[j + 2];
+        in[j].xm = m1[j];
       }
-      return true;
+      if (COMPUTE != 1) {
+        in[j].fd = up[j];
+        in[j].fu = dn[j];
+        in[j].ym = m2[j];
+      }
+      if (COMPUTE == 4)
+        in[j].fc = x6[j + 1];
     }
-    const float fc = ff[i];
-    if (!(all || is_def(fc, undef)))
-      return false;
-    if (want) {
-      const float d2fdx = (float)((double)fl - 2.0 * (double)fc + (double)fr);
-      const float d2fdy = (float)((double)fd - 2.0 * (double)fc + (double)fu);
-      const double mx = (double)xm[i], my = (double)ym[i];
+  }
+  template <bool ALL>
+  __device__ __forceinline__ bool eval(const In<ALL>& r, float undef, float* val) const
+  {
+    bool ok = true;
+    if (!ALL) {
+      if (COMPUTE == 1)
+        ok = def2(r.fl, r.fr, undef);
+      else if (COMPUTE == 2)
+        ok = def2(r.fd, r.fu, undef);
+      else if (COMPUTE == 3)
+        ok = def4(r.fd, r.fl, r.fr, r.fu, undef);
+      else
+        ok = def4(r.fd, r.fl, r.fr, r.fu, undef) && is_def(r.fc, undef);
+      if (!ok)
+        return false;
+    }
+    if (COMPUTE == 1) {
+      val[0] = (float)half_map_diff(r.xm, r.fr, r.fl);
+    } else if (COMPUTE == 2) {
+      val[0] = (float)half_map_diff(r.ym, r.fu, r.fd);
+    } else if (COMPUTE == 3) {
+      const float dfdx = (float)half_map_diff(r.xm, r.fr, r.fl);
+      const float dfdy = (float)half_map_diff(r.ym, r.fu, r.fd);
+      val[0] = dev::absval(dfdx, dfdy);
+    } else {
+      const float d2fdx = (float)((double)r.fl - 2.0 * (double)r.fc + (double)r.fr);
+      const float d2fdy = (float)((double)r.fd - 2.0 * (double)r.fc + (double)r.fu);
+      const double mx = (double)r.xm, my = (double)r.ym;
       val[0] = (float)(4.0 * (0.25 * mx * mx * (double)d2fdx + 0.25 * my * my * (double)d2fdy));
     }
-    return true;
+    return ok;
   }
 };
 
@@ -229,28 +599,104 @@ struct JacobianOp
 {
   static constexpr int NOUT = 1;
   static constexpr bool TESTS_WHEN_ALL = false;
-  bool count_flat;
   const float *f1, *f2, *xm, *ym;
   float* o;
-  __device__ __forceinline__ bool all_defined(int, bool in_all) const { return in_all; }
-  __device__ __forceinline__ float* out(int, int field, int n) const { return o + (long long)field * n; }
-  __device__ __forceinline__ bool eval(int field, int i, int nx, int n, bool all, float undef, bool want, float* val) const
+  template <bool ALL>
+  struct In
   {
-    const float* a = f1 + (long long)field * n;
-    const float* b = f2 + (long long)field * n;
-    const float ad = a[i - nx], al = a[i - 1], ar = a[i + 1], au = a[i + nx];
-    const float bd = b[i - nx], bl = b[i - 1], br = b[i + 1], bu = b[i + nx];
-    if (!(def4(all, ad, al, ar, au, undef) && def4(all, bd, bl, br, bu, undef)))
-      return false;
-    if (want) {
-      const float xmi = xm[i], ymi = ym[i];
-      const float df1dx = (float)half_map_diff(xmi, ar, al);
-      const float df1dy = (float)half_map_diff(ymi, au, ad);
-      const float df2dx = (float)half_map_diff(xmi, br, bl);
-      const float df2dy = (float)half_map_diff(ymi, bu, bd);
-      val[0] = df1dx * df2dy - df1dy * df2dx;
+    float ad, al, ar, au, bd, bl, br, bu, xm, ym;
+  };
+  __device__ __forceinline__ bool all_defined(int, bool in_all) const { return in_all; }
+  __device__ __forceinline__ JacobianOp at(int field, int n) const
+  {
+    JacobianOp r = *this;
+    const long long off = (long long)field * n;
+    r.f1 += off;
+    r.f2 += off;
+    r.o += off;
+    return r;
+  }
+  __host__ __device__ __forceinline__ float* out(int) const { return o; }
+  template <bool ALL>
+  __device__ __forceinline__ In<ALL> load(int i, int nx) const
+  {
+    In<ALL> r;
+    r.ad = f1[i - nx];
+    r.al = f1[i - 1];
+    r.ar = f1[i + 1];
+    r.au = f1[i + nx];
+    r.bd = f2[i - nx];
+    r.bl = f2[i - 1];
+    r.br = f2[i + 1];
+    r.bu = f2[i + nx];
+    r.xm = xm[i];
+    r.ym = ym[i];
+    return r;
+  }
+  static constexpr int NFIELD_PTRS = 3, NMAP_PTRS = 2;
+  __host__ void field_ptrs(const void** p) const { p[0] = f1, p[1] = f2, p[2] = o; }
+  __host__ void map_ptrs(const void** p) const { p[0] = xm, p[1] = ym; }
+  __host__ __device__ __forceinline__ const float* map0() const { return xm; }
+  struct Raw
+  {
+    float4 ax, aup, adn, bx, bup, bdn, m1, m2;
+  };
+  template <bool ALL, int SNX, int SMAP>
+  __device__ __forceinline__ Raw load_raw(int i_al, int nx, int gi, int ng) const
+  {
+    constexpr int SUP = (4 - SNX) & 3, SDN = SNX;
+    Raw r;
+    r.ax = ldx(f1 + i_al, gi, ng);
+    r.aup = ldr<SUP>(f1 + i_al - nx, gi, ng);
+    r.adn = ldr<SDN>(f1 + i_al + nx, gi, ng);
+    r.bx = ldx(f2 + i_al, gi, ng);
+    r.bup = ldr<SUP>(f2 + i_al - nx, gi, ng);
+    r.bdn = ldr<SDN>(f2 + i_al + nx, gi, ng);
+    r.m1 = ldr<SMAP>(xm + i_al, gi, ng);
+    r.m2 = ldr<SMAP>(ym + i_al, gi, ng);
+    return r;
+  }
+  template <bool ALL, int SNX, int SMAP>
+  __device__ __forceinline__ void assemble(const Raw& r, In<ALL> (&in)[4]) const
+  {
+    constexpr int SUP = (4 - SNX) & 3, SDN = SNX;
+    float ax[6], aup[4], adn[4], bx[6], bup[4], bdn[4], m1[4], m2[4];
+    ex6(r.ax, ax);
+    ex4<SUP>(r.aup, aup);
+    ex4<SDN>(r.adn, adn);
+    ex6(r.bx, bx);
+    ex4<SUP>(r.bup, bup);
+    ex4<SDN>(r.bdn, bdn);
+    ex4<SMAP>(r.m1, m1);
+    ex4<SMAP>(r.m2, m2);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      in[j].ad = aup[j];
+      in[j].al = ax[j];
+      in[j].ar = ax[j + 2];
+      in[j].au = adn[j];
+      in[j].bd = bup[j];
+      in[j].bl = bx[j];
+      in[j].br = bx[j + 2];
+      in[j].bu = bdn[j];
+      in[j].xm = m1[j];
+      in[j].ym = m2[j];
     }
-    return true;
+  }
+  template <bool ALL>
+  __device__ __forceinline__ bool eval(const In<ALL>& r, float undef, float* val) const
+  {
+    bool ok = true;
+    if (!ALL)
+      ok = def4(r.ad, r.al, r.ar, r.au, undef) && def4(r.bd, r.bl, r.br, r.bu, undef);
+    if (!ok)
+      return false;
+    const float df1dx = (float)half_map_diff(r.xm, r.ar, r.al);
+    const float df1dy = (float)half_map_diff(r.ym, r.au, r.ad);
+    const float df2dx = (float)half_map_diff(r.xm, r.br, r.bl);
+    const float df2dy = (float)half_map_diff(r.ym, r.bu, r.bd);
+    val[0] = df1dx * df2dy - df1dy * df2dx;
+    return ok;
   }
 };
 
@@ -259,23 +705,92 @@ struct GwindOp
 {
   static constexpr int NOUT = 2;
   static constexpr bool TESTS_WHEN_ALL = false;
-  bool count_flat;
   const float *m, *xm, *ym, *fc;
   float *ug, *vg;
-  __device__ __forceinline__ bool all_defined(int, bool in_all) const { return in_all; }
-  __device__ __forceinline__ float* out(int k, int field, int n) const { return (k == 0 ? ug : vg) + (long long)field * n; }
-  __device__ __forceinline__ bool eval(int field, int i, int nx, int n, bool all, float undef, bool want, float* val) const
+  template <bool ALL>
+  struct In
   {
-    const float* mm = m + (long long)field * n;
-    const float md = mm[i - nx], ml = mm[i - 1], mr = mm[i + 1], mu = mm[i + nx];
-    if (!def4(all, md, ml, mr, mu, undef))
-      return false;
-    if (want) {
-      const double f = (double)fc[i];
-      val[0] = (float)(-0.5 * (double)ym[i] * (double)(mu - md) / f);
-      val[1] = (float)(0.5 * (double)xm[i] * (double)(mr - ml) / f);
+    float md, ml, mr, mu, xm, ym, fc;
+  };
+  __device__ __forceinline__ bool all_defined(int, bool in_all) const { return in_all; }
+  __device__ __forceinline__ GwindOp at(int field, int n) const
+  {
+    GwindOp r = *this;
+    const long long off = (long long)field * n;
+    r.m += off;
+    r.ug += off;
+    r.vg += off;
+    return r;
+  }
+  __host__ __device__ __forceinline__ float* out(int k) const { return k == 0 ? ug : vg; }
+  template <bool ALL>
+  __device__ __forceinline__ In<ALL> load(int i, int nx) const
+  {
+    In<ALL> r;
+    r.md = m[i - nx];
+    r.ml = m[i - 1];
+    r.mr = m[i + 1];
+    r.mu = m[i + nx];
+    r.xm = xm[i];
+    r.ym = ym[i];
+    r.fc = fc[i];
+    return r;
+  }
+  static constexpr int NFIELD_PTRS = 3, NMAP_PTRS = 3;
+  __host__ void field_ptrs(const void** p) const { p[0] = m, p[1] = ug, p[2] = vg; }
+  __host__ void map_ptrs(const void** p) const { p[0] = xm, p[1] = ym, p[2] = fc; }
+  __host__ __device__ __forceinline__ const float* map0() const { return xm; }
+  struct Raw
+  {
+    float4 x, up, dn, m1, m2, m3;
+  };
+  template <bool ALL, int SNX, int SMAP>
+  __device__ __forceinline__ Raw load_raw(int i_al, int nx, int gi, int ng) const
+  {
+    constexpr int SUP = (4 - SNX) & 3, SDN = SNX;
+    Raw r;
+    r.x = ldx(m + i_al, gi, ng);
+    r.up = ldr<SUP>(m + i_al - nx, gi, ng);
+    r.dn = ldr<SDN>(m + i_al + nx, gi, ng);
+    r.m1 = ldr<SMAP>(xm + i_al, gi, ng);
+    r.m2 = ldr<SMAP>(ym + i_al, gi, ng);
+    r.m3 = ldr<SMAP>(fc + i_al, gi, ng);
+    return r;
+  }
+  template <bool ALL, int SNX, int SMAP>
+  __device__ __forceinline__ void assemble(const Raw& r, In<ALL> (&in)[4]) const
+  {
+    constexpr int SUP = (4 - SNX) & 3, SDN = SNX;
+    float x6[6], up[4], dn[4], m1[4], m2[4], m3[4];
+    ex6(r.x, x6);
+    ex4<SUP>(r.up, up);
+    ex4<SDN>(r.dn, dn);
+    ex4<SMAP>(r.m1, m1);
+    ex4<SMAP>(r.m2, m2);
+    ex4<SMAP>(r.m3, m3);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      in[j].md = up[j];
+      in[j].ml = x6[j];
+      in[j].mr = x6[j + 2];
+      in[j].mu = dn[j];
+      in[j].xm = m1[j];
+      in[j].ym = m2[j];
+      in[j].fc = m3[j];
     }
-    return true;
+  }
+  template <bool ALL>
+  __device__ __forceinline__ bool eval(const In<ALL>& r, float undef, float* val) const
+  {
+    bool ok = true;
+    if (!ALL)
+      ok = def4(r.md, r.ml, r.mr, r.mu, undef);
+    if (!ok)
+      return false; // also keeps undefined operands out of the double division
+    const double f = (double)r.fc;
+    val[0] = (float)(-0.5 * (double)r.ym * (double)(r.mu - r.md) / f);
+    val[1] = (float)(0.5 * (double)r.xm * (double)(r.mr - r.ml) / f);
+    return ok;
   }
 };
 
@@ -286,52 +801,308 @@ struct TfpOp
 {
   static constexpr int NOUT = 1;
   static constexpr bool TESTS_WHEN_ALL = true;
-  bool count_flat;
   const float *tx, *ad, *xm, *ym;
   const unsigned long long* pass1_counters;
   float* o;
-  __device__ __forceinline__ bool all_defined(int field, bool) const { return pass1_counters[field] == 0; }
-  __device__ __forceinline__ float* out(int, int field, int n) const { return o + (long long)field * n; }
-  __device__ __forceinline__ bool eval(int field, int i, int nx, int n, bool all, float undef, bool want, float* val) const
+  template <bool ALL>
+  struct In
   {
-    const float* t = tx + (long long)field * n;
-    const float* a = ad + (long long)field * n;
-    const float td = t[i - nx], tl = t[i - 1], tr = t[i + 1], tu = t[i + nx];
-    const float adn = a[i - nx], al = a[i - 1], ac = a[i], ar = a[i + 1], au = a[i + nx];
-    if (!(def4(all, td, tl, tr, tu, undef) && def4(all, adn, al, ar, au, undef) && (all || is_def(ac, undef))))
-      return false;
-    if (!(ac != 0)) // tested even when allDefined (FC.cc:2292)
-      return false;
-    if (want) {
-      const float xmi = xm[i], ymi = ym[i];
-      const float dadx = (float)half_map_diff(xmi, ar, al);
-      const float dady = (float)half_map_diff(ymi, au, adn);
-      const float dtdxa = (float)(half_map_diff(xmi, tr, tl) / (double)ac);
-      const float dtdya = (float)(half_map_diff(ymi, tu, td) / (double)ac);
-      val[0] = -(dadx * dtdxa + dady * dtdya);
+    float td, tl, tr, tu, adn, al, ac, ar, au, xm, ym;
+  };
+  __device__ __forceinline__ bool all_defined(int field, bool) const { return pass1_counters[field] == 0; }
+  __device__ __forceinline__ TfpOp at(int field, int n) const
+  {
+    TfpOp r = *this;
+    const long long off = (long long)field * n;
+    r.tx += off;
+    r.ad += off;
+    r.o += off;
+    return r;
+  }
+  __host__ __device__ __forceinline__ float* out(int) const { return o; }
+  template <bool ALL>
+  __device__ __forceinline__ In<ALL> load(int i, int nx) const
+  {
+    In<ALL> r;
+    r.td = tx[i - nx];
+    r.tl = tx[i - 1];
+    r.tr = tx[i + 1];
+    r.tu = tx[i + nx];
+    r.adn = ad[i - nx];
+    r.al = ad[i - 1];
+    r.ac = ad[i];
+    r.ar = ad[i + 1];
+    r.au = ad[i + nx];
+    r.xm = xm[i];
+    r.ym = ym[i];
+    return r;
+  }
+  static constexpr int NFIELD_PTRS = 3, NMAP_PTRS = 2;
+  __host__ void field_ptrs(const void** p) const { p[0] = tx, p[1] = ad, p[2] = o; }
+  __host__ void map_ptrs(const void** p) const { p[0] = xm, p[1] = ym; }
+  __host__ __device__ __forceinline__ const float* map0() const { return xm; }
+  struct Raw
+  {
+    float4 t, tup, tdn, a, aup, adn, m1, m2;
+  };
+  template <bool ALL, int SNX, int SMAP>
+  __device__ __forceinline__ Raw load_raw(int i_al, int nx, int gi, int ng) const
+  {
+    constexpr int SUP = (4 - SNX) & 3, SDN = SNX;
+    Raw r;
+    r.t = ldx(tx + i_al, gi, ng);
+    r.tup = ldr<SUP>(tx + i_al - nx, gi, ng);
+    r.tdn = ldr<SDN>(tx + i_al + nx, gi, ng);
+    r.a = ldx(ad + i_al, gi, ng);
+    r.aup = ldr<SUP>(ad + i_al - nx, gi, ng);
+    r.adn = ldr<SDN>(ad + i_al + nx, gi, ng);
+    r.m1 = ldr<SMAP>(xm + i_al, gi, ng);
+    r.m2 = ldr<SMAP>(ym + i_al, gi, ng);
+    return r;
+  }
+  template <bool ALL, int SNX, int SMAP>
+  __device__ __forceinline__ void assemble(const Raw& r, In<ALL> (&in)[4]) const
+  {
+    constexpr int SUP = (4 - SNX) & 3, SDN = SNX;
+    float t6[6], tup[4], tdn[4], a6[6], aup[4], adn4[4], m1[4], m2[4];
+    ex6(r.t, t6);
+    ex4<SUP>(r.tup, tup);
+    ex4<SDN>(r.tdn, tdn);
+    ex6(r.a, a6);
+    ex4<SUP>(r.aup, aup);
+    ex4<SDN>(r.adn, adn4);
+    ex4<SMAP>(r.m1, m1);
+    ex4<SMAP>(r.m2, m2);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      in[j].td = tup[j];
+      in[j].tl = t6[j];
+      in[j].tr = t6[j + 2];
+      in[j].tu = tdn[j];
+      in[j].adn = aup[j];
+      in[j].al = a6[j];
+      in[j].ac = a6[j + 1];
+      in[j].ar = a6[j + 2];
+      in[j].au = adn4[j];
+      in[j].xm = m1[j];
+      in[j].ym = m2[j];
     }
-    return true;
+  }
+  template <bool ALL>
+  __device__ __forceinline__ bool eval(const In<ALL>& r, float undef, float* val) const
+  {
+    bool ok = true;
+    if (!ALL)
+      ok = def4(r.td, r.tl, r.tr, r.tu, undef) && def4(r.adn, r.al, r.ar, r.au, undef) && is_def(r.ac, undef);
+    ok = ok && (r.ac != 0); // tested even when allDefined (FC.cc:2292)
+    if (!ok)
+      return false;
+    const float dadx = (float)half_map_diff(r.xm, r.ar, r.al);
+    const float dady = (float)half_map_diff(r.ym, r.au, r.adn);
+    const float dtdxa = (float)(half_map_diff(r.xm, r.tr, r.tl) / (double)r.ac);
+    const float dtdya = (float)(half_map_diff(r.ym, r.tu, r.td) / (double)r.ac);
+    val[0] = -(dadx * dtdxa + dady * dtdya);
+    return ok;
   }
 };
 
+// ---- the float4 kernel ------------------------------------------------------------------------------------
+// Same flat loop, four consecutive points per lane, 30 producing lanes per warp, SV_UNROLL warp steps
+// per CTA pass: 16-byte loads and stores throughout (the scalar kernel above is LSU-issue bound: 7
+// memory instructions per point, stall reason lg_throttle).  The groups start at the first point of
+// the range whose address is 16-byte aligned in the per-field arrays; the < 4 points before it and
+// the < 4 points after the last whole group go through the scalar code, in the field's first CTA.
+constexpr int SV_UNROLL = 2;
+constexpr int SV_WARPS = ST_THREADS / 32;
+constexpr int SV_LANES = 30;                                      // producing lanes per warp
+constexpr int SV_CHUNK_GROUPS = SV_WARPS * SV_UNROLL * SV_LANES;  // groups per CTA
+
+template <class Op, bool ALL>
+__device__ __forceinline__ void stencil_vec_group(const Op& op, int i0, const typename Op::template In<ALL> (&in)[4], float undef, unsigned& nundef)
+{
+  float r[Op::NOUT][4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    float val[Op::NOUT];
+    const bool ok = op.template eval<ALL>(in[j], undef, val);
+    if (!ok)
+      nundef += 1;
+#pragma unroll
+    for (int k = 0; k < Op::NOUT; ++k)
+      r[k][j] = ok ? val[k] : undef;
+  }
+#pragma unroll
+  for (int k = 0; k < Op::NOUT; ++k)
+    *reinterpret_cast<float4*>(op.out(k) + i0) = make_float4(r[k][0], r[k][1], r[k][2], r[k][3]);
+}
+
+template <class Op, bool ALL, int SNX, int SMAP>
+__device__ __forceinline__ unsigned stencil_vec_body(const Op& op, const StencilGeom& g, int chunk, int i_al, int ngroups)
+{
+  typedef typename Op::template In<ALL> In;
+  const int nx = g.nx;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int units = (ngroups + SV_LANES - 1) / SV_LANES; // warp steps in this field
+  const int wu0 = chunk * (SV_WARPS * SV_UNROLL) + warp;
+  unsigned nundef = 0;
+  // every branch below is warp-uniform (the assembly shuffles).  Phase 1 issues every load of the
+  // CTA pass, phase 2 exchanges neighbours between lanes, computes and stores.
+  typename Op::Raw raw[SV_UNROLL];
+  if (units > 0) {
+#pragma unroll
+  for (int u = 0; u < SV_UNROLL; ++u) {
+    const int wu = min(wu0 + u * SV_WARPS, units - 1); // past the end: reload the last step, unused
+    raw[u] = op.template load_raw<ALL, SNX, SMAP>(i_al, nx, wu * SV_LANES - 1 + lane, ngroups);
+  }
+#pragma unroll
+  for (int u = 0; u < SV_UNROLL; ++u) {
+    const int wu = wu0 + u * SV_WARPS;
+    if (wu < units) {
+      const int gi = wu * SV_LANES - 1 + lane;
+      In in[4];
+      op.template assemble<ALL, SNX, SMAP>(raw[u], in);
+      if (lane >= 1 && lane <= SV_LANES && gi < ngroups)
+        stencil_vec_group<Op, ALL>(op, i_al + 4 * gi, in, g.undef, nundef);
+    }
+  }
+  }
+  if (chunk == 0) { // the unaligned head and tail points of the range
+    const int tail0 = i_al + 4 * ngroups;
+    int idx = -1;
+    if ((int)threadIdx.x < i_al - g.lo)
+      idx = g.lo + threadIdx.x;
+    else if (threadIdx.x >= 32 && (int)threadIdx.x - 32 < g.hi - tail0)
+      idx = tail0 + (threadIdx.x - 32);
+    if (idx >= 0)
+      nundef += stencil_point<Op, ALL>(op, op.template load<ALL>(idx, nx), idx, g.undef);
+  }
+  return nundef;
+}
+
+template <class Op, bool ALL, int SNX>
+__device__ __forceinline__ unsigned stencil_vec_dispatch(const Op& op, const StencilGeom& g, int chunk, int i_al, int ngroups, int smap)
+{
+  switch (smap) {
+  case 0:
+    return stencil_vec_body<Op, ALL, SNX, 0>(op, g, chunk, i_al, ngroups);
+  case 1:
+    return stencil_vec_body<Op, ALL, SNX, 1>(op, g, chunk, i_al, ngroups);
+  case 2:
+    return stencil_vec_body<Op, ALL, SNX, 2>(op, g, chunk, i_al, ngroups);
+  default:
+    return stencil_vec_body<Op, ALL, SNX, 3>(op, g, chunk, i_al, ngroups);
+  }
+}
+
+template <class Op, int SNX>
+__global__ void __launch_bounds__(ST_THREADS) stencil_vec_kernel(const Op op0, const StencilGeom g)
+{
+  const int field = blockIdx.z * g.group + blockIdx.x, chunk = blockIdx.y + g.chunk_base;
+  if (field >= g.nfields)
+    return;
+  const bool all = op0.all_defined(field, g.meta[field].all != 0);
+  const Op op = op0.at(field, g.n);
+  // element alignment of this field (identical in all its arrays: checked by the host) and of the maps
+  const int a = (int)((reinterpret_cast<uintptr_t>(op.out(0)) >> 2) & 3);
+  int i_al = g.lo + ((4 - ((a + g.lo) & 3)) & 3);
+  if (i_al > g.hi)
+    i_al = g.hi;
+  const int ngroups = (g.hi - i_al) >> 2;
+  const int smap = (int)(((reinterpret_cast<uintptr_t>(op.map0()) >> 2) + i_al) & 3);
+  unsigned nundef;
+  if (all)
+    nundef = stencil_vec_dispatch<Op, true, SNX>(op, g, chunk, i_al, ngroups, smap);
+  else
+    nundef = stencil_vec_dispatch<Op, false, SNX>(op, g, chunk, i_al, ngroups, smap);
+  __shared__ unsigned s_count;
+  if (threadIdx.x == 0)
+    s_count = 0;
+  __syncthreads();
+  nundef = __reduce_add_sync(0xffffffffu, nundef);
+  if ((threadIdx.x & 31) == 0 && nundef)
+    atomicAdd(&s_count, nundef);
+  __syncthreads();
+  if (threadIdx.x == 0 && s_count)
+    atomicAdd(g.counters + field, (unsigned long long)s_count);
+}
+
+// every per-field array on the same 4-byte-multiple offset from a 16-byte boundary, every map likewise
 template <class Op>
-bool launch_stencil(Call& call, const Op& op, int nx, int ny, int nfields, float undef, const FieldMeta* meta, unsigned long long* counters)
+bool stencil_vec_ok(const Op& op, int nx, int ny, int nfields)
+{
+  const void* fp[8];
+  const void* mp[4];
+  op.field_ptrs(fp);
+  op.map_ptrs(mp);
+  for (int k = 0; k < Op::NFIELD_PTRS; ++k)
+    if ((reinterpret_cast<uintptr_t>(fp[k]) & 3) || (reinterpret_cast<uintptr_t>(fp[k]) & 15) != (reinterpret_cast<uintptr_t>(fp[0]) & 15))
+      return false;
+  for (int k = 0; k < Op::NMAP_PTRS; ++k)
+    if ((reinterpret_cast<uintptr_t>(mp[k]) & 3) || (reinterpret_cast<uintptr_t>(mp[k]) & 15) != (reinterpret_cast<uintptr_t>(mp[0]) & 15))
+      return false;
+  return (long long)nx * ny >= 64;
+}
+
+template <class Op>
+void launch_stencil_vec(cudaStream_t stream, const Op& op, const StencilGeom& g, dim3 grid)
+{
+  switch (g.nx & 3) {
+  case 0:
+    stencil_vec_kernel<Op, 0><<<grid, ST_THREADS, 0, stream>>>(op, g);
+    break;
+  case 1:
+    stencil_vec_kernel<Op, 1><<<grid, ST_THREADS, 0, stream>>>(op, g);
+    break;
+  case 2:
+    stencil_vec_kernel<Op, 2><<<grid, ST_THREADS, 0, stream>>>(op, g);
+    break;
+  default:
+    stencil_vec_kernel<Op, 3><<<grid, ST_THREADS, 0, stream>>>(op, g);
+    break;
+  }
+}
+
+// main kernel over the reference's flat range, then the border ring
+template <class Op>
+bool launch_stencil(Call& call, const Op& op, int nx, int ny, int nfields, float undef, const FieldMeta* meta, unsigned long long* counters,
+                    bool flat_range = false)
 {
   StencilGeom g;
   g.nx = nx;
   g.ny = ny;
   g.n = nx * ny;
   g.nfields = nfields;
-  g.chunks = (g.n + ST_THREADS * ST_UNROLL - 1) / (ST_THREADS * ST_UNROLL);
+  g.lo = flat_range ? 1 : nx;
+  g.hi = flat_range ? g.n - 1 : g.n - nx;
   g.undef = undef;
   g.meta = meta;
   g.counters = counters;
-  const long long grid = (long long)g.chunks * nfields;
-  if (grid > 0x7fffffffLL) {
-    set_error("fcb200: batch too large for one launch (%lld CTAs)", grid);
+  static const int env_group = getenv("FCB200_ST_GROUP") ? atoi(getenv("FCB200_ST_GROUP")) : 0; // tuning aid
+  g.group = env_group > 0 ? env_group : ST_GROUP;
+  if (g.group > nfields)
+    g.group = nfields;
+  const int groups = (nfields + g.group - 1) / g.group;
+  if (groups > 65535) {
+    set_error("fcb200: batch too large for one launch (%d fields)", nfields);
     return false;
   }
-  stencil_kernel<Op><<<(unsigned)grid, ST_THREADS, 0, call.stream()>>>(op, g);
+  const bool vec = stencil_vec_ok(op, nx, ny, nfields);
+  const int per_chunk = vec ? SV_CHUNK_GROUPS * 4 : ST_THREADS * ST_UNROLL;
+  const int total_chunks = (g.hi - g.lo + per_chunk - 1) / per_chunk;
+  // gridDim.y <= 65535: a longer range takes several launches
+  for (int c0 = 0; c0 < total_chunks; c0 += 65535) {
+    g.chunk_base = c0;
+    g.chunks = total_chunks - c0 < 65535 ? total_chunks - c0 : 65535;
+    const dim3 grid((unsigned)g.group, (unsigned)g.chunks, (unsigned)groups);
+    if (vec)
+      launch_stencil_vec(call.stream(), op, g, grid);
+    else
+      stencil_kernel<Op><<<grid, ST_THREADS, 0, call.stream()>>>(op, g);
+    count_launch();
+  }
+  const int ring = 2 * nx + 2 * (ny - 2);
+  const dim3 fe_grid((ring + FE_THREADS - 1) / FE_THREADS, nfields < 4096 ? nfields : 4096);
+  fill_edges_kernel<<<fe_grid, FE_THREADS, 0, call.stream()>>>(op.out(0), Op::NOUT > 1 ? op.out(1) : nullptr, nx, ny, nfields);
   count_launch();
   return true;
 }
@@ -370,106 +1141,191 @@ Finalizer flags_from_counters(int* fDefined, int nfields, unsigned long long den
 // separable 2-D filter with these boundary rules (the flat-loop wrap never survives, FC.cc:2117-2120):
 //   x pass: out(x,y) = filtered for 1 <= x <= nx-2 (EVERY row), copy for x = 0, nx-1
 //   y pass: out(x,y) = filtered for 1 <= y <= ny-2 (EVERY column), copy for y = 0, ny-1
-// All four passes run on one shared-memory tile with a halo of 2: each pass invalidates one more ring
-// of the halo, and after four passes exactly the tile interior is final.  8 B/point of HBM traffic
-// instead of the reference's nine array sweeps.
 //   all-defined branch: s = +0.25 then -0.25; f + s*(fl + fr - 2.*f): float sum, the rest in double.
 //   masked branch: weights 0.25/0 from 3-point definedness of the ORIGINAL field, BOTH iterations use
 //   +0.25 (the `s = -0.25` update is dead, FC.cc:2136-2168), all-float arithmetic.
-constexpr int SH_TX = 64, SH_TY = 32, SH_H = 2;
-constexpr int SH_EX = SH_TX + 2 * SH_H, SH_EY = SH_TY + 2 * SH_H;
-constexpr int SH_THREADS = 256;
+//
+// All four passes run in REGISTERS: a thread owns W adjacent columns (W = 4: one float4 per row when
+// every row is 16-byte aligned; W = 1 otherwise) and marches down a band of rows.  x passes take their
+// neighbour columns from the adjacent lanes by warp shuffle; y passes use a three-row window of the
+// previous pass kept in registers (the pipeline lags two rows behind the load).  A warp strip of 32*W
+// loaded columns yields (32 - 2*HL)*W final columns: the HL outermost lanes on each side are halo
+// (the result at column x depends on the input columns x-2 .. x+2); a band of RB rows loads RB+4.
+// The field is read once and written once: 8 B/point.
+constexpr int SH_WARPS = 4;
+constexpr int SH_PF = 4; // rows in flight per thread
 
-__global__ void __launch_bounds__(SH_THREADS) shapiro2_kernel(const float* __restrict__ fin, float* __restrict__ fout, int nx, int ny, int tiles_x,
-                                                              int tiles_y, const FieldMeta* meta, float undef)
+template <int W>
+struct ShapiroGeom
 {
-  __shared__ float bufA[SH_EY][SH_EX + 1];
-  __shared__ float bufB[SH_EY][SH_EX + 1];
-  __shared__ unsigned char wmask[SH_EY][SH_EX + 1]; // bit 0: x weight is 0.25, bit 1: y weight is 0.25
+  static constexpr int HL = (W == 4) ? 1 : 2;           // halo lanes per side
+  static constexpr int USEFUL = (32 - 2 * HL) * W;      // output columns per warp strip
+};
 
-  const int tiles = tiles_x * tiles_y;
-  const int field = blockIdx.x / tiles;
-  const int t = blockIdx.x - field * tiles;
-  const int ty = t / tiles_x, tx = t - ty * tiles_x;
-  const int x0 = tx * SH_TX - SH_H, y0 = ty * SH_TY - SH_H; // global coordinates of cell (0,0)
-  const bool all = meta[field].all != 0;
+template <int W, bool ALL>
+__device__ __forceinline__ void shapiro_xpass(const float (&f)[W], float (&out)[W], double s, unsigned wbits, unsigned copybits)
+{
+  const float left = __shfl_up_sync(0xffffffffu, f[W - 1], 1);
+  const float right = __shfl_down_sync(0xffffffffu, f[0], 1);
+#pragma unroll
+  for (int j = 0; j < W; ++j) {
+    const float lo = (j == 0) ? left : f[j - 1];
+    const float hi = (j == W - 1) ? right : f[j + 1];
+    float r;
+    if (ALL) {
+      r = (float)fma(s, fma(-2.0, (double)f[j], (double)(lo + hi)), (double)f[j]);
+    } else {
+      const float w = ((wbits >> j) & 1u) ? 0.25f : 0.f;
+      r = f[j] + w * (lo + hi - 2.f * f[j]);
+    }
+    out[j] = ((copybits >> j) & 1u) ? f[j] : r;
+  }
+}
+
+template <int W, bool ALL>
+__device__ __forceinline__ void shapiro_ypass(const float (&lo)[W], const float (&f)[W], const float (&hi)[W], float (&out)[W], double s,
+                                              unsigned wbits, bool copy)
+{
+#pragma unroll
+  for (int j = 0; j < W; ++j) {
+    float r;
+    if (ALL) {
+      r = (float)fma(s, fma(-2.0, (double)f[j], (double)(lo[j] + hi[j])), (double)f[j]);
+    } else {
+      const float w = ((wbits >> j) & 1u) ? 0.25f : 0.f;
+      r = f[j] + w * (lo[j] + hi[j] - 2.f * f[j]);
+    }
+    out[j] = copy ? f[j] : r;
+  }
+}
+
+template <int W, bool ALL>
+__device__ __forceinline__ void shapiro_band(const float* __restrict__ src, float* __restrict__ dst, int nx, int ny, int x0, int r0, int r1, float undef)
+{
+  constexpr int HL = ShapiroGeom<W>::HL;
+  const int lane = threadIdx.x & 31;
+  const bool col_ok = x0 >= 0 && x0 + W <= nx; // W = 4: nx % 4 == 0 and x0 % 4 == 0, a float4 is entirely in or out
+  const bool store_lane = col_ok && lane >= HL && lane < 32 - HL;
+  unsigned copybits = 0; // columns 0 and nx-1 are copied by the x passes
+#pragma unroll
+  for (int j = 0; j < W; ++j)
+    if (x0 + j <= 0 || x0 + j >= nx - 1)
+      copybits |= 1u << j;
+
+  const int rbeg = r0 - 2, rend = r1 + 2; // rows marched: [rbeg, rend), stores lag two rows
+  auto load_row = [&](int r, float (&q)[W]) {
+    if (col_ok && r >= 0 && r < ny && r < rend) {
+      const float* p = src + (long long)r * nx + x0;
+      if (W == 4) {
+        const float4 t = *reinterpret_cast<const float4*>(p);
+        q[0] = t.x;
+        q[W > 1 ? 1 : 0] = t.y;
+        q[W > 2 ? 2 : 0] = t.z;
+        q[W > 3 ? 3 : 0] = t.w;
+      } else {
+        q[0] = *p;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < W; ++j)
+        q[j] = 0.f;
+    }
+  };
+
+  float q[SH_PF][W];
+#pragma unroll
+  for (int k = 0; k < SH_PF; ++k)
+    load_row(rbeg + k, q[k]);
+
+  float a0[W] = {}, a1[W] = {}, c0[W] = {}, c1[W] = {};
+  unsigned d0 = 0, d1 = 0;       // definedness bits of the original rows r-2, r-1
+  unsigned mx_prev = 0;          // x weights of row r-1
+  unsigned my_prev = 0;          // y weights of row r-2
+
+  for (int rb = rbeg; rb < rend; rb += SH_PF) {
+    float cur[SH_PF][W];
+#pragma unroll
+    for (int k = 0; k < SH_PF; ++k)
+#pragma unroll
+      for (int j = 0; j < W; ++j)
+        cur[k][j] = q[k][j];
+#pragma unroll
+    for (int k = 0; k < SH_PF; ++k)
+      load_row(rb + SH_PF + k, q[k]);
+#pragma unroll
+    for (int k = 0; k < SH_PF; ++k) {
+      const int r = rb + k;
+      if (r >= rend)
+        break;
+      const float(&f)[W] = cur[k];
+      unsigned d2 = 0, mx = 0, my = 0;
+      if (!ALL) {
+        if (r >= 0 && r < ny) {
+#pragma unroll
+          for (int j = 0; j < W; ++j)
+            if (is_def(f[j], undef))
+              d2 |= 1u << j;
+        }
+        const unsigned dl = (__shfl_up_sync(0xffffffffu, d2, 1) >> (W - 1)) & 1u;
+        const unsigned dr = __shfl_down_sync(0xffffffffu, d2, 1) & 1u;
+        const unsigned ext = dl | (d2 << 1) | (dr << (W + 1));
+        mx = ext & (ext >> 1) & (ext >> 2);
+        my = d0 & d1 & d2;
+      }
+      // iteration 1: x pass on row r, y pass on row r-1
+      float a2[W], b[W], c2[W], d[W];
+      shapiro_xpass<W, ALL>(f, a2, 0.25, mx, copybits);
+      shapiro_ypass<W, ALL>(a0, a1, a2, b, 0.25, my, r - 1 <= 0 || r - 1 >= ny - 1);
+      // iteration 2: x pass on row r-1, y pass on row r-2
+      shapiro_xpass<W, ALL>(b, c2, -0.25, mx_prev, copybits);
+      shapiro_ypass<W, ALL>(c0, c1, c2, d, -0.25, my_prev, r - 2 <= 0 || r - 2 >= ny - 1);
+      const int ro = r - 2;
+      if (store_lane && ro >= r0 && ro < r1) {
+        float* p = dst + (long long)ro * nx + x0;
+        if (W == 4)
+          *reinterpret_cast<float4*>(p) = make_float4(d[0], d[W > 1 ? 1 : 0], d[W > 2 ? 2 : 0], d[W > 3 ? 3 : 0]);
+        else
+          *p = d[0];
+      }
+#pragma unroll
+      for (int j = 0; j < W; ++j) {
+        a0[j] = a1[j];
+        a1[j] = a2[j];
+        c0[j] = c1[j];
+        c1[j] = c2[j];
+      }
+      d0 = d1;
+      d1 = d2;
+      mx_prev = mx;
+      my_prev = my;
+    }
+  }
+}
+
+template <int W>
+__global__ void __launch_bounds__(SH_WARPS * 32) shapiro2_kernel(const float* __restrict__ fin, float* __restrict__ fout, int nx, int ny, int strips,
+                                                                int bands, int rows_per_band, const FieldMeta* meta, float undef)
+{
+  constexpr int HL = ShapiroGeom<W>::HL;
+  constexpr int USEFUL = ShapiroGeom<W>::USEFUL;
+  const int strip_groups = (strips + SH_WARPS - 1) / SH_WARPS;
+  const int per_field = strip_groups * bands;
+  const int field = blockIdx.x / per_field;
+  const int t = blockIdx.x - field * per_field;
+  const int band = t / strip_groups;
+  const int strip = (t - band * strip_groups) * SH_WARPS + (threadIdx.x >> 5);
+  if (strip >= strips)
+    return; // whole warp
+  const int lane = threadIdx.x & 31;
+  const int x0 = strip * USEFUL + (lane - HL) * W;
+  const int r0 = band * rows_per_band;
+  const int r1 = min(r0 + rows_per_band, ny);
   const float* src = fin + (long long)field * nx * ny;
   float* dst = fout + (long long)field * nx * ny;
-
-  // load: out-of-grid cells get 0 and are never consumed by an in-grid filter point
-  for (int c = threadIdx.x; c < SH_EX * SH_EY; c += SH_THREADS) {
-    const int ly = c / SH_EX, lx = c - ly * SH_EX;
-    const int gx = x0 + lx, gy = y0 + ly;
-    float v = 0.f;
-    if (gx >= 0 && gx < nx && gy >= 0 && gy < ny)
-      v = src[(long long)gy * nx + gx];
-    bufA[ly][lx] = v;
-  }
-  __syncthreads();
-
-  if (!all) {
-    for (int c = threadIdx.x; c < SH_EX * SH_EY; c += SH_THREADS) {
-      const int ly = c / SH_EX, lx = c - ly * SH_EX;
-      unsigned char m = 0;
-      const bool dc = is_def(bufA[ly][lx], undef);
-      if (lx >= 1 && lx < SH_EX - 1 && dc && is_def(bufA[ly][lx - 1], undef) && is_def(bufA[ly][lx + 1], undef))
-        m |= 1;
-      if (ly >= 1 && ly < SH_EY - 1 && dc && is_def(bufA[ly - 1][lx], undef) && is_def(bufA[ly + 1][lx], undef))
-        m |= 2;
-      wmask[ly][lx] = m;
-    }
-    __syncthreads();
-  }
-
-  float(*cur)[SH_EX + 1] = bufA;
-  float(*nxt)[SH_EX + 1] = bufB;
-#pragma unroll 1
-  for (int pass = 0; pass < 4; ++pass) {
-    const bool xpass = (pass & 1) == 0;
-    const float s = (pass < 2) ? 0.25f : -0.25f;
-    for (int c = threadIdx.x; c < SH_EX * SH_EY; c += SH_THREADS) {
-      const int ly = c / SH_EX, lx = c - ly * SH_EX;
-      const int gx = x0 + lx, gy = y0 + ly;
-      const float f = cur[ly][lx];
-      float r = f;
-      const bool in_grid = gx >= 0 && gx < nx && gy >= 0 && gy < ny;
-      bool filt;
-      float lo = 0.f, hi = 0.f;
-      if (xpass) {
-        filt = in_grid && gx >= 1 && gx <= nx - 2 && lx >= 1 && lx < SH_EX - 1;
-        if (filt) {
-          lo = cur[ly][lx - 1];
-          hi = cur[ly][lx + 1];
-        }
-      } else {
-        filt = in_grid && gy >= 1 && gy <= ny - 2 && ly >= 1 && ly < SH_EY - 1;
-        if (filt) {
-          lo = cur[ly - 1][lx];
-          hi = cur[ly + 1][lx];
-        }
-      }
-      if (filt) {
-        if (all) {
-          r = (float)((double)f + (double)s * ((double)(lo + hi) - 2. * (double)f));
-        } else {
-          const float w = (wmask[ly][lx] & (xpass ? 1 : 2)) ? 0.25f : 0.f;
-          r = f + w * (lo + hi - 2.f * f);
-        }
-      }
-      nxt[ly][lx] = r;
-    }
-    __syncthreads();
-    float(*tmp)[SH_EX + 1] = cur;
-    cur = nxt;
-    nxt = tmp;
-  }
-
-  for (int c = threadIdx.x; c < SH_TX * SH_TY; c += SH_THREADS) {
-    const int ly = c / SH_TX, lx = c - ly * SH_TX;
-    const int gx = tx * SH_TX + lx, gy = ty * SH_TY + ly;
-    if (gx < nx && gy < ny)
-      dst[(long long)gy * nx + gx] = cur[ly + SH_H][lx + SH_H];
-  }
+  if (meta[field].all != 0)
+    shapiro_band<W, true>(src, dst, nx, ny, x0, r0, r1, undef);
+  else
+    shapiro_band<W, false>(src, dst, nx, ny, x0, r0, r1, undef);
 }
 
 } // namespace
@@ -481,19 +1337,20 @@ using namespace fcb200;
 namespace {
 
 template <class Op>
-int run_stencil(Call& call, const Op& op, int nx, int ny, int nfields, int* fDefined, float undef, unsigned long long denom)
+int run_stencil(Call& call, const Op& op, int nx, int ny, int nfields, int* fDefined, float undef, unsigned long long denom, bool flat_range = false)
 {
   const FieldMeta* meta = flags_to_meta(call, fDefined, nfields);
   unsigned long long* counters = call.counters(nfields);
   if (!call.ok())
     return -1;
-  if (!launch_stencil(call, op, nx, ny, nfields, undef, meta, counters))
+  if (!launch_stencil(call, op, nx, ny, nfields, undef, meta, counters, flat_range))
     return -1;
   return call.finish(flags_from_counters(fDefined, nfields, denom));
 }
 
-int vortdiv(int mode, int nx, int ny, int nfields, const float* u, const float* v, const float* xmapr, const float* ymapr, const float* fcoriolis,
-            float* out, int* fDefined, float undef)
+template <int MODE>
+int vortdiv(int nx, int ny, int nfields, const float* u, const float* v, const float* xmapr, const float* ymapr, const float* fcoriolis, float* out,
+            int* fDefined, float undef)
 {
   if (nx < 3 || ny < 3)
     return 0;
@@ -501,14 +1358,12 @@ int vortdiv(int mode, int nx, int ny, int nfields, const float* u, const float* 
     return -1;
   const size_t n = (size_t)nx * ny;
   Call call;
-  VortDivOp op;
-  op.count_flat = false;
-  op.mode = mode;
+  VortDivOp<MODE> op;
   op.u = call.in(u, n * nfields);
   op.v = call.in(v, n * nfields);
   op.xm = call.in(xmapr, n);
   op.ym = call.in(ymapr, n);
-  op.fc = (mode == 1) ? call.in(fcoriolis, n) : nullptr;
+  op.fc = (MODE == 1) ? call.in(fcoriolis, n) : nullptr;
   op.o = call.out(out, n * nfields);
   return run_stencil(call, op, nx, ny, nfields, fDefined, undef, n - 2 * (size_t)nx);
 }
@@ -520,33 +1375,33 @@ extern "C" {
 int fcb200_relvort_batched(int nx, int ny, int nfields, const float* u, const float* v, const float* xmapr, const float* ymapr, float* rvort,
                            int* fDefined, float undef)
 {
-  return vortdiv(0, nx, ny, nfields, u, v, xmapr, ymapr, nullptr, rvort, fDefined, undef);
+  return vortdiv<0>(nx, ny, nfields, u, v, xmapr, ymapr, nullptr, rvort, fDefined, undef);
 }
 int fcb200_relvort(int nx, int ny, const float* u, const float* v, const float* xmapr, const float* ymapr, float* rvort, int* fDefined, float undef)
 {
-  return vortdiv(0, nx, ny, 1, u, v, xmapr, ymapr, nullptr, rvort, fDefined, undef);
+  return vortdiv<0>(nx, ny, 1, u, v, xmapr, ymapr, nullptr, rvort, fDefined, undef);
 }
 
 int fcb200_absvort_batched(int nx, int ny, int nfields, const float* u, const float* v, const float* xmapr, const float* ymapr,
                            const float* fcoriolis, float* avort, int* fDefined, float undef)
 {
-  return vortdiv(1, nx, ny, nfields, u, v, xmapr, ymapr, fcoriolis, avort, fDefined, undef);
+  return vortdiv<1>(nx, ny, nfields, u, v, xmapr, ymapr, fcoriolis, avort, fDefined, undef);
 }
 int fcb200_absvort(int nx, int ny, const float* u, const float* v, const float* xmapr, const float* ymapr, const float* fcoriolis, float* avort,
                    int* fDefined, float undef)
 {
-  return vortdiv(1, nx, ny, 1, u, v, xmapr, ymapr, fcoriolis, avort, fDefined, undef);
+  return vortdiv<1>(nx, ny, 1, u, v, xmapr, ymapr, fcoriolis, avort, fDefined, undef);
 }
 
 int fcb200_divergence_batched(int nx, int ny, int nfields, const float* u, const float* v, const float* xmapr, const float* ymapr, float* diverg,
                               int* fDefined, float undef)
 {
-  return vortdiv(2, nx, ny, nfields, u, v, xmapr, ymapr, nullptr, diverg, fDefined, undef);
+  return vortdiv<2>(nx, ny, nfields, u, v, xmapr, ymapr, nullptr, diverg, fDefined, undef);
 }
 int fcb200_divergence(int nx, int ny, const float* u, const float* v, const float* xmapr, const float* ymapr, float* diverg, int* fDefined,
                       float undef)
 {
-  return vortdiv(2, nx, ny, 1, u, v, xmapr, ymapr, nullptr, diverg, fDefined, undef);
+  return vortdiv<2>(nx, ny, 1, u, v, xmapr, ymapr, nullptr, diverg, fDefined, undef);
 }
 
 int fcb200_advection_batched(int nx, int ny, int nfields, const float* f, const float* u, const float* v, const float* xmapr, const float* ymapr,
@@ -559,7 +1414,6 @@ int fcb200_advection_batched(int nx, int ny, int nfields, const float* f, const 
   const size_t n = (size_t)nx * ny;
   Call call;
   AdvectionOp op;
-  op.count_flat = false;
   op.f = call.in(f, n * nfields);
   op.u = call.in(u, n * nfields);
   op.v = call.in(v, n * nfields);
@@ -586,15 +1440,22 @@ int fcb200_gradient_batched(int nx, int ny, int nfields, const float* field, con
     return -1;
   const size_t n = (size_t)nx * ny;
   Call call;
-  GradientOp op;
-  op.count_flat = (compute == 1);
-  op.compute = compute;
-  op.f = call.in(field, n * nfields);
+  const float* d_f = call.in(field, n * nfields);
   // the reference only dereferences the map ratio(s) the mode needs; keep that so callers may pass the other as null
-  op.xm = (compute != 2) ? call.in(xmapr, n) : nullptr;
-  op.ym = (compute != 1) ? call.in(ymapr, n) : nullptr;
-  op.o = call.out(fgrad, n * nfields);
-  return run_stencil(call, op, nx, ny, nfields, fDefined, undef, n - 2 * (size_t)nx);
+  const float* d_xm = (compute != 2) ? call.in(xmapr, n) : nullptr;
+  const float* d_ym = (compute != 1) ? call.in(ymapr, n) : nullptr;
+  float* d_o = call.out(fgrad, n * nfields);
+  const unsigned long long denom = n - 2 * (size_t)nx; // for every mode, also c=1 whose loop is [1, N-1) (FC.cc:2014, 2068)
+  switch (compute) {
+  case 1:
+    return run_stencil(call, GradientOp<1>{d_f, d_xm, d_ym, d_o}, nx, ny, nfields, fDefined, undef, denom, true);
+  case 2:
+    return run_stencil(call, GradientOp<2>{d_f, d_xm, d_ym, d_o}, nx, ny, nfields, fDefined, undef, denom);
+  case 3:
+    return run_stencil(call, GradientOp<3>{d_f, d_xm, d_ym, d_o}, nx, ny, nfields, fDefined, undef, denom);
+  default:
+    return run_stencil(call, GradientOp<4>{d_f, d_xm, d_ym, d_o}, nx, ny, nfields, fDefined, undef, denom);
+  }
 }
 int fcb200_gradient(int nx, int ny, const float* field, const float* xmapr, const float* ymapr, int compute, float* fgrad, int* fDefined,
                     float undef)
@@ -612,7 +1473,6 @@ int fcb200_jacobian_batched(int nx, int ny, int nfields, const float* field1, co
   const size_t n = (size_t)nx * ny;
   Call call;
   JacobianOp op;
-  op.count_flat = false;
   op.f1 = call.in(field1, n * nfields);
   op.f2 = call.in(field2, n * nfields);
   op.xm = call.in(xmapr, n);
@@ -636,7 +1496,6 @@ int fcb200_ilevelgwind_batched(int nx, int ny, int nfields, const float* mpot, c
   const size_t n = (size_t)nx * ny;
   Call call;
   GwindOp op;
-  op.count_flat = false;
   op.m = call.in(mpot, n * nfields);
   op.xm = call.in(xmapr, n);
   op.ym = call.in(ymapr, n);
@@ -669,17 +1528,10 @@ int fcb200_thermalFrontParameter_batched(int nx, int ny, int nfields, const floa
   unsigned long long* counters = call.counters(2 * nfields); // [0, nfields): pass 1, [nfields, 2 nfields): pass 2
   if (!call.ok())
     return -1;
-  GradientOp g;
-  g.count_flat = false;
-  g.compute = 3;
-  g.f = d_t;
-  g.xm = d_xm;
-  g.ym = d_ym;
-  g.o = d_ad;
+  const GradientOp<3> g{d_t, d_xm, d_ym, d_ad};
   if (!launch_stencil(call, g, nx, ny, nfields, undef, meta, counters))
     return -1;
   TfpOp op;
-  op.count_flat = false;
   op.tx = d_t;
   op.ad = d_ad;
   op.xm = d_xm;
@@ -715,13 +1567,25 @@ int fcb200_shapiro2_filter_batched(int nx, int ny, int nfields, float* field, fl
   const FieldMeta* meta = flags_to_meta(call, fDefined, nfields);
   if (!call.ok())
     return -1;
-  const int tiles_x = (nx + SH_TX - 1) / SH_TX, tiles_y = (ny + SH_TY - 1) / SH_TY;
-  const long long grid = (long long)tiles_x * tiles_y * nfields;
+  // W = 4 needs every row of every field on a 16-byte boundary
+  const bool vec = (nx % 4 == 0) && ((reinterpret_cast<uintptr_t>(d_in) | reinterpret_cast<uintptr_t>(d_tmp)) & 15) == 0;
+  const int useful = vec ? ShapiroGeom<4>::USEFUL : ShapiroGeom<1>::USEFUL;
+  const int strips = (nx + useful - 1) / useful;
+  const int strip_groups = (strips + SH_WARPS - 1) / SH_WARPS;
+  // rows per band: as tall as possible (a band re-reads 4 halo rows) while the launch still fills the GPU
+  int rows_per_band = 64;
+  while (rows_per_band > 8 && (long long)strips * ((ny + rows_per_band - 1) / rows_per_band) * nfields < 24LL * sm_count())
+    rows_per_band /= 2;
+  const int bands = (ny + rows_per_band - 1) / rows_per_band;
+  const long long grid = (long long)strip_groups * bands * nfields;
   if (grid > 0x7fffffffLL) {
     set_error("fcb200: batch too large for one launch (%lld CTAs)", grid);
     return -1;
   }
-  shapiro2_kernel<<<(unsigned)grid, SH_THREADS, 0, call.stream()>>>(d_in, d_tmp, nx, ny, tiles_x, tiles_y, meta, undef);
+  if (vec)
+    shapiro2_kernel<4><<<(unsigned)grid, SH_WARPS * 32, 0, call.stream()>>>(d_in, d_tmp, nx, ny, strips, bands, rows_per_band, meta, undef);
+  else
+    shapiro2_kernel<1><<<(unsigned)grid, SH_WARPS * 32, 0, call.stream()>>>(d_in, d_tmp, nx, ny, strips, bands, rows_per_band, meta, undef);
   count_launch();
   if (aliased) {
     if (!cuda_ok(cudaMemcpyAsync(d_out, d_tmp, sizeof(float) * n * nfields, cudaMemcpyDeviceToDevice, call.stream()), "cudaMemcpyAsync(D2D)"))

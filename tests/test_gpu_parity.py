@@ -141,3 +141,87 @@ def test_fused_alevel_chain_equals_four_reference_calls(gpu, mask, flag, unit):
                 case.floor = floor
                 problems = cases.compare(case, (1, [got[oi][k]], int(fout[oi, k])), (1, [o], int(f[0])), rtol=rtol)
                 assert not problems, "output %d (%s) field %d device=%s: %s" % (oi, name, k, device, problems)
+
+
+def _batched_case(name, nx, ny, nf, params, device):
+    """nf single-field cases (different seeds, masks and flags) sharing the grid-constant arrays, stacked into
+    the argument list of `<name>_batched`; returns (batched args, out positions, flags array, single cases)"""
+    spec = cases.SPECS[name]
+    variants = [("none", cases.ALL), ("bernoulli", cases.SOME), ("edge", cases.SOME), ("nan", cases.ALL), ("all", cases.SOME), ("blobs", cases.SOME)]
+    singles = []
+    for k in range(nf):
+        mask, flag = variants[k % len(variants)]
+        singles.append(cases.build(name, nx, ny, seed=100 + k, flag_in=flag, mask=mask, **params))
+    pos, shared = 0, {}
+    for d in spec:  # grid-constant arrays come from case 0
+        if isinstance(d, tuple) and d[0] == "in!":
+            for c in singles[1:]:
+                c.args[pos] = singles[0].args[pos]
+        pos += 2 if isinstance(d, tuple) and d[0] in ("members", "limits") else 1
+    args, out_pos, pos = [], [], 0
+    flags = np.array([c.args[c.flag_idx][0] for c in singles], np.int32)
+    for d in spec:
+        a0 = singles[0].args[pos]
+        if d == "ny":
+            args += [a0, nf]
+        elif d == "flag":
+            args.append(flags)
+        elif d == "out" or (isinstance(d, tuple) and d[0] in ("in", "inout")):
+            stacked = np.stack([c.args[pos] for c in singles])
+            if device:
+                stacked = _to_device(stacked)
+            if d == "out":
+                out_pos.append(len(args))
+            args.append(stacked)
+        elif isinstance(d, tuple) and d[0] == "in!":
+            args.append(_to_device(a0) if device else a0)
+        else:
+            args.append(a0)
+        pos += 1
+    return args, out_pos, flags, singles
+
+
+@pytest.mark.parametrize("device", [False, True])
+@pytest.mark.parametrize("name", sorted(matrix.STENCILS) + ["aleveltemp", "alevelhum", "fieldOPERfield", "windCooling", "vesselIcingOverland",
+                                                            "momentumXcoordinate"])
+def test_batched_equals_single_field_calls(gpu, name, device):
+    """`<op>_batched` over nf stacked fields == nf reference calls, field by field (values, masks, flags);
+    odd nx (fields of a batch are only 4-byte aligned) and nx % 4 == 0 (the float4 paths)"""
+    arb = _arbiter()
+    for nx, ny in ((37, 23), (64, 19), (949, 9)):
+        for params in matrix.VARIANTS[name][:2] if name != "gradient" else matrix.VARIANTS[name][:4]:
+            nf = 7
+            args, out_pos, flags, singles = _batched_case(name, nx, ny, nf, params, device)
+            r = gpu.call(name + "_batched", *args)
+            assert r == 1, (name, params, r, gpu.last_error())
+            for k, c in enumerate(singles):
+                want = cases.run(arb, c)
+                outs = [(args[p][k].cpu().numpy() if device else args[p][k]) for p in out_pos]
+                problems = cases.compare(c, (1, outs, int(flags[k])), want, rtol=cases.TRANSCENDENTAL.get(name, 0.0))
+                assert not problems, "%s %s %dx%d field %d (%s): %s" % (name, params, nx, ny, k, c.params["mask"], "\n".join(problems))
+
+
+@pytest.mark.parametrize("name", ["relvort", "divergence", "advection", "gradient", "jacobian", "ilevelgwind", "thermalFrontParameter", "shapiro2_filter",
+                                  "aleveltemp", "fieldOPERfield", "meanValue"])
+@pytest.mark.parametrize("offsets", ["same", "mixed"])
+def test_device_pointers_off_16_byte_alignment(gpu, name, offsets):
+    """device fields that start 4, 8 or 12 bytes past a 16-byte boundary: all arrays alike (the float4 paths
+    with a peeled head) and every array different (the scalar paths)"""
+    import torch
+    arb = _arbiter()
+    nx, ny = 131, 29
+    for mask, flag in [("none", cases.ALL), ("bernoulli", cases.SOME)]:
+        case = cases.build(name, nx, ny, seed=23, flag_in=flag, mask=mask, **matrix.VARIANTS[name][0])
+        counter = [0]
+
+        def to_dev(a):
+            counter[0] += 1
+            off = 1 if offsets == "same" else counter[0] % 4
+            buf = torch.empty(a.size + 8, dtype=torch.float32, device="cuda")
+            view = buf[off:off + a.size].view(a.shape)
+            view.copy_(torch.from_numpy(np.ascontiguousarray(a)))
+            return view
+
+        got = cases.run(gpu, case, to_device=to_dev)
+        problems = cases.compare(case, got, cases.run(arb, case), rtol=cases.TRANSCENDENTAL.get(name, 0.0))
+        assert not problems, "%s %s %s: %s" % (name, offsets, mask, "\n".join(problems))
