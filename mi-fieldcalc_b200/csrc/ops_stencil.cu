@@ -11,6 +11,7 @@
 //
 // Citations: FC.cc = the reference's src/mi_fieldcalc/FieldCalculations.cc.
 #include "device_common.cuh"
+#include "stencil_tile.cuh"
 
 #include "../../include/fcb200.h"
 
@@ -125,41 +126,6 @@ __global__ void __launch_bounds__(ST_THREADS) stencil_kernel(const Op op0, const
     stencil_body<Op, false>(op, g, chunk, g.counters + field);
 }
 
-// fillEdges (FC.cc:59-74): out(x, y) = interior(clamp(x, 1, nx-2), clamp(y, 1, ny-2)) on the border ring.
-// One thread per border cell; the sources are interior cells, which this kernel never writes.
-constexpr int FE_THREADS = 128;
-
-__global__ void __launch_bounds__(FE_THREADS) fill_edges_kernel(float* o0, float* o1, int nx, int ny, int nfields)
-{
-  const int ring = 2 * nx + 2 * (ny - 2);
-  const int b = blockIdx.x * FE_THREADS + threadIdx.x;
-  if (b >= ring)
-    return;
-  int x, y;
-  if (b < nx) {
-    x = b;
-    y = 0;
-  } else if (b < 2 * nx) {
-    x = b - nx;
-    y = ny - 1;
-  } else {
-    const int c = b - 2 * nx;
-    y = 1 + (c >> 1);
-    x = (c & 1) ? nx - 1 : 0;
-  }
-  const int sx = min(max(x, 1), nx - 2), sy = min(max(y, 1), ny - 2);
-  const long long n = (long long)nx * ny;
-  const int dst = y * nx + x, src = sy * nx + sx;
-  for (int field = blockIdx.y; field < nfields; field += gridDim.y) {
-    float* p = o0 + field * n;
-    p[dst] = p[src];
-    if (o1) {
-      float* q = o1 + field * n;
-      q[dst] = q[src];
-    }
-  }
-}
-
 __device__ __forceinline__ bool def2(float a, float b, float undef)
 {
   return is_def(a, undef) && is_def(b, undef);
@@ -174,57 +140,6 @@ __device__ __forceinline__ bool def4(float a, float b, float c, float d, float u
 __device__ __forceinline__ double half_map_diff(float mapr, float hi, float lo)
 {
   return 0.5 * (double)mapr * (double)(hi - lo);
-}
-
-// ---- vector loads for the float4 path ------------------------------------------------------------------
-// A lane of the vector kernel owns "group" gi = 4 consecutive flat points i0 .. i0+3 whose address is
-// 16-byte aligned in every per-field array; the 32 lanes of a warp own 32 consecutive groups.  Every
-// global access is ONE aligned LDG.128 per lane and array row; what a lane needs beyond its own 16
-// bytes comes from the adjacent lanes by warp shuffle:
-//   * x neighbours: point i0-1 is lane-1's .w, point i0+4 is lane+1's .x;
-//   * a neighbour row (i0 +- nx) or a grid-constant array starts SH = 0..3 elements past a 16-byte
-//     boundary (SH is uniform per CTA, a template parameter): the lane loads the aligned block that
-//     holds its first 4-SH values and takes the other SH from lane+1's block.
-// Lanes 0 and 31 therefore only serve as halo: a warp produces 30 groups (120 points) per step.
-// (Loading two blocks per lane instead was measured L1-bound: 72 % l1tex throughput, 50 B/point.)
-// A block is only loaded when it holds at least one element some lane needs, so no access leaves the
-// arrays: groups -1 and ngroups (the range's unaligned head and tail) exist for the halo only.
-constexpr unsigned FULL = 0xffffffffu;
-
-// Loads are unconditional: a lane whose group lies outside [first, last] loads the nearest group that
-// some lane needs instead (an L1 hit, result unused).  first/last per kind of array:
-//   x-neighbour arrays: [-1, ngroups]; rows / maps with SH > 0: [0, ngroups]; with SH == 0: [0, ngroups-1].
-__device__ __forceinline__ float4 ldx(const float* p_al, int gi, int ngroups)
-{
-  const int g = min(max(gi, -1), ngroups);
-  return *reinterpret_cast<const float4*>(p_al + 4 * g);
-}
-template <int SH>
-__device__ __forceinline__ float4 ldr(const float* p_al, int gi, int ngroups)
-{
-  const int g = min(max(gi, 0), SH ? ngroups : ngroups - 1);
-  return *reinterpret_cast<const float4*>(p_al + 4 * g - SH);
-}
-// o[0] = p[-1], o[1..4] = p[0..3], o[5] = p[4]
-__device__ __forceinline__ void ex6(const float4& a, float (&o)[6])
-{
-  o[0] = __shfl_up_sync(FULL, a.w, 1);
-  o[1] = a.x;
-  o[2] = a.y;
-  o[3] = a.z;
-  o[4] = a.w;
-  o[5] = __shfl_down_sync(FULL, a.x, 1);
-}
-template <int SH>
-__device__ __forceinline__ void ex4(const float4& a, float (&o)[4])
-{
-  float t[8] = {a.x, a.y, a.z, a.w, 0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-  for (int j = 0; j < SH; ++j)
-    t[4 + j] = __shfl_down_sync(FULL, t[j], 1);
-#pragma unroll
-  for (int j = 0; j < 4; ++j)
-    o[j] = t[j + SH];
 }
 
 // relvort / absvort / divergence (FC.cc:1843-1940).  MODE: 0 relvort, 1 absvort, 2 divergence
@@ -282,70 +197,30 @@ struct VortDivOp
       r.fc = fc[i];
     return r;
   }
-  static constexpr int NFIELD_PTRS = 3, NMAP_PTRS = (MODE == 1) ? 3 : 2;
-  __host__ void field_ptrs(const void** p) const { p[0] = u, p[1] = v, p[2] = o; }
-  __host__ void map_ptrs(const void** p) const { p[0] = xm, p[1] = ym, p[2] = fc; }
-  __host__ __device__ __forceinline__ const float* map0() const { return xm; }
-  struct Raw
+  // tile engine: array 0 is read at x +- 1, array 1 at y +- 1 (divergence's masked path reads both at both)
+  static constexpr int TY = 8, NARR = 2, NMAPS = (MODE == 1) ? 3 : 2;
+  __host__ __device__ __forceinline__ const float* arr(int k) const { return (MODE == 2) ? (k == 0 ? u : v) : (k == 0 ? v : u); }
+  __host__ __device__ static constexpr int halo(int k) { return (MODE == 2) ? 1 : k; }
+  __host__ __device__ __forceinline__ const float* map(int k) const { return k == 0 ? xm : k == 1 ? ym : fc; }
+  template <bool ALL, class View>
+  __device__ __forceinline__ In<ALL> fetch(const View& t, int r, const float* m) const
   {
-    float4 x, up, dn, m1, m2, m3, tx, tup, tdn;
-  };
-  // p_al = array + i_al: the address of group 0
-  template <bool ALL, int SNX, int SMAP>
-  __device__ __forceinline__ Raw load_raw(int i_al, int nx, int gi, int ng) const
-  {
-    constexpr int SUP = (4 - SNX) & 3, SDN = SNX;
-    const float* fx = (MODE == 2) ? u : v; // the array whose x neighbours are used
-    const float* fy = (MODE == 2) ? v : u; // the array whose y neighbours are used
-    Raw r;
-    r.x = ldx(fx + i_al, gi, ng);
-    r.up = ldr<SUP>(fy + i_al - nx, gi, ng);
-    r.dn = ldr<SDN>(fy + i_al + nx, gi, ng);
-    r.m1 = ldr<SMAP>(xm + i_al, gi, ng);
-    r.m2 = ldr<SMAP>(ym + i_al, gi, ng);
-    if (MODE == 1)
-      r.m3 = ldr<SMAP>(fc + i_al, gi, ng);
+    In<ALL> in;
+    in.a = t.template at<0>(r, -1);
+    in.b = t.template at<0>(r, 1);
+    in.c = t.template at<1>(r - 1, 0);
+    in.d = t.template at<1>(r + 1, 0);
     if (MODE == 2 && !ALL) {
-      r.tx = ldx(v + i_al, gi, ng);
-      r.tup = ldr<SUP>(u + i_al - nx, gi, ng);
-      r.tdn = ldr<SDN>(u + i_al + nx, gi, ng);
+      in.ta = t.template at<1>(r, -1);
+      in.tb = t.template at<1>(r, 1);
+      in.tc = t.template at<0>(r - 1, 0);
+      in.td = t.template at<0>(r + 1, 0);
     }
-    return r;
-  }
-  template <bool ALL, int SNX, int SMAP>
-  __device__ __forceinline__ void assemble(const Raw& r, In<ALL> (&in)[4]) const
-  {
-    constexpr int SUP = (4 - SNX) & 3, SDN = SNX;
-    float x6[6], up[4], dn[4], m1[4], m2[4], m3[4], tx6[6], tup[4], tdn[4];
-    ex6(r.x, x6);
-    ex4<SUP>(r.up, up);
-    ex4<SDN>(r.dn, dn);
-    ex4<SMAP>(r.m1, m1);
-    ex4<SMAP>(r.m2, m2);
+    in.xm = m[0];
+    in.ym = m[1];
     if (MODE == 1)
-      ex4<SMAP>(r.m3, m3);
-    if (MODE == 2 && !ALL) {
-      ex6(r.tx, tx6);
-      ex4<SUP>(r.tup, tup);
-      ex4<SDN>(r.tdn, tdn);
-    }
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      in[j].a = x6[j];
-      in[j].b = x6[j + 2];
-      in[j].c = up[j];
-      in[j].d = dn[j];
-      in[j].xm = m1[j];
-      in[j].ym = m2[j];
-      if (MODE == 1)
-        in[j].fc = m3[j];
-      if (MODE == 2 && !ALL) {
-        in[j].ta = tx6[j];
-        in[j].tb = tx6[j + 2];
-        in[j].tc = tup[j];
-        in[j].td = tdn[j];
-      }
-    }
+      in.fc = m[2];
+    return in;
   }
   template <bool ALL>
   __device__ __forceinline__ bool eval(const In<ALL>& r, float undef, float* val) const
@@ -404,51 +279,23 @@ struct AdvectionOp
     r.ym = ym[i];
     return r;
   }
-  static constexpr int NFIELD_PTRS = 4, NMAP_PTRS = 2;
-  __host__ void field_ptrs(const void** p) const { p[0] = f, p[1] = u, p[2] = v, p[3] = o; }
-  __host__ void map_ptrs(const void** p) const { p[0] = xm, p[1] = ym; }
-  __host__ __device__ __forceinline__ const float* map0() const { return xm; }
-  struct Raw
+  static constexpr int TY = 8, NARR = 3, NMAPS = 2;
+  __host__ __device__ __forceinline__ const float* arr(int k) const { return k == 0 ? f : k == 1 ? u : v; }
+  __host__ __device__ static constexpr int halo(int k) { return k == 0 ? 1 : 0; }
+  __host__ __device__ __forceinline__ const float* map(int k) const { return k == 0 ? xm : ym; }
+  template <bool ALL, class View>
+  __device__ __forceinline__ In<ALL> fetch(const View& t, int r, const float* m) const
   {
-    float4 x, up, dn, uc, vc, m1, m2;
-  };
-  template <bool ALL, int SNX, int SMAP>
-  __device__ __forceinline__ Raw load_raw(int i_al, int nx, int gi, int ng) const
-  {
-    constexpr int SUP = (4 - SNX) & 3, SDN = SNX;
-    Raw r;
-    r.x = ldx(f + i_al, gi, ng);
-    r.up = ldr<SUP>(f + i_al - nx, gi, ng);
-    r.dn = ldr<SDN>(f + i_al + nx, gi, ng);
-    r.uc = ldr<0>(u + i_al, gi, ng);
-    r.vc = ldr<0>(v + i_al, gi, ng);
-    r.m1 = ldr<SMAP>(xm + i_al, gi, ng);
-    r.m2 = ldr<SMAP>(ym + i_al, gi, ng);
-    return r;
-  }
-  template <bool ALL, int SNX, int SMAP>
-  __device__ __forceinline__ void assemble(const Raw& r, In<ALL> (&in)[4]) const
-  {
-    constexpr int SUP = (4 - SNX) & 3, SDN = SNX;
-    float x6[6], up[4], dn[4], uc[4], vc[4], m1[4], m2[4];
-    ex6(r.x, x6);
-    ex4<SUP>(r.up, up);
-    ex4<SDN>(r.dn, dn);
-    ex4<0>(r.uc, uc);
-    ex4<0>(r.vc, vc);
-    ex4<SMAP>(r.m1, m1);
-    ex4<SMAP>(r.m2, m2);
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      in[j].ui = uc[j];
-      in[j].vi = vc[j];
-      in[j].fd = up[j];
-      in[j].fl = x6[j];
-      in[j].fr = x6[j + 2];
-      in[j].fu = dn[j];
-      in[j].xm = m1[j];
-      in[j].ym = m2[j];
-    }
+    In<ALL> in;
+    in.ui = t.template at<1>(r, 0);
+    in.vi = t.template at<2>(r, 0);
+    in.fd = t.template at<0>(r - 1, 0);
+    in.fl = t.template at<0>(r, -1);
+    in.fr = t.template at<0>(r, 1);
+    in.fu = t.template at<0>(r + 1, 0);
+    in.xm = m[0];
+    in.ym = m[1];
+    return in;
   }
   template <bool ALL>
   __device__ __forceinline__ bool eval(const In<ALL>& r, float undef, float* val) const
@@ -506,59 +353,27 @@ struct GradientOp
       r.fc = f[i];
     return r;
   }
-  static constexpr int NFIELD_PTRS = 2, NMAP_PTRS = (COMPUTE <= 2) ? 1 : 2;
-  __host__ void field_ptrs(const void** p) const { p[0] = f, p[1] = o; }
-  __host__ void map_ptrs(const void** p) const { p[0] = (COMPUTE == 2) ? ym : xm, p[1] = ym; }
-  __host__ __device__ __forceinline__ const float* map0() const { return (COMPUTE == 2) ? ym : xm; }
-  struct Raw
+  static constexpr int TY = 8, NARR = 1, NMAPS = (COMPUTE <= 2) ? 1 : 2;
+  __host__ __device__ __forceinline__ const float* arr(int) const { return f; }
+  __host__ __device__ static constexpr int halo(int) { return (COMPUTE == 1) ? 0 : 1; }
+  __host__ __device__ __forceinline__ const float* map(int k) const { return (COMPUTE == 2 || k == 1) ? ym : xm; }
+  template <bool ALL, class View>
+  __device__ __forceinline__ In<ALL> fetch(const View& t, int r, const float* m) const
   {
-    float4 x, up, dn, m1, m2;
-  };
-  template <bool ALL, int SNX, int SMAP>
-  __device__ __forceinline__ Raw load_raw(int i_al, int nx, int gi, int ng) const
-  {
-    constexpr int SUP = (4 - SNX) & 3, SDN = SNX;
-    Raw r;
+    In<ALL> in;
     if (COMPUTE != 2) {
-      r.x = ldx(f + i_al, gi, ng);
-      r.m1 = ldr<SMAP>(xm + i_al, gi, ng);
+      in.fl = t.template at<0>(r, -1);
+      in.fr = t.template at<0>(r, 1);
+      in.xm = m[0];
     }
     if (COMPUTE != 1) {
-      r.up = ldr<SUP>(f + i_al - nx, gi, ng);
-      r.dn = ldr<SDN>(f + i_al + nx, gi, ng);
-      r.m2 = ldr<SMAP>(ym + i_al, gi, ng);
+      in.fd = t.template at<0>(r - 1, 0);
+      in.fu = t.template at<0>(r + 1, 0);
+      in.ym = (COMPUTE == 2) ? m[0] : m[1];
     }
-    return r;
-  }
-  template <bool ALL, int SNX, int SMAP>
-  __device__ __forceinline__ void assemble(const Raw& r, In<ALL> (&in)[4]) const
-  {
-    constexpr int SUP = (4 - SNX) & 3, SDN = SNX;
-    float x6[6], up[4], dn[4], m1[4], m2[4];
-    if (COMPUTE != 2) {
-      ex6(r.x, x6);
-      ex4<SMAP>(r.m1, m1);
-    }
-    if (COMPUTE != 1) {
-      ex4<SUP>(r.up, up);
-      ex4<SDN>(r.dn, dn);
-      ex4<SMAP>(r.m2, m2);
-    }
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      if (COMPUTE != 2) {
-        in[j].fl = x6[j];
-        in[j].fr = x6[j + 2];
-        in[j].xm = m1[j];
-      }
-      if (COMPUTE != 1) {
-        in[j].fd = up[j];
-        in[j].fu = dn[j];
-        in[j].ym = m2[j];
-      }
-      if (COMPUTE == 4)
-        in[j].fc = x6[j + 1];
-    }
+    if (COMPUTE == 4)
+      in.fc = t.template at<0>(r, 0);
+    return in;
   }
   template <bool ALL>
   __device__ __forceinline__ bool eval(const In<ALL>& r, float undef, float* val) const
@@ -633,55 +448,25 @@ struct JacobianOp
     r.ym = ym[i];
     return r;
   }
-  static constexpr int NFIELD_PTRS = 3, NMAP_PTRS = 2;
-  __host__ void field_ptrs(const void** p) const { p[0] = f1, p[1] = f2, p[2] = o; }
-  __host__ void map_ptrs(const void** p) const { p[0] = xm, p[1] = ym; }
-  __host__ __device__ __forceinline__ const float* map0() const { return xm; }
-  struct Raw
+  static constexpr int TY = 8, NARR = 2, NMAPS = 2;
+  __host__ __device__ __forceinline__ const float* arr(int k) const { return k == 0 ? f1 : f2; }
+  __host__ __device__ static constexpr int halo(int) { return 1; }
+  __host__ __device__ __forceinline__ const float* map(int k) const { return k == 0 ? xm : ym; }
+  template <bool ALL, class View>
+  __device__ __forceinline__ In<ALL> fetch(const View& t, int r, const float* m) const
   {
-    float4 ax, aup, adn, bx, bup, bdn, m1, m2;
-  };
-  template <bool ALL, int SNX, int SMAP>
-  __device__ __forceinline__ Raw load_raw(int i_al, int nx, int gi, int ng) const
-  {
-    constexpr int SUP = (4 - SNX) & 3, SDN = SNX;
-    Raw r;
-    r.ax = ldx(f1 + i_al, gi, ng);
-    r.aup = ldr<SUP>(f1 + i_al - nx, gi, ng);
-    r.adn = ldr<SDN>(f1 + i_al + nx, gi, ng);
-    r.bx = ldx(f2 + i_al, gi, ng);
-    r.bup = ldr<SUP>(f2 + i_al - nx, gi, ng);
-    r.bdn = ldr<SDN>(f2 + i_al + nx, gi, ng);
-    r.m1 = ldr<SMAP>(xm + i_al, gi, ng);
-    r.m2 = ldr<SMAP>(ym + i_al, gi, ng);
-    return r;
-  }
-  template <bool ALL, int SNX, int SMAP>
-  __device__ __forceinline__ void assemble(const Raw& r, In<ALL> (&in)[4]) const
-  {
-    constexpr int SUP = (4 - SNX) & 3, SDN = SNX;
-    float ax[6], aup[4], adn[4], bx[6], bup[4], bdn[4], m1[4], m2[4];
-    ex6(r.ax, ax);
-    ex4<SUP>(r.aup, aup);
-    ex4<SDN>(r.adn, adn);
-    ex6(r.bx, bx);
-    ex4<SUP>(r.bup, bup);
-    ex4<SDN>(r.bdn, bdn);
-    ex4<SMAP>(r.m1, m1);
-    ex4<SMAP>(r.m2, m2);
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      in[j].ad = aup[j];
-      in[j].al = ax[j];
-      in[j].ar = ax[j + 2];
-      in[j].au = adn[j];
-      in[j].bd = bup[j];
-      in[j].bl = bx[j];
-      in[j].br = bx[j + 2];
-      in[j].bu = bdn[j];
-      in[j].xm = m1[j];
-      in[j].ym = m2[j];
-    }
+    In<ALL> in;
+    in.ad = t.template at<0>(r - 1, 0);
+    in.al = t.template at<0>(r, -1);
+    in.ar = t.template at<0>(r, 1);
+    in.au = t.template at<0>(r + 1, 0);
+    in.bd = t.template at<1>(r - 1, 0);
+    in.bl = t.template at<1>(r, -1);
+    in.br = t.template at<1>(r, 1);
+    in.bu = t.template at<1>(r + 1, 0);
+    in.xm = m[0];
+    in.ym = m[1];
+    return in;
   }
   template <bool ALL>
   __device__ __forceinline__ bool eval(const In<ALL>& r, float undef, float* val) const
@@ -736,48 +521,22 @@ struct GwindOp
     r.fc = fc[i];
     return r;
   }
-  static constexpr int NFIELD_PTRS = 3, NMAP_PTRS = 3;
-  __host__ void field_ptrs(const void** p) const { p[0] = m, p[1] = ug, p[2] = vg; }
-  __host__ void map_ptrs(const void** p) const { p[0] = xm, p[1] = ym, p[2] = fc; }
-  __host__ __device__ __forceinline__ const float* map0() const { return xm; }
-  struct Raw
+  static constexpr int TY = 8, NARR = 1, NMAPS = 3;
+  __host__ __device__ __forceinline__ const float* arr(int) const { return m; }
+  __host__ __device__ static constexpr int halo(int) { return 1; }
+  __host__ __device__ __forceinline__ const float* map(int k) const { return k == 0 ? xm : k == 1 ? ym : fc; }
+  template <bool ALL, class View>
+  __device__ __forceinline__ In<ALL> fetch(const View& t, int r, const float* mp) const
   {
-    float4 x, up, dn, m1, m2, m3;
-  };
-  template <bool ALL, int SNX, int SMAP>
-  __device__ __forceinline__ Raw load_raw(int i_al, int nx, int gi, int ng) const
-  {
-    constexpr int SUP = (4 - SNX) & 3, SDN = SNX;
-    Raw r;
-    r.x = ldx(m + i_al, gi, ng);
-    r.up = ldr<SUP>(m + i_al - nx, gi, ng);
-    r.dn = ldr<SDN>(m + i_al + nx, gi, ng);
-    r.m1 = ldr<SMAP>(xm + i_al, gi, ng);
-    r.m2 = ldr<SMAP>(ym + i_al, gi, ng);
-    r.m3 = ldr<SMAP>(fc + i_al, gi, ng);
-    return r;
-  }
-  template <bool ALL, int SNX, int SMAP>
-  __device__ __forceinline__ void assemble(const Raw& r, In<ALL> (&in)[4]) const
-  {
-    constexpr int SUP = (4 - SNX) & 3, SDN = SNX;
-    float x6[6], up[4], dn[4], m1[4], m2[4], m3[4];
-    ex6(r.x, x6);
-    ex4<SUP>(r.up, up);
-    ex4<SDN>(r.dn, dn);
-    ex4<SMAP>(r.m1, m1);
-    ex4<SMAP>(r.m2, m2);
-    ex4<SMAP>(r.m3, m3);
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      in[j].md = up[j];
-      in[j].ml = x6[j];
-      in[j].mr = x6[j + 2];
-      in[j].mu = dn[j];
-      in[j].xm = m1[j];
-      in[j].ym = m2[j];
-      in[j].fc = m3[j];
-    }
+    In<ALL> in;
+    in.md = t.template at<0>(r - 1, 0);
+    in.ml = t.template at<0>(r, -1);
+    in.mr = t.template at<0>(r, 1);
+    in.mu = t.template at<0>(r + 1, 0);
+    in.xm = mp[0];
+    in.ym = mp[1];
+    in.fc = mp[2];
+    return in;
   }
   template <bool ALL>
   __device__ __forceinline__ bool eval(const In<ALL>& r, float undef, float* val) const
@@ -837,56 +596,26 @@ struct TfpOp
     r.ym = ym[i];
     return r;
   }
-  static constexpr int NFIELD_PTRS = 3, NMAP_PTRS = 2;
-  __host__ void field_ptrs(const void** p) const { p[0] = tx, p[1] = ad, p[2] = o; }
-  __host__ void map_ptrs(const void** p) const { p[0] = xm, p[1] = ym; }
-  __host__ __device__ __forceinline__ const float* map0() const { return xm; }
-  struct Raw
+  static constexpr int TY = 8, NARR = 2, NMAPS = 2;
+  __host__ __device__ __forceinline__ const float* arr(int k) const { return k == 0 ? tx : ad; }
+  __host__ __device__ static constexpr int halo(int) { return 1; }
+  __host__ __device__ __forceinline__ const float* map(int k) const { return k == 0 ? xm : ym; }
+  template <bool ALL, class View>
+  __device__ __forceinline__ In<ALL> fetch(const View& t, int r, const float* m) const
   {
-    float4 t, tup, tdn, a, aup, adn, m1, m2;
-  };
-  template <bool ALL, int SNX, int SMAP>
-  __device__ __forceinline__ Raw load_raw(int i_al, int nx, int gi, int ng) const
-  {
-    constexpr int SUP = (4 - SNX) & 3, SDN = SNX;
-    Raw r;
-    r.t = ldx(tx + i_al, gi, ng);
-    r.tup = ldr<SUP>(tx + i_al - nx, gi, ng);
-    r.tdn = ldr<SDN>(tx + i_al + nx, gi, ng);
-    r.a = ldx(ad + i_al, gi, ng);
-    r.aup = ldr<SUP>(ad + i_al - nx, gi, ng);
-    r.adn = ldr<SDN>(ad + i_al + nx, gi, ng);
-    r.m1 = ldr<SMAP>(xm + i_al, gi, ng);
-    r.m2 = ldr<SMAP>(ym + i_al, gi, ng);
-    return r;
-  }
-  template <bool ALL, int SNX, int SMAP>
-  __device__ __forceinline__ void assemble(const Raw& r, In<ALL> (&in)[4]) const
-  {
-    constexpr int SUP = (4 - SNX) & 3, SDN = SNX;
-    float t6[6], tup[4], tdn[4], a6[6], aup[4], adn4[4], m1[4], m2[4];
-    ex6(r.t, t6);
-    ex4<SUP>(r.tup, tup);
-    ex4<SDN>(r.tdn, tdn);
-    ex6(r.a, a6);
-    ex4<SUP>(r.aup, aup);
-    ex4<SDN>(r.adn, adn4);
-    ex4<SMAP>(r.m1, m1);
-    ex4<SMAP>(r.m2, m2);
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      in[j].td = tup[j];
-      in[j].tl = t6[j];
-      in[j].tr = t6[j + 2];
-      in[j].tu = tdn[j];
-      in[j].adn = aup[j];
-      in[j].al = a6[j];
-      in[j].ac = a6[j + 1];
-      in[j].ar = a6[j + 2];
-      in[j].au = adn4[j];
-      in[j].xm = m1[j];
-      in[j].ym = m2[j];
-    }
+    In<ALL> in;
+    in.td = t.template at<0>(r - 1, 0);
+    in.tl = t.template at<0>(r, -1);
+    in.tr = t.template at<0>(r, 1);
+    in.tu = t.template at<0>(r + 1, 0);
+    in.adn = t.template at<1>(r - 1, 0);
+    in.al = t.template at<1>(r, -1);
+    in.ac = t.template at<1>(r, 0);
+    in.ar = t.template at<1>(r, 1);
+    in.au = t.template at<1>(r + 1, 0);
+    in.xm = m[0];
+    in.ym = m[1];
+    return in;
   }
   template <bool ALL>
   __device__ __forceinline__ bool eval(const In<ALL>& r, float undef, float* val) const
@@ -906,162 +635,6 @@ struct TfpOp
   }
 };
 
-// ---- the float4 kernel ------------------------------------------------------------------------------------
-// Same flat loop, four consecutive points per lane, 30 producing lanes per warp, SV_UNROLL warp steps
-// per CTA pass: 16-byte loads and stores throughout (the scalar kernel above is LSU-issue bound: 7
-// memory instructions per point, stall reason lg_throttle).  The groups start at the first point of
-// the range whose address is 16-byte aligned in the per-field arrays; the < 4 points before it and
-// the < 4 points after the last whole group go through the scalar code, in the field's first CTA.
-constexpr int SV_UNROLL = 2;
-constexpr int SV_WARPS = ST_THREADS / 32;
-constexpr int SV_LANES = 30;                                      // producing lanes per warp
-constexpr int SV_CHUNK_GROUPS = SV_WARPS * SV_UNROLL * SV_LANES;  // groups per CTA
-
-template <class Op, bool ALL>
-__device__ __forceinline__ void stencil_vec_group(const Op& op, int i0, const typename Op::template In<ALL> (&in)[4], float undef, unsigned& nundef)
-{
-  float r[Op::NOUT][4];
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    float val[Op::NOUT];
-    const bool ok = op.template eval<ALL>(in[j], undef, val);
-    if (!ok)
-      nundef += 1;
-#pragma unroll
-    for (int k = 0; k < Op::NOUT; ++k)
-      r[k][j] = ok ? val[k] : undef;
-  }
-#pragma unroll
-  for (int k = 0; k < Op::NOUT; ++k)
-    *reinterpret_cast<float4*>(op.out(k) + i0) = make_float4(r[k][0], r[k][1], r[k][2], r[k][3]);
-}
-
-template <class Op, bool ALL, int SNX, int SMAP>
-__device__ __forceinline__ unsigned stencil_vec_body(const Op& op, const StencilGeom& g, int chunk, int i_al, int ngroups)
-{
-  typedef typename Op::template In<ALL> In;
-  const int nx = g.nx;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int units = (ngroups + SV_LANES - 1) / SV_LANES; // warp steps in this field
-  const int wu0 = chunk * (SV_WARPS * SV_UNROLL) + warp;
-  unsigned nundef = 0;
-  // every branch below is warp-uniform (the assembly shuffles).  Phase 1 issues every load of the
-  // CTA pass, phase 2 exchanges neighbours between lanes, computes and stores.
-  typename Op::Raw raw[SV_UNROLL];
-  if (units > 0) {
-#pragma unroll
-  for (int u = 0; u < SV_UNROLL; ++u) {
-    const int wu = min(wu0 + u * SV_WARPS, units - 1); // past the end: reload the last step, unused
-    raw[u] = op.template load_raw<ALL, SNX, SMAP>(i_al, nx, wu * SV_LANES - 1 + lane, ngroups);
-  }
-#pragma unroll
-  for (int u = 0; u < SV_UNROLL; ++u) {
-    const int wu = wu0 + u * SV_WARPS;
-    if (wu < units) {
-      const int gi = wu * SV_LANES - 1 + lane;
-      In in[4];
-      op.template assemble<ALL, SNX, SMAP>(raw[u], in);
-      if (lane >= 1 && lane <= SV_LANES && gi < ngroups)
-        stencil_vec_group<Op, ALL>(op, i_al + 4 * gi, in, g.undef, nundef);
-    }
-  }
-  }
-  if (chunk == 0) { // the unaligned head and tail points of the range
-    const int tail0 = i_al + 4 * ngroups;
-    int idx = -1;
-    if ((int)threadIdx.x < i_al - g.lo)
-      idx = g.lo + threadIdx.x;
-    else if (threadIdx.x >= 32 && (int)threadIdx.x - 32 < g.hi - tail0)
-      idx = tail0 + (threadIdx.x - 32);
-    if (idx >= 0)
-      nundef += stencil_point<Op, ALL>(op, op.template load<ALL>(idx, nx), idx, g.undef);
-  }
-  return nundef;
-}
-
-template <class Op, bool ALL, int SNX>
-__device__ __forceinline__ unsigned stencil_vec_dispatch(const Op& op, const StencilGeom& g, int chunk, int i_al, int ngroups, int smap)
-{
-  switch (smap) {
-  case 0:
-    return stencil_vec_body<Op, ALL, SNX, 0>(op, g, chunk, i_al, ngroups);
-  case 1:
-    return stencil_vec_body<Op, ALL, SNX, 1>(op, g, chunk, i_al, ngroups);
-  case 2:
-    return stencil_vec_body<Op, ALL, SNX, 2>(op, g, chunk, i_al, ngroups);
-  default:
-    return stencil_vec_body<Op, ALL, SNX, 3>(op, g, chunk, i_al, ngroups);
-  }
-}
-
-template <class Op, int SNX>
-__global__ void __launch_bounds__(ST_THREADS) stencil_vec_kernel(const Op op0, const StencilGeom g)
-{
-  const int field = blockIdx.z * g.group + blockIdx.x, chunk = blockIdx.y + g.chunk_base;
-  if (field >= g.nfields)
-    return;
-  const bool all = op0.all_defined(field, g.meta[field].all != 0);
-  const Op op = op0.at(field, g.n);
-  // element alignment of this field (identical in all its arrays: checked by the host) and of the maps
-  const int a = (int)((reinterpret_cast<uintptr_t>(op.out(0)) >> 2) & 3);
-  int i_al = g.lo + ((4 - ((a + g.lo) & 3)) & 3);
-  if (i_al > g.hi)
-    i_al = g.hi;
-  const int ngroups = (g.hi - i_al) >> 2;
-  const int smap = (int)(((reinterpret_cast<uintptr_t>(op.map0()) >> 2) + i_al) & 3);
-  unsigned nundef;
-  if (all)
-    nundef = stencil_vec_dispatch<Op, true, SNX>(op, g, chunk, i_al, ngroups, smap);
-  else
-    nundef = stencil_vec_dispatch<Op, false, SNX>(op, g, chunk, i_al, ngroups, smap);
-  __shared__ unsigned s_count;
-  if (threadIdx.x == 0)
-    s_count = 0;
-  __syncthreads();
-  nundef = __reduce_add_sync(0xffffffffu, nundef);
-  if ((threadIdx.x & 31) == 0 && nundef)
-    atomicAdd(&s_count, nundef);
-  __syncthreads();
-  if (threadIdx.x == 0 && s_count)
-    atomicAdd(g.counters + field, (unsigned long long)s_count);
-}
-
-// every per-field array on the same 4-byte-multiple offset from a 16-byte boundary, every map likewise
-template <class Op>
-bool stencil_vec_ok(const Op& op, int nx, int ny, int nfields)
-{
-  const void* fp[8];
-  const void* mp[4];
-  op.field_ptrs(fp);
-  op.map_ptrs(mp);
-  for (int k = 0; k < Op::NFIELD_PTRS; ++k)
-    if ((reinterpret_cast<uintptr_t>(fp[k]) & 3) || (reinterpret_cast<uintptr_t>(fp[k]) & 15) != (reinterpret_cast<uintptr_t>(fp[0]) & 15))
-      return false;
-  for (int k = 0; k < Op::NMAP_PTRS; ++k)
-    if ((reinterpret_cast<uintptr_t>(mp[k]) & 3) || (reinterpret_cast<uintptr_t>(mp[k]) & 15) != (reinterpret_cast<uintptr_t>(mp[0]) & 15))
-      return false;
-  return (long long)nx * ny >= 64;
-}
-
-template <class Op>
-void launch_stencil_vec(cudaStream_t stream, const Op& op, const StencilGeom& g, dim3 grid)
-{
-  switch (g.nx & 3) {
-  case 0:
-    stencil_vec_kernel<Op, 0><<<grid, ST_THREADS, 0, stream>>>(op, g);
-    break;
-  case 1:
-    stencil_vec_kernel<Op, 1><<<grid, ST_THREADS, 0, stream>>>(op, g);
-    break;
-  case 2:
-    stencil_vec_kernel<Op, 2><<<grid, ST_THREADS, 0, stream>>>(op, g);
-    break;
-  default:
-    stencil_vec_kernel<Op, 3><<<grid, ST_THREADS, 0, stream>>>(op, g);
-    break;
-  }
-}
-
 // main kernel over the reference's flat range, then the border ring
 template <class Op>
 bool launch_stencil(Call& call, const Op& op, int nx, int ny, int nfields, float undef, const FieldMeta* meta, unsigned long long* counters,
@@ -1077,32 +650,73 @@ bool launch_stencil(Call& call, const Op& op, int nx, int ny, int nfields, float
   g.undef = undef;
   g.meta = meta;
   g.counters = counters;
-  static const int env_group = getenv("FCB200_ST_GROUP") ? atoi(getenv("FCB200_ST_GROUP")) : 0; // tuning aid
-  g.group = env_group > 0 ? env_group : ST_GROUP;
-  if (g.group > nfields)
-    g.group = nfields;
+  const int ring = 2 * nx + 2 * (ny - 2);
+  const dim3 edge_grid((ring + tile::EDGE_THREADS - 1) / tile::EDGE_THREADS, nfields < 4096 ? nfields : 4096);
+  // the tile engine stages every per-field input with one shift pattern: they must share their 16-byte alignment
+  bool same_align = true;
+  for (int k = 1; k < Op::NARR; ++k)
+    same_align = same_align && ((reinterpret_cast<uintptr_t>(op.arr(k)) ^ reinterpret_cast<uintptr_t>(op.arr(0))) & 15) == 0;
+  if (nx >= 34 && g.n >= 8192 && same_align) {
+    // tiles staged in shared memory by the TMA unit (stencil_tile.cuh), then the border ring
+    typedef tile::TileLayout<Op> L;
+    tile::TileGeom t;
+    t.nx = nx;
+    t.ny = ny;
+    t.n = g.n;
+    t.nfields = nfields;
+    t.tiles_x = (nx - 2 + tile::TX - 1) / tile::TX;
+    t.tiles_y = (ny - 2 + Op::TY - 1) / Op::TY;
+    t.period = (g.n % 4 == 0) ? 1 : (g.n % 2 == 0) ? 2 : 4;
+    t.undef = undef;
+    t.meta = meta;
+    t.counters = counters;
+    const long long tiles = (long long)t.tiles_x * t.tiles_y;
+    // as many fields per CTA as possible (the maps are fetched once per CTA, the pipeline fills once)
+    // while the grid still gives every SM a few CTAs
+    t.fb = 16;
+    while (t.fb > 1 && tiles * ((nfields + t.fb - 1) / t.fb) < 6LL * sm_count())
+      t.fb /= 2;
+    if (t.fb > nfields)
+      t.fb = nfields;
+    // pipeline depth: up to 3 fields in flight, two CTAs per SM
+    t.stages = t.fb < tile::MAX_STAGES ? t.fb : tile::MAX_STAGES;
+    while (t.stages > 1 && L::smem_bytes(t.stages) > 110 * 1024)
+      t.stages -= 1;
+    const size_t smem = L::smem_bytes(t.stages);
+    static bool attr_set = false; // per instantiation
+    if (!attr_set) {
+      if (!cuda_ok(cudaFuncSetAttribute(tile::stencil_tile_kernel<Op>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::smem_bytes(tile::MAX_STAGES)),
+                   "cudaFuncSetAttribute(stencil_tile_kernel)"))
+        return false;
+      attr_set = true;
+    }
+    if (tiles > 65535 || (nfields + t.fb - 1) / t.fb > 0x7fffffff) {
+      set_error("fcb200: grid too large for one launch (%lld tiles)", tiles);
+      return false;
+    }
+    tile::stencil_tile_kernel<Op><<<dim3((unsigned)((nfields + t.fb - 1) / t.fb), (unsigned)tiles), tile::TILE_THREADS, smem, call.stream()>>>(op, t);
+    tile::stencil_edge_kernel<Op><<<edge_grid, tile::EDGE_THREADS, 0, call.stream()>>>(op, nx, ny, nfields, g.lo, g.hi, undef, meta, counters, true);
+    count_launch(2);
+    return true;
+  }
+  // small grids: the flat scalar kernel (it counts the ring cells of its range itself), then the border ring
+  g.group = nfields < ST_GROUP ? nfields : ST_GROUP;
   const int groups = (nfields + g.group - 1) / g.group;
   if (groups > 65535) {
     set_error("fcb200: batch too large for one launch (%d fields)", nfields);
     return false;
   }
-  const bool vec = stencil_vec_ok(op, nx, ny, nfields);
-  const int per_chunk = vec ? SV_CHUNK_GROUPS * 4 : ST_THREADS * ST_UNROLL;
+  const int per_chunk = ST_THREADS * ST_UNROLL;
   const int total_chunks = (g.hi - g.lo + per_chunk - 1) / per_chunk;
   // gridDim.y <= 65535: a longer range takes several launches
   for (int c0 = 0; c0 < total_chunks; c0 += 65535) {
     g.chunk_base = c0;
     g.chunks = total_chunks - c0 < 65535 ? total_chunks - c0 : 65535;
     const dim3 grid((unsigned)g.group, (unsigned)g.chunks, (unsigned)groups);
-    if (vec)
-      launch_stencil_vec(call.stream(), op, g, grid);
-    else
-      stencil_kernel<Op><<<grid, ST_THREADS, 0, call.stream()>>>(op, g);
+    stencil_kernel<Op><<<grid, ST_THREADS, 0, call.stream()>>>(op, g);
     count_launch();
   }
-  const int ring = 2 * nx + 2 * (ny - 2);
-  const dim3 fe_grid((ring + FE_THREADS - 1) / FE_THREADS, nfields < 4096 ? nfields : 4096);
-  fill_edges_kernel<<<fe_grid, FE_THREADS, 0, call.stream()>>>(op.out(0), Op::NOUT > 1 ? op.out(1) : nullptr, nx, ny, nfields);
+  tile::stencil_edge_kernel<Op><<<edge_grid, tile::EDGE_THREADS, 0, call.stream()>>>(op, nx, ny, nfields, g.lo, g.hi, undef, meta, counters, false);
   count_launch();
   return true;
 }

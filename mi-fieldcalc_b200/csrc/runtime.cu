@@ -121,8 +121,46 @@ struct ThreadState
   Arena dev;
   Arena pin;
   std::vector<Deferred> queue;
+  // Undefined-point counters come from a device pool that is ALWAYS ZERO when handed out: the pool's used
+  // part is copied to its pinned mirror once per drain (not once per call) and cleared right after,
+  // so a call costs no memset and no device-to-host copy of its own.
+  unsigned long long* counter_pool = nullptr;
+  unsigned long long* counter_mirror = nullptr; // pinned
+  size_t counter_used = 0;
+  static constexpr size_t COUNTER_POOL = size_t(1) << 18; // counters (2 MB)
 
   ThreadState() { pin.pinned = true; }
+
+  void release_counter_pool()
+  {
+    if (counter_pool)
+      cudaFree(counter_pool);
+    if (counter_mirror)
+      cudaFreeHost(counter_mirror);
+    counter_pool = counter_mirror = nullptr;
+    counter_used = 0;
+  }
+
+  // `count` zeroed counters from the pool (nullptr: pool exhausted or unavailable, the caller falls back)
+  unsigned long long* pool_counters(size_t count)
+  {
+    if (!counter_pool) {
+      if (cudaMalloc((void**)&counter_pool, COUNTER_POOL * sizeof(unsigned long long)) != cudaSuccess ||
+          cudaMallocHost((void**)&counter_mirror, COUNTER_POOL * sizeof(unsigned long long)) != cudaSuccess ||
+          cudaMemsetAsync(counter_pool, 0, COUNTER_POOL * sizeof(unsigned long long), stream()) != cudaSuccess) {
+        cudaGetLastError();
+        release_counter_pool();
+        return nullptr;
+      }
+      // the pool may be used from the pipeline slots' streams: make the clear visible to all of them
+      cudaStreamSynchronize(stream());
+    }
+    if (counter_used + count > COUNTER_POOL)
+      return nullptr;
+    unsigned long long* p = counter_pool + counter_used;
+    counter_used += count;
+    return p;
+  }
   ~ThreadState()
   {
     // the context may already be gone at thread/process exit: ignore errors
@@ -131,6 +169,7 @@ struct ThreadState
     dev.release_all();
     pin.release_all();
     release_slots();
+    release_counter_pool();
     cudaGetLastError();
   }
 
@@ -179,6 +218,7 @@ struct ThreadState
         dev.release_all();
         pin.release_all();
         release_slots();
+        release_counter_pool();
         own_stream = nullptr;
         cudaSetDevice(d);
       }
@@ -195,7 +235,13 @@ struct ThreadState
 
   bool drain()
   {
-    bool ok = cuda_ok(cudaStreamSynchronize(stream()), "cudaStreamSynchronize");
+    bool ok = true;
+    if (counter_used > 0)
+      ok = cuda_ok(cudaMemcpyAsync(counter_mirror, counter_pool, counter_used * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream()),
+                   "cudaMemcpyAsync(D2H counters)") &&
+           cuda_ok(cudaMemsetAsync(counter_pool, 0, counter_used * sizeof(unsigned long long), stream()), "cudaMemsetAsync(counters)");
+    counter_used = 0;
+    ok = cuda_ok(cudaStreamSynchronize(stream()), "cudaStreamSynchronize") && ok;
     if (ok) {
       for (auto& d : queue)
         if (d.fin)
@@ -447,6 +493,10 @@ unsigned long long* Call::counters(int count)
   if (!ok_)
     return nullptr;
   counters_n_ = count;
+  counters_dev_ = ts_->pool_counters((size_t)count);
+  counters_pooled_ = counters_dev_ != nullptr;
+  if (counters_pooled_)
+    return counters_dev_;
   counters_dev_ = static_cast<unsigned long long*>(arena_alloc(sizeof(unsigned long long) * (size_t)count));
   if (!counters_dev_)
     return nullptr;
@@ -471,7 +521,9 @@ int Call::finish(const Finalizer& fin)
     }
   }
   const unsigned long long* host_counters = nullptr;
-  if (counters_n_ > 0) {
+  if (counters_n_ > 0 && counters_pooled_) {
+    host_counters = ts_->counter_mirror + (counters_dev_ - ts_->counter_pool); // filled by drain()
+  } else if (counters_n_ > 0) {
     // counters are read by the finaliser when the whole call drains: they live in the main pinned
     // arena, which is not recycled while work is in flight
     void* pin = ts_->pin.alloc(sizeof(unsigned long long) * (size_t)counters_n_);

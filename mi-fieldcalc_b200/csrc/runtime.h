@@ -121,6 +121,7 @@ private:
   int meta_n_ = 0;
   unsigned long long* counters_dev_ = nullptr;
   int counters_n_ = 0;
+  bool counters_pooled_ = false;
   bool finished_ = false;
 };
 

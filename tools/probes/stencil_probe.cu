@@ -20,6 +20,9 @@ __global__ void __launch_bounds__(T) k(const float* __restrict__ u, const float*
     const int i = i0 + q * T;
     if (i < n - nx) {
       if (VAR == 0) { a[q] = u[i]; b[q] = v[i]; }
+      else if (VAR == 6) { a[q] = u[i]; b[q] = v[i]; m1[q] = xm[i]; m2[q] = ym[i]; }
+      else if (VAR == 7) { a[q] = u[i]; b[q] = v[i]; c[q] = u[i + nx]; }
+      else if (VAR == 8) { a[q] = u[i]; b[q] = v[i]; c[q] = u[i + nx]; m1[q] = xm[i]; m2[q] = ym[i]; }
       else {
         a[q] = v[i - 1]; b[q] = v[i + 1];
         if (VAR == 5) { c[q] = u[i]; d[q] = u[i]; } else { c[q] = u[i - nx]; d[q] = u[i + nx]; }
@@ -33,6 +36,9 @@ __global__ void __launch_bounds__(T) k(const float* __restrict__ u, const float*
     if (i < n - nx) {
       float r;
       if (VAR == 0) r = a[q] + b[q];
+      else if (VAR == 6) r = a[q] + b[q] + m1[q] + m2[q];
+      else if (VAR == 7) r = a[q] + b[q] + c[q];
+      else if (VAR == 8) r = a[q] + b[q] + c[q] + m1[q] + m2[q];
       else if (VAR == 1 || VAR == 4) r = 0.5f * m1[q] * (b[q] - a[q]) - 0.5f * m2[q] * (d[q] - c[q]);
       else r = (float)(0.5 * (double)m1[q] * (double)(b[q] - a[q]) - 0.5 * (double)m2[q] * (double)(d[q] - c[q]));
       o[i] = r;
@@ -116,9 +122,10 @@ void runloop(const float* u, const float* v, const float* xm, const float* ym, f
   printf("field loop FPC=%2d prefetch=%d                      %8.4f ms  %7.1f GB/s (12 B/pt)\n", FPC, (int)PF, best, 12.0 * n * nf / best * 1e-6);
 }
 
-int main()
+int main(int argc, char** argv)
 {
   const int nx = 949, ny = 1069, n = nx * ny, nf = 64;
+  const int reps = argc > 1 ? atoi(argv[1]) : 12;
   float *u, *v, *o, *xm, *ym;
   cudaMalloc(&u, sizeof(float) * (size_t)n * nf * 2);
   cudaMalloc(&v, sizeof(float) * (size_t)n * nf * 2);
@@ -134,10 +141,12 @@ int main()
   cudaEventCreate(&e0);
   cudaEventCreate(&e1);
   const char* names[] = {"0 copy-like u[i]+v[i]", "1 relvort loads, float math, maps", "2 relvort loads, double math, maps", "3 relvort loads, double math, no maps",
-                         "4 relvort loads, float math, no maps", "5 u[i] twice instead of u[i+-nx], double, maps"};
-  for (int var = 0; var < 6; ++var) {
+                         "4 relvort loads, float math, no maps", "5 u[i] twice instead of u[i+-nx], double, maps", "6 copy-like + maps", "7 copy-like + u[i+nx]",
+                         "8 copy-like + u[i+nx] + maps"};
+  for (int ai = 2; ai < (argc > 2 ? argc : 11); ++ai) {
+    const int var = argc > 2 ? atoi(argv[ai]) : ai - 2;
     float best = 1e9f;
-    for (int rep = 0; rep < 12; ++rep) {
+    for (int rep = 0; rep < reps; ++rep) {
       const size_t s = (size_t)(rep & 1) * n * nf;
       cudaEventRecord(e0);
       dim3 grid(chunks, nf);
@@ -148,6 +157,9 @@ int main()
       case 3: k<3><<<grid, T>>>(u + s, v + s, xm, ym, o + s, nx, n, chunks); break;
       case 4: k<4><<<grid, T>>>(u + s, v + s, xm, ym, o + s, nx, n, chunks); break;
       case 5: k<5><<<grid, T>>>(u + s, v + s, xm, ym, o + s, nx, n, chunks); break;
+      case 6: k<6><<<grid, T>>>(u + s, v + s, xm, ym, o + s, nx, n, chunks); break;
+      case 7: k<7><<<grid, T>>>(u + s, v + s, xm, ym, o + s, nx, n, chunks); break;
+      case 8: k<8><<<grid, T>>>(u + s, v + s, xm, ym, o + s, nx, n, chunks); break;
       }
       cudaEventRecord(e1);
       cudaEventSynchronize(e1);
@@ -157,13 +169,6 @@ int main()
     }
     printf("%-50s %8.4f ms  %7.1f GB/s (12 B/pt)\n", names[var], best, 12.0 * n * nf / best * 1e-6);
   }
-  runloop<2, false>(u, v, xm, ym, o, nx, n, nf, e0, e1);
-  runloop<4, false>(u, v, xm, ym, o, nx, n, nf, e0, e1);
-  runloop<8, false>(u, v, xm, ym, o, nx, n, nf, e0, e1);
-  runloop<16, false>(u, v, xm, ym, o, nx, n, nf, e0, e1);
-  runloop<4, true>(u, v, xm, ym, o, nx, n, nf, e0, e1);
-  runloop<8, true>(u, v, xm, ym, o, nx, n, nf, e0, e1);
-  runloop<16, true>(u, v, xm, ym, o, nx, n, nf, e0, e1);
   printf("%s\n", cudaGetErrorString(cudaGetLastError()));
   return 0;
 }
