@@ -15,6 +15,7 @@
 
 #include "../../include/fcb200.h"
 
+#include <algorithm>
 #include <cmath>
 #include <cstdlib>
 
@@ -142,6 +143,20 @@ __device__ __forceinline__ double half_map_diff(float mapr, float hi, float lo)
   return 0.5 * (double)mapr * (double)(hi - lo);
 }
 
+// (float)half_map_diff(...), i.e. a derivative that the reference rounds to float on its own, without double
+// arithmetic: 0.5*mapr and the product of two floats are exact in double, so the reference's value is the
+// exact product rounded ONCE to float -- which is what a float multiplication returns (overflow, underflow
+// to subnormals, infinities and NaN included), provided 0.5f*mapr is exact in float, i.e. mapr is not
+// tiny (|mapr| >= 2^-100 or 0; tile::map_is_regular).  The float<->double conversions run on the quarter-rate XU pipe (16/clk/SM on B200, measured):
+// with 4..9 of them per point these operators were XU-bound well below the HBM roofline.
+template <bool FAST>
+__device__ __forceinline__ float half_map_diff_f(float mapr, float hi, float lo)
+{
+  if (FAST) // the tile kernel checked that none of the CTA's map ratios is tiny, subnormal or NaN
+    return (0.5f * mapr) * (hi - lo);
+  return (float)(0.5 * (double)mapr * (double)(hi - lo));
+}
+
 // relvort / absvort / divergence (FC.cc:1843-1940).  MODE: 0 relvort, 1 absvort, 2 divergence
 template <int MODE>
 struct VortDivOp
@@ -198,6 +213,10 @@ struct VortDivOp
     return r;
   }
   // tile engine: array 0 is read at x +- 1, array 1 at y +- 1 (divergence's masked path reads both at both)
+  static constexpr int HX = 1, EXTRA_FLOATS = 0;
+  static constexpr bool CUSTOM_TILE = false;
+  template <class V, class M>
+  __device__ unsigned tile_custom(const V&, const M&, float*, bool, bool, int, int, int, int, int, int, int, float) const { return 0; }
   static constexpr int TY = 8, NARR = 2, NMAPS = (MODE == 1) ? 3 : 2;
   __host__ __device__ __forceinline__ const float* arr(int k) const { return (MODE == 2) ? (k == 0 ? u : v) : (k == 0 ? v : u); }
   __host__ __device__ static constexpr int halo(int k) { return (MODE == 2) ? 1 : k; }
@@ -222,7 +241,7 @@ struct VortDivOp
       in.fc = m[2];
     return in;
   }
-  template <bool ALL>
+  template <bool ALL, bool FAST = false>
   __device__ __forceinline__ bool eval(const In<ALL>& r, float undef, float* val) const
   {
     bool ok = true;
@@ -279,6 +298,10 @@ struct AdvectionOp
     r.ym = ym[i];
     return r;
   }
+  static constexpr int HX = 1, EXTRA_FLOATS = 0;
+  static constexpr bool CUSTOM_TILE = false;
+  template <class V, class M>
+  __device__ unsigned tile_custom(const V&, const M&, float*, bool, bool, int, int, int, int, int, int, int, float) const { return 0; }
   static constexpr int TY = 8, NARR = 3, NMAPS = 2;
   __host__ __device__ __forceinline__ const float* arr(int k) const { return k == 0 ? f : k == 1 ? u : v; }
   __host__ __device__ static constexpr int halo(int k) { return k == 0 ? 1 : 0; }
@@ -297,7 +320,7 @@ struct AdvectionOp
     in.ym = m[1];
     return in;
   }
-  template <bool ALL>
+  template <bool ALL, bool FAST = false>
   __device__ __forceinline__ bool eval(const In<ALL>& r, float undef, float* val) const
   {
     bool ok = true;
@@ -353,6 +376,10 @@ struct GradientOp
       r.fc = f[i];
     return r;
   }
+  static constexpr int HX = 1, EXTRA_FLOATS = 0;
+  static constexpr bool CUSTOM_TILE = false;
+  template <class V, class M>
+  __device__ unsigned tile_custom(const V&, const M&, float*, bool, bool, int, int, int, int, int, int, int, float) const { return 0; }
   static constexpr int TY = 8, NARR = 1, NMAPS = (COMPUTE <= 2) ? 1 : 2;
   __host__ __device__ __forceinline__ const float* arr(int) const { return f; }
   __host__ __device__ static constexpr int halo(int) { return (COMPUTE == 1) ? 0 : 1; }
@@ -375,7 +402,7 @@ struct GradientOp
       in.fc = t.template at<0>(r, 0);
     return in;
   }
-  template <bool ALL>
+  template <bool ALL, bool FAST = false>
   __device__ __forceinline__ bool eval(const In<ALL>& r, float undef, float* val) const
   {
     bool ok = true;
@@ -392,12 +419,12 @@ struct GradientOp
         return false;
     }
     if (COMPUTE == 1) {
-      val[0] = (float)half_map_diff(r.xm, r.fr, r.fl);
+      val[0] = half_map_diff_f<FAST>(r.xm, r.fr, r.fl);
     } else if (COMPUTE == 2) {
-      val[0] = (float)half_map_diff(r.ym, r.fu, r.fd);
+      val[0] = half_map_diff_f<FAST>(r.ym, r.fu, r.fd);
     } else if (COMPUTE == 3) {
-      const float dfdx = (float)half_map_diff(r.xm, r.fr, r.fl);
-      const float dfdy = (float)half_map_diff(r.ym, r.fu, r.fd);
+      const float dfdx = half_map_diff_f<FAST>(r.xm, r.fr, r.fl);
+      const float dfdy = half_map_diff_f<FAST>(r.ym, r.fu, r.fd);
       val[0] = dev::absval(dfdx, dfdy);
     } else {
       const float d2fdx = (float)((double)r.fl - 2.0 * (double)r.fc + (double)r.fr);
@@ -448,6 +475,10 @@ struct JacobianOp
     r.ym = ym[i];
     return r;
   }
+  static constexpr int HX = 1, EXTRA_FLOATS = 0;
+  static constexpr bool CUSTOM_TILE = false;
+  template <class V, class M>
+  __device__ unsigned tile_custom(const V&, const M&, float*, bool, bool, int, int, int, int, int, int, int, float) const { return 0; }
   static constexpr int TY = 8, NARR = 2, NMAPS = 2;
   __host__ __device__ __forceinline__ const float* arr(int k) const { return k == 0 ? f1 : f2; }
   __host__ __device__ static constexpr int halo(int) { return 1; }
@@ -468,7 +499,7 @@ struct JacobianOp
     in.ym = m[1];
     return in;
   }
-  template <bool ALL>
+  template <bool ALL, bool FAST = false>
   __device__ __forceinline__ bool eval(const In<ALL>& r, float undef, float* val) const
   {
     bool ok = true;
@@ -476,10 +507,10 @@ struct JacobianOp
       ok = def4(r.ad, r.al, r.ar, r.au, undef) && def4(r.bd, r.bl, r.br, r.bu, undef);
     if (!ok)
       return false;
-    const float df1dx = (float)half_map_diff(r.xm, r.ar, r.al);
-    const float df1dy = (float)half_map_diff(r.ym, r.au, r.ad);
-    const float df2dx = (float)half_map_diff(r.xm, r.br, r.bl);
-    const float df2dy = (float)half_map_diff(r.ym, r.bu, r.bd);
+    const float df1dx = half_map_diff_f<FAST>(r.xm, r.ar, r.al);
+    const float df1dy = half_map_diff_f<FAST>(r.ym, r.au, r.ad);
+    const float df2dx = half_map_diff_f<FAST>(r.xm, r.br, r.bl);
+    const float df2dy = half_map_diff_f<FAST>(r.ym, r.bu, r.bd);
     val[0] = df1dx * df2dy - df1dy * df2dx;
     return ok;
   }
@@ -521,6 +552,10 @@ struct GwindOp
     r.fc = fc[i];
     return r;
   }
+  static constexpr int HX = 1, EXTRA_FLOATS = 0;
+  static constexpr bool CUSTOM_TILE = false;
+  template <class V, class M>
+  __device__ unsigned tile_custom(const V&, const M&, float*, bool, bool, int, int, int, int, int, int, int, float) const { return 0; }
   static constexpr int TY = 8, NARR = 1, NMAPS = 3;
   __host__ __device__ __forceinline__ const float* arr(int) const { return m; }
   __host__ __device__ static constexpr int halo(int) { return 1; }
@@ -538,7 +573,7 @@ struct GwindOp
     in.fc = mp[2];
     return in;
   }
-  template <bool ALL>
+  template <bool ALL, bool FAST = false>
   __device__ __forceinline__ bool eval(const In<ALL>& r, float undef, float* val) const
   {
     bool ok = true;
@@ -553,71 +588,82 @@ struct GwindOp
   }
 };
 
-// second pass of thermalFrontParameter (FC.cc:2286-2303).  `ad` = abs(grad T) from gradient(c=3) INCLUDING
-// its fillEdges; the pass's allDefined is the first pass's OUTPUT flag, i.e. "the first pass counted
-// nothing" (FC.cc:2281-2286) -- read from the first pass's device counter, no host round trip.
-struct TfpOp
+// thermalFrontParameter, FUSED (FC.cc:2266-2309).  The reference runs gradient(c=3) into a scratch field
+// `absdelt` (with its fillEdges, so absdelt(x, y) = G(clamp(x, 1, nx-2), clamp(y, 1, ny-2)), G = |grad T| at an
+// interior point) and then a second five-point pass over T and absdelt.  Here a tile of T with a halo of
+// two is staged once, |grad T| is evaluated for the tile plus a halo of one into shared memory and the
+// second pass reads it from there: 8 B/point of HBM traffic instead of 20, no scratch field.
+//   all1 (pass 1) = the input flag; all2 (pass 2) = pass 1's output flag = "pass 1 counted nothing" =
+//   "no element of T is undefined" (the flat loop [nx, N-nx) tests every element of the field): for fields
+//   whose input flag is not ALL_DEFINED a pre-pass counts the undefined elements of T (t_undef).
+// The scalar load() evaluates G on the fly for the five absdelt operands: it serves the border ring
+// (stencil_edge_kernel) and the small grids of the flat kernel.
+constexpr int TFP_APITCH = tile::TX + 4; // |grad T| tile: (TY + 2) rows of TX + 2 columns
+
+struct TfpFusedOp
 {
   static constexpr int NOUT = 1;
   static constexpr bool TESTS_WHEN_ALL = true;
-  const float *tx, *ad, *xm, *ym;
-  const unsigned long long* pass1_counters;
+  const float *tx, *xm, *ym;
+  const unsigned long long* t_undef; // per field: undefined elements of T (only counted when the flag is not ALL)
+  const FieldMeta* meta;
+  int gnx, gny;
+  float undef_;
+  bool all1;
   float* o;
   template <bool ALL>
   struct In
   {
     float td, tl, tr, tu, adn, al, ac, ar, au, xm, ym;
   };
-  __device__ __forceinline__ bool all_defined(int field, bool) const { return pass1_counters[field] == 0; }
-  __device__ __forceinline__ TfpOp at(int field, int n) const
+  __device__ __forceinline__ bool all_defined(int field, bool in_all) const { return in_all || t_undef[field] == 0; }
+  __device__ __forceinline__ TfpFusedOp at(int field, int n) const
   {
-    TfpOp r = *this;
+    TfpFusedOp r = *this;
     const long long off = (long long)field * n;
     r.tx += off;
-    r.ad += off;
     r.o += off;
+    r.all1 = meta[field].all != 0;
     return r;
   }
   __host__ __device__ __forceinline__ float* out(int) const { return o; }
+  // pass 1 at an interior point (FC.cc:2037-2042)
+  template <bool FAST = false>
+  __device__ __forceinline__ float grad(float fd, float fl, float fr, float fu, float xmi, float ymi) const
+  {
+    if (!all1 && !def4(fd, fl, fr, fu, undef_))
+      return undef_;
+    const float dfdx = half_map_diff_f<FAST>(xmi, fr, fl);
+    const float dfdy = half_map_diff_f<FAST>(ymi, fu, fd);
+    return dev::absval(dfdx, dfdy);
+  }
+  // absdelt at flat index i: pass 1's value at the clamped interior point
+  __device__ float absdelt(int i) const
+  {
+    const int y = i / gnx, x = i - y * gnx;
+    const int cx = min(max(x, 1), gnx - 2), cy = min(max(y, 1), gny - 2);
+    const int j = cy * gnx + cx;
+    return grad(tx[j - gnx], tx[j - 1], tx[j + 1], tx[j + gnx], xm[j], ym[j]);
+  }
   template <bool ALL>
-  __device__ __forceinline__ In<ALL> load(int i, int nx) const
+  __device__ In<ALL> load(int i, int nx) const
   {
     In<ALL> r;
     r.td = tx[i - nx];
     r.tl = tx[i - 1];
     r.tr = tx[i + 1];
     r.tu = tx[i + nx];
-    r.adn = ad[i - nx];
-    r.al = ad[i - 1];
-    r.ac = ad[i];
-    r.ar = ad[i + 1];
-    r.au = ad[i + nx];
+    r.adn = absdelt(i - nx);
+    r.al = absdelt(i - 1);
+    r.ac = absdelt(i);
+    r.ar = absdelt(i + 1);
+    r.au = absdelt(i + nx);
     r.xm = xm[i];
     r.ym = ym[i];
     return r;
   }
-  static constexpr int TY = 8, NARR = 2, NMAPS = 2;
-  __host__ __device__ __forceinline__ const float* arr(int k) const { return k == 0 ? tx : ad; }
-  __host__ __device__ static constexpr int halo(int) { return 1; }
-  __host__ __device__ __forceinline__ const float* map(int k) const { return k == 0 ? xm : ym; }
-  template <bool ALL, class View>
-  __device__ __forceinline__ In<ALL> fetch(const View& t, int r, const float* m) const
-  {
-    In<ALL> in;
-    in.td = t.template at<0>(r - 1, 0);
-    in.tl = t.template at<0>(r, -1);
-    in.tr = t.template at<0>(r, 1);
-    in.tu = t.template at<0>(r + 1, 0);
-    in.adn = t.template at<1>(r - 1, 0);
-    in.al = t.template at<1>(r, -1);
-    in.ac = t.template at<1>(r, 0);
-    in.ar = t.template at<1>(r, 1);
-    in.au = t.template at<1>(r + 1, 0);
-    in.xm = m[0];
-    in.ym = m[1];
-    return in;
-  }
-  template <bool ALL>
+  // the second pass, FC.cc:2286-2303
+  template <bool ALL, bool FAST = false>
   __device__ __forceinline__ bool eval(const In<ALL>& r, float undef, float* val) const
   {
     bool ok = true;
@@ -626,14 +672,158 @@ struct TfpOp
     ok = ok && (r.ac != 0); // tested even when allDefined (FC.cc:2292)
     if (!ok)
       return false;
-    const float dadx = (float)half_map_diff(r.xm, r.ar, r.al);
-    const float dady = (float)half_map_diff(r.ym, r.au, r.adn);
+    const float dadx = half_map_diff_f<FAST>(r.xm, r.ar, r.al);
+    const float dady = half_map_diff_f<FAST>(r.ym, r.au, r.adn);
+    // (a shared-reciprocal division with a Markstein correction was measured SLOWER than the two IEEE divisions)
     const float dtdxa = (float)(half_map_diff(r.xm, r.tr, r.tl) / (double)r.ac);
     const float dtdya = (float)(half_map_diff(r.ym, r.tu, r.td) / (double)r.ac);
     val[0] = -(dadx * dtdxa + dady * dtdya);
-    return ok;
+    return true;
+  }
+
+  // ---- tile engine: T staged with a halo of two rows and two columns
+  static constexpr int HX = 2, TY = 8, NARR = 1, NMAPS = 2;
+  static constexpr int EXTRA_FLOATS = (TY + 2) * TFP_APITCH;
+  static constexpr bool CUSTOM_TILE = true;
+  __host__ __device__ __forceinline__ const float* arr(int) const { return tx; }
+  __host__ __device__ static constexpr int halo(int) { return 2; }
+  __host__ __device__ __forceinline__ const float* map(int k) const { return k == 0 ? xm : ym; }
+  template <bool ALL, class View>
+  __device__ __forceinline__ In<ALL> fetch(const View&, int, const float*) const
+  {
+    return In<ALL>();
+  }
+
+  template <bool ALL2, bool FAST, class View>
+  __device__ __forceinline__ unsigned pass2(const View& tv, const tile::MapSlots& maps, const float* ad, int nrows, bool col_ok, int i0, int nx, float undef) const
+  {
+    unsigned nundef = 0;
+#pragma unroll
+    for (int r = 0; r < TY; ++r) {
+      if (r < nrows) { // warp-uniform
+        In<ALL2> in;
+        in.td = tv.template at<0>(r - 1, 0);
+        in.tl = tv.template at<0>(r, -1);
+        in.tr = tv.template at<0>(r, 1);
+        in.tu = tv.template at<0>(r + 1, 0);
+        const float* a = ad + (r + 1) * TFP_APITCH; // row r of the |grad T| tile, this thread's column
+        in.adn = a[-TFP_APITCH];
+        in.al = a[-1];
+        in.ac = a[0];
+        in.ar = a[1];
+        in.au = a[TFP_APITCH];
+        in.xm = maps.get(0, r, TY);
+        in.ym = maps.get(1, r, TY);
+        float val[1];
+        const bool ok = eval<ALL2, FAST>(in, undef, val);
+        if (col_ok) {
+          if (!ok)
+            nundef += 1;
+          o[i0 + r * nx] = ok ? val[0] : undef;
+        }
+      }
+    }
+    return nundef;
+  }
+
+  // consumers only (TX threads); `scratch` = EXTRA_FLOATS floats of shared memory
+  template <class View>
+  __device__ unsigned tile_custom(const View& tv, const tile::MapSlots& maps, float* scratch, bool all2, bool fast, int x0, int y0, int xlast, int ylast, int c, int nx,
+                                  int ny, float undef) const
+  {
+    if (fast)
+      return tile_two_phase<true>(tv, maps, scratch, all2, x0, y0, xlast, ylast, c, nx, ny, undef);
+    return tile_two_phase<false>(tv, maps, scratch, all2, x0, y0, xlast, ylast, c, nx, ny, undef);
+  }
+  template <bool FAST, class View>
+  __device__ __forceinline__ unsigned tile_two_phase(const View& tv, const tile::MapSlots& maps, float* scratch, bool all2, int x0, int y0, int xlast, int ylast, int c,
+                                                     int nx, int ny, float undef) const
+  {
+    const int nrows = ylast - y0 + 1, ncols = xlast - x0 + 1;
+    const bool col_ok = c < ncols;
+    float* ad = scratch + c + 1; // column c of the |grad T| tile; tile row rr lives at (rr + 1) * TFP_APITCH
+    // phase 1a: G at the interior points of tile rows -1 .. TY, this thread's column.  The map ratios of rows
+    // -1 and TY are not in registers: two extra (L2-resident) loads per thread.
+    asm volatile("bar.sync 1, %0;" ::"n"(tile::TX)); // the previous field's pass 2 no longer reads the scratch tile
+    const int x = x0 + c;
+#pragma unroll
+    for (int rr = -1; rr <= TY; ++rr) {
+      const int y = y0 + rr;
+      if (rr <= nrows && y >= 1 && y <= ny - 2 && x <= nx - 2) {
+        float xmi, ymi;
+        if (rr >= 0 && rr < TY && rr < nrows && col_ok) {
+          xmi = maps.get(0, rr < 0 ? 0 : (rr >= TY ? TY - 1 : rr), TY);
+          ymi = maps.get(1, rr < 0 ? 0 : (rr >= TY ? TY - 1 : rr), TY);
+        } else {
+          xmi = xm[y * nx + x];
+          ymi = ym[y * nx + x];
+        }
+        // (the halo rows' map ratios are not covered by the CTA's regularity check: reference arithmetic there)
+        ad[(rr + 1) * TFP_APITCH] =
+            (rr >= 0 && rr < TY) ? grad<FAST>(tv.template at<0>(rr - 1, 0), tv.template at<0>(rr, -1), tv.template at<0>(rr, 1), tv.template at<0>(rr + 1, 0), xmi, ymi)
+                                 : grad<false>(tv.template at<0>(rr - 1, 0), tv.template at<0>(rr, -1), tv.template at<0>(rr, 1), tv.template at<0>(rr + 1, 0), xmi, ymi);
+      }
+    }
+    // the two halo columns -1 and ncols (when they are interior columns of the grid): threads 0 .. TY+1 and 32 .. 32+TY+1
+    {
+      const int which = c >> 5, rr = (c & 31) - 1; // which: 0 = column -1, 1 = column ncols
+      if (which < 2 && rr <= TY && rr <= nrows) {
+        const int cc = which == 0 ? -1 : ncols;
+        const int xx = x0 + cc, y = y0 + rr;
+        if (xx >= 1 && xx <= nx - 2 && y >= 1 && y <= ny - 2) {
+          const float* t = tx + (long long)y * nx + xx; // 10 + 10 points per tile: straight from global memory
+          scratch[(rr + 1) * TFP_APITCH + cc + 1] = grad(t[-nx], t[-1], t[1], t[nx], xm[y * nx + xx], ym[y * nx + xx]);
+        }
+      }
+    }
+    asm volatile("bar.sync 1, %0;" ::"n"(tile::TX));
+    // phase 1b: fillEdges of pass 1 inside the tile's halo -- border columns first, then border rows (FC.cc:59-74)
+    if (x0 == 1 || xlast == nx - 2) {
+      const int which = c >> 5, rr = (c & 31) - 1;
+      if (which < 2 && rr <= TY && rr <= nrows) {
+        const int y = y0 + rr;
+        if (y >= 1 && y <= ny - 2) {
+          if (which == 0 && x0 == 1)
+            scratch[(rr + 1) * TFP_APITCH + 0] = scratch[(rr + 1) * TFP_APITCH + 1];
+          if (which == 1 && xlast == nx - 2)
+            scratch[(rr + 1) * TFP_APITCH + ncols + 1] = scratch[(rr + 1) * TFP_APITCH + ncols];
+        }
+      }
+    }
+    if (y0 == 1 || ylast == ny - 2) {
+      asm volatile("bar.sync 1, %0;" ::"n"(tile::TX));
+      // columns -1 .. ncols: thread c takes column c - 1, threads 0 and 1 also take ncols - 1 + 1 .. (TX + 2 columns, TX threads)
+      for (int cc = c - 1; cc <= ncols; cc += tile::TX) {
+        if (y0 == 1)
+          scratch[0 * TFP_APITCH + cc + 1] = scratch[1 * TFP_APITCH + cc + 1];
+        if (ylast == ny - 2)
+          scratch[(nrows + 1) * TFP_APITCH + cc + 1] = scratch[nrows * TFP_APITCH + cc + 1];
+      }
+    }
+    asm volatile("bar.sync 1, %0;" ::"n"(tile::TX));
+    // phase 2
+    const int i0 = y0 * nx + x;
+    if (all2)
+      return pass2<true, FAST>(tv, maps, ad, nrows, col_ok, i0, nx, undef);
+    return pass2<false, FAST>(tv, maps, ad, nrows, col_ok, i0, nx, undef);
   }
 };
+
+// undefined elements of each field whose flag is not ALL_DEFINED (the fused TFP's all2, see above)
+__global__ void __launch_bounds__(256) count_undefined_kernel(const float* __restrict__ f, int n, int nfields, float undef, const FieldMeta* meta,
+                                                              unsigned long long* counters)
+{
+  const int field = blockIdx.y;
+  if (meta[field].all != 0)
+    return;
+  const float* p = f + (long long)field * n;
+  unsigned bad = 0;
+  for (int i = blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256)
+    bad += is_def(p[i], undef) ? 0u : 1u;
+  bad = __reduce_add_sync(0xffffffffu, bad);
+  if ((threadIdx.x & 31) == 0 && bad)
+    atomicAdd(counters + field, (unsigned long long)bad);
+}
 
 // main kernel over the reference's flat range, then the border ring
 template <class Op>
@@ -1126,7 +1316,7 @@ int fcb200_ilevelgwind(int nx, int ny, const float* mpot, const float* xmapr, co
 
 int fcb200_thermalFrontParameter_batched(int nx, int ny, int nfields, const float* t, const float* xmapr, const float* ymapr, float* tfp,
                                          int* fDefined, float undef)
-{ // FC.cc:2266-2309: gradient(c=3) into scratch (with its fillEdges and flag), then the second five-point pass
+{ // FC.cc:2266-2309, both passes in one kernel (TfpFusedOp)
   if (nx < 3 || ny < 3)
     return 0;
   if (!grid_ok(nx, ny, nfields))
@@ -1137,20 +1327,32 @@ int fcb200_thermalFrontParameter_batched(int nx, int ny, int nfields, const floa
   const float* d_xm = call.in(xmapr, n);
   const float* d_ym = call.in(ymapr, n);
   float* d_out = call.out(tfp, n * nfields);
-  float* d_ad = static_cast<float*>(call.scratch(sizeof(float) * n * nfields));
   const FieldMeta* meta = flags_to_meta(call, fDefined, nfields);
-  unsigned long long* counters = call.counters(2 * nfields); // [0, nfields): pass 1, [nfields, 2 nfields): pass 2
+  unsigned long long* counters = call.counters(2 * nfields); // [0, nfields): undefined elements of T, [nfields, 2 nfields): pass 2
   if (!call.ok())
     return -1;
-  const GradientOp<3> g{d_t, d_xm, d_ym, d_ad};
-  if (!launch_stencil(call, g, nx, ny, nfields, undef, meta, counters))
-    return -1;
-  TfpOp op;
+  bool any_masked = false;
+  for (int k = 0; k < nfields; ++k)
+    any_masked = any_masked || fDefined[k] != ALL_DEFINED;
+  if (any_masked) {
+    if (nfields > 65535) {
+      set_error("fcb200: batch too large for one launch (%d fields)", nfields);
+      return -1;
+    }
+    count_undefined_kernel<<<dim3((unsigned)std::min<size_t>((n + 4095) / 4096, 1024), (unsigned)nfields), 256, 0, call.stream()>>>(d_t, (int)n, nfields, undef, meta,
+                                                                                                                            counters);
+    count_launch();
+  }
+  TfpFusedOp op;
   op.tx = d_t;
-  op.ad = d_ad;
   op.xm = d_xm;
   op.ym = d_ym;
-  op.pass1_counters = counters;
+  op.t_undef = counters;
+  op.meta = meta;
+  op.gnx = nx;
+  op.gny = ny;
+  op.undef_ = undef;
+  op.all1 = false;
   op.o = d_out;
   if (!launch_stencil(call, op, nx, ny, nfields, undef, meta, counters + nfields))
     return -1;

@@ -11,8 +11,8 @@
 //     are brought to shared memory by the TMA unit: one bulk copy (cp.async.bulk, completion on an
 //     mbarrier) per row segment, issued by the lanes of warp 0 -- no registers, no LSU instructions,
 //     and up to NSTAGE fields in flight per CTA whatever the occupancy;
-//   * the grid-constant arrays (xmapr, ymapr, fcoriolis) of the tile sit in REGISTERS for all the
-//     fields of the block (a thread owns one column of the tile);
+//   * the grid-constant arrays (xmapr, ymapr, fcoriolis) of the tile stay on chip for all the fields of
+//     the block (a thread owns one column of the tile and parks its values in shared memory);
 //   * neighbours are read from shared memory, conflict free (consecutive lanes, consecutive words).
 // Fields are dense and unpadded, so a row segment starts anywhere relative to a 16-byte boundary
 // (nx = 949 is odd; fields of a batch are 4-byte aligned only).  A bulk copy needs 16-byte aligned
@@ -92,14 +92,19 @@ template <class Op>
 struct TileLayout
 {
   static constexpr int TY = Op::TY;
+  static constexpr int HX = Op::HX;     // halo columns staged left and right of the tile (1, or 2 for the fused TFP)
+  __host__ __device__ static constexpr int hmax(int k) { return k < 0 ? 0 : (Op::halo(k) > hmax(k - 1) ? Op::halo(k) : hmax(k - 1)); }
+  static constexpr int HMAX = hmax(Op::NARR - 1); // largest row halo of the operator's arrays
   __host__ __device__ static constexpr int rows(int k) { return TY + 2 * Op::halo(k); }
   __host__ __device__ static constexpr int row0(int k) { return k == 0 ? 0 : row0(k - 1) + rows(k - 1); } // first row slot of array k
   static constexpr int ROWS = row0(Op::NARR);                                                             // row slots per stage
   static constexpr int STAGE_FLOATS = ROWS * PITCH;
-  static constexpr size_t smem_bytes(int stages) { return 128 + (size_t)stages * STAGE_FLOATS * sizeof(float); } // 128: the mbarriers
+  // 128 bytes of mbarriers, the stages, the operator's own scratch (the fused TFP's |grad T| tile), the maps
+  static constexpr int MAP_FLOATS = Op::NMAPS * TY * TX; // the tile's grid-constant values, one private slot per consumer thread and row
+  static constexpr size_t smem_bytes(int stages) { return 128 + ((size_t)stages * STAGE_FLOATS + Op::EXTRA_FLOATS + MAP_FLOATS) * sizeof(float); }
 };
 
-// What a consumer thread needs to index the staged rows of one field.  off[rr + 1] is the float offset,
+// What a consumer thread needs to index the staged rows of one field.  off[rr + HMAX] is the float offset,
 // from the stage's base, of "array 0, tile row rr, this thread's column": the row's shift (0..3
 // elements, it grows by nx & 3 per row) is folded in, so a neighbour is ONE LDS with an immediate
 // offset.  Every per-field array of an operator has the same shift pattern (the host checks that
@@ -108,25 +113,42 @@ template <class Op>
 struct TileView
 {
   const float* stage;
-  int off[Op::TY + 2];
+  int off[Op::TY + 2 * TileLayout<Op>::HMAX];
+  // array K at tile row rr (-halo(K) .. TY-1+halo(K)) and column delta dc (|dc| <= HX) from the thread's column
   template <int K>
   __device__ __forceinline__ float at(int rr, int dc) const
   {
     typedef TileLayout<Op> L;
     constexpr int KOFF = (L::row0(K) + Op::halo(K) - Op::halo(0)) * PITCH;
-    return stage[off[rr + 1] + KOFF + dc];
+    return stage[off[rr + L::HMAX] + KOFF + dc];
   }
-  // sh0 = shift of tile row 0, c = the thread's column in the tile
+  // sh0 = shift of tile row 0, c = the thread's column counted from the first staged column
   __device__ __forceinline__ void set_rows(int sh0, int snx, int c)
   {
-    int sh = (sh0 - snx) & 3; // row -1
+    typedef TileLayout<Op> L;
+    int sh = (sh0 - L::HMAX * snx) & 3; // row -HMAX
 #pragma unroll
-    for (int q = 0; q < Op::TY + 2; ++q) {
-      off[q] = (Op::halo(0) + q - 1) * PITCH + sh + c + 1;
+    for (int q = 0; q < Op::TY + 2 * L::HMAX; ++q) {
+      off[q] = (Op::halo(0) + q - L::HMAX) * PITCH + sh + c;
       sh = (sh + snx) & 3;
     }
   }
 };
+
+// The tile's grid-constant values (xmapr, ymapr, fcoriolis) stay on chip for every field of the block.  Each
+// consumer thread parks the values of ITS column in shared memory (slot [k][r][c]: private to the thread, so
+// no barrier; consecutive lanes, consecutive words) instead of 16..24 registers.
+struct MapSlots
+{
+  const float* p; // this thread's column of map 0, row 0
+  __device__ __forceinline__ float get(int k, int r, int ty) const { return p[(k * ty + r) * TX]; }
+};
+
+// 0.5f * m is exact in float (see half_map_diff_f in ops_stencil.cu)
+__device__ __forceinline__ bool map_is_regular(float m)
+{
+  return fabsf(m) >= 7.8886e-31f /* 2^-100 */ || m == 0.f; // false for NaN
+}
 
 // the fields of a block in an order that keeps fields of equal alignment together (fields k and k + period
 // start at the same offset from a 16-byte boundary): the consumers rebuild their row offsets only when
@@ -145,9 +167,8 @@ struct FieldOrder
   }
 };
 
-template <class Op, bool ALL, bool FULL>
-__device__ __forceinline__ unsigned tile_compute(const Op& op, const TileView<Op>& tv, const float (&maps)[Op::NMAPS > 0 ? Op::NMAPS : 1][Op::TY], int i0,
-                                                 bool col_ok, int nrows, int nx, float undef)
+template <class Op, bool ALL, bool FULL, bool FAST>
+__device__ __forceinline__ unsigned tile_compute(const Op& op, const TileView<Op>& tv, const MapSlots& maps, int i0, bool col_ok, int nrows, int nx, float undef)
 {
   unsigned nundef = 0;
   float* o[Op::NOUT];
@@ -160,11 +181,11 @@ __device__ __forceinline__ unsigned tile_compute(const Op& op, const TileView<Op
       float m[Op::NMAPS > 0 ? Op::NMAPS : 1];
 #pragma unroll
       for (int k = 0; k < Op::NMAPS; ++k)
-        m[k] = maps[k][r];
+        m[k] = maps.get(k, r, Op::TY);
       // columns past the tile's last one compute on whatever the stage holds there; nothing is stored or counted
       const typename Op::template In<ALL> in = op.template fetch<ALL>(tv, r, m);
       float val[Op::NOUT];
-      const bool ok = op.template eval<ALL>(in, undef, val);
+      const bool ok = op.template eval<ALL, FAST>(in, undef, val);
       if ((!ALL || Op::TESTS_WHEN_ALL) && col_ok && !ok)
         nundef += 1;
 #pragma unroll
@@ -221,14 +242,34 @@ __global__ void __launch_bounds__(TILE_THREADS, 2) stencil_tile_kernel(const Op 
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  __syncthreads();
+  // consumers: park the grid-constant values of their column (rows of the tile) in shared memory and check
+  // that the float shortcut for 0.5 * map * difference is exact for all of them
+  float* extra = stage0 + (size_t)S * L::STAGE_FLOATS; // the operator's scratch, then the map slots
+  MapSlots maps;
+  maps.p = extra + Op::EXTRA_FLOATS + threadIdx.x;
+  int irregular = 0;
+  if (warp < CONSUMER_WARPS) {
+    const int x = x0 + (int)threadIdx.x;
+#pragma unroll
+    for (int k = 0; k < NMAPS; ++k) {
+      const float* mp = op0.map(k);
+#pragma unroll
+      for (int r = 0; r < TY; ++r) {
+        const float m = (x <= xlast && y0 + r <= ylast) ? mp[(y0 + r) * nx + x] : 0.f;
+        extra[Op::EXTRA_FLOATS + (k * TY + r) * TX + threadIdx.x] = m;
+        irregular |= map_is_regular(m) ? 0 : 1;
+      }
+    }
+  }
+  const bool fast = __syncthreads_or(irregular) == 0;
 
   FieldOrder order(g.period, nf);
   int s = 0;
   unsigned phase = 0; // parity of the current round over the stages
   if (warp == CONSUMER_WARPS) {
     // ---------------------------------------------------------------- producer
-    const int ncols = xlast - x0 + 3; // x0-1 .. xlast+1
+    const int xs = max(x0 - L::HX, 0);                      // first staged column
+    const int ncols = min(xlast + L::HX, nx - 1) - xs + 1; // .. last staged column
 #pragma unroll 1
     for (int j = 0; j < nf; ++j) {
       mbar_wait(&empty[s], phase ^ 1u); // passes at once the first time a stage is used
@@ -250,11 +291,12 @@ __global__ void __launch_bounds__(TILE_THREADS, 2) stencil_tile_kernel(const Op 
             if (slot >= L::row0(a))
               k = a;
           const int y = y0 + slot - L::row0(k) - Op::halo(k); // tile rows -halo .. TY-1+halo
-          if (y <= ylast + Op::halo(k)) {
-            const float* p = op.arr(k) + (long long)y * nx + (x0 - 1);
+          if (y >= 0 && y <= min(ylast + Op::halo(k), ny - 1)) {
+            const float* p = op.arr(k) + (long long)y * nx + xs;
             const int sh = (int)((reinterpret_cast<uintptr_t>(p) >> 2) & 3);
+            const int cols = ncols;
             src[q] = p - sh;
-            len[q] = (unsigned)((sh + ncols + 3) & ~3) * 4u;
+            len[q] = (unsigned)((sh + cols + 3) & ~3) * 4u;
             bytes += len[q];
           }
         }
@@ -275,16 +317,8 @@ __global__ void __launch_bounds__(TILE_THREADS, 2) stencil_tile_kernel(const Op 
     const int c = threadIdx.x, x = x0 + c;
     const bool col_ok = x <= xlast;
     const int nrows = ylast - y0 + 1;
+    const int xs = max(x0 - L::HX, 0); // first staged column
     const int i0 = y0 * nx + x;
-    // the grid-constant arrays of this thread's column, in registers for every field of the block
-    float maps[NMAPS > 0 ? NMAPS : 1][TY];
-#pragma unroll
-    for (int k = 0; k < NMAPS; ++k) {
-      const float* mp = op0.map(k);
-#pragma unroll
-      for (int r = 0; r < TY; ++r)
-        maps[k][r] = (col_ok && r < nrows) ? mp[i0 + r * nx] : 0.f;
-    }
     TileView<Op> tv;
     int cur_sh0 = -1;
 #pragma unroll 1
@@ -292,24 +326,26 @@ __global__ void __launch_bounds__(TILE_THREADS, 2) stencil_tile_kernel(const Op 
       const int field = f0 + order.f;
       const Op op = op0.at(field, g.n);
       const bool all = op0.all_defined(field, g.meta[field].all != 0);
-      const int sh0 = (int)(((reinterpret_cast<uintptr_t>(op.arr(0)) >> 2) + (unsigned long long)y0 * nx + (x0 - 1)) & 3);
+      const int sh0 = (int)(((reinterpret_cast<uintptr_t>(op.arr(0)) >> 2) + (long long)y0 * nx + xs) & 3);
       if (sh0 != cur_sh0) { // warp-uniform
-        tv.set_rows(sh0, nx & 3, c);
+        tv.set_rows(sh0, nx & 3, c + (x0 - xs));
         cur_sh0 = sh0;
       }
       tv.stage = stage0 + (size_t)s * L::STAGE_FLOATS;
       mbar_wait(&full[s], phase);
       unsigned nundef;
-      if (nrows == TY) {
+      if (Op::CUSTOM_TILE) {
+        nundef = op.tile_custom(tv, maps, extra, all, fast, x0, y0, xlast, ylast, c, nx, ny, g.undef);
+      } else if (nrows == TY && fast) {
         if (all)
-          nundef = tile_compute<Op, true, true>(op, tv, maps, i0, col_ok, nrows, nx, g.undef);
+          nundef = tile_compute<Op, true, true, true>(op, tv, maps, i0, col_ok, nrows, nx, g.undef);
         else
-          nundef = tile_compute<Op, false, true>(op, tv, maps, i0, col_ok, nrows, nx, g.undef);
-      } else {
+          nundef = tile_compute<Op, false, true, true>(op, tv, maps, i0, col_ok, nrows, nx, g.undef);
+      } else { // the grid's last tile row, or a tile with a tiny / NaN map ratio: the reference's double arithmetic
         if (all)
-          nundef = tile_compute<Op, true, false>(op, tv, maps, i0, col_ok, nrows, nx, g.undef);
+          nundef = tile_compute<Op, true, false, false>(op, tv, maps, i0, col_ok, nrows, nx, g.undef);
         else
-          nundef = tile_compute<Op, false, false>(op, tv, maps, i0, col_ok, nrows, nx, g.undef);
+          nundef = tile_compute<Op, false, false, false>(op, tv, maps, i0, col_ok, nrows, nx, g.undef);
       }
       __syncwarp();
       if (lane == 0)
