@@ -966,41 +966,88 @@ struct ShapiroGeom
   static constexpr int USEFUL = (32 - 2 * HL) * W;      // output columns per warp strip
 };
 
-template <int W, bool ALL>
-__device__ __forceinline__ void shapiro_xpass(const float (&f)[W], float (&out)[W], double s, unsigned wbits, unsigned copybits)
+// One point of one pass of the all-defined branch: (float)(f + s*((lo + hi) - 2.*f)), float sum, the rest in double
+// (FC.cc:2113, 2121).  The three float<->double conversions per point and pass run on the quarter-rate XU
+// pipe (16/clk/SM on B200): with all four passes in double the kernel is XU-bound at a third of the HBM
+// roofline.  FLOATPATH evaluates the same value in float: T = S - 2f (S = lo + hi) is checked for
+// exactness with Knuth's TwoSum; if it is exact (smooth data: always), f + s*T is a sum of two floats,
+// for which rounding through double and rounding once agree, and that single rounding is fmaf(s, T, f).
+// Anything else -- inexact T, NaN, infinities -- takes the double expression.  Half of the passes use
+// each path so that neither the XU pipe nor the issue slots saturate.
+__device__ __forceinline__ float shapiro_point_double(float lo, float f, float hi, double sd)
 {
-  const float left = __shfl_up_sync(0xffffffffu, f[W - 1], 1);
-  const float right = __shfl_down_sync(0xffffffffu, f[0], 1);
+  return (float)fma(sd, fma(-2.0, (double)f, (double)(lo + hi)), (double)f);
+}
+// float evaluation; `inexact` is raised when the result must not be used
+__device__ __forceinline__ float shapiro_point_float(float lo, float f, float hi, float sf, bool& inexact)
+{
+  const float S = lo + hi;
+  const float b = f + f;
+  const float T = S - b;
+  const float a1 = T + b;    // TwoSum(S, -b): a1 ~ S
+  const float b1 = T - a1;   //                b1 ~ -b
+  const float da = S - a1;
+  const float db = (-b) - b1;
+  const float err = da + db; // the rounding error of T, exactly (NaN if anything overflowed)
+  inexact = inexact || !(err == 0.f);
+  return __fmaf_rn(sf, T, f);
+}
+template <int W, bool ALL, bool FLOATPATH>
+__device__ __forceinline__ void shapiro_pass(const float (&lo)[W], const float (&f)[W], const float (&hi)[W], float (&r)[W], float s, unsigned wbits)
+{
+  if (!ALL) {
 #pragma unroll
-  for (int j = 0; j < W; ++j) {
-    const float lo = (j == 0) ? left : f[j - 1];
-    const float hi = (j == W - 1) ? right : f[j + 1];
-    float r;
-    if (ALL) {
-      r = (float)fma(s, fma(-2.0, (double)f[j], (double)(lo + hi)), (double)f[j]);
-    } else {
+    for (int j = 0; j < W; ++j) {
       const float w = ((wbits >> j) & 1u) ? 0.25f : 0.f;
-      r = f[j] + w * (lo + hi - 2.f * f[j]);
+      r[j] = f[j] + w * (lo[j] + hi[j] - 2.f * f[j]);
     }
-    out[j] = ((copybits >> j) & 1u) ? f[j] : r;
+  } else if (FLOATPATH) {
+    bool inexact = false;
+#pragma unroll
+    for (int j = 0; j < W; ++j)
+      r[j] = shapiro_point_float(lo[j], f[j], hi[j], s, inexact);
+    if (__any_sync(0xffffffffu, inexact)) { // rare, warp-uniform: a real branch, not a select
+#pragma unroll
+      for (int j = 0; j < W; ++j)
+        r[j] = shapiro_point_double(lo[j], f[j], hi[j], (double)s);
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < W; ++j)
+      r[j] = shapiro_point_double(lo[j], f[j], hi[j], (double)s);
   }
 }
 
-template <int W, bool ALL>
-__device__ __forceinline__ void shapiro_ypass(const float (&lo)[W], const float (&f)[W], const float (&hi)[W], float (&out)[W], double s,
-                                              unsigned wbits, bool copy)
+template <int W, bool ALL, bool FLOATPATH>
+__device__ __forceinline__ void shapiro_xpass(const float (&f)[W], float (&out)[W], float s, unsigned wbits, unsigned copybits)
 {
+  float lo[W], hi[W], r[W];
+  lo[0] = __shfl_up_sync(0xffffffffu, f[W - 1], 1);
+  hi[W - 1] = __shfl_down_sync(0xffffffffu, f[0], 1);
 #pragma unroll
-  for (int j = 0; j < W; ++j) {
-    float r;
-    if (ALL) {
-      r = (float)fma(s, fma(-2.0, (double)f[j], (double)(lo[j] + hi[j])), (double)f[j]);
-    } else {
-      const float w = ((wbits >> j) & 1u) ? 0.25f : 0.f;
-      r = f[j] + w * (lo[j] + hi[j] - 2.f * f[j]);
-    }
-    out[j] = copy ? f[j] : r;
+  for (int j = 1; j < W; ++j) {
+    lo[j] = f[j - 1];
+    hi[j - 1] = f[j];
   }
+  shapiro_pass<W, ALL, FLOATPATH>(lo, f, hi, r, s, wbits);
+  // columns 0 and nx-1 are copied.  W = 4: x0 and nx are multiples of 4, so they can only be the lane's
+  // first resp. last column
+#pragma unroll
+  for (int j = 0; j < W; ++j)
+    out[j] = ((W == 1 || j == 0 || j == W - 1) && ((copybits >> j) & 1u)) ? f[j] : r[j];
+}
+
+template <int W, bool ALL, bool FLOATPATH>
+__device__ __forceinline__ void shapiro_ypass(const float (&lo)[W], const float (&f)[W], const float (&hi)[W], float (&out)[W], float s, unsigned wbits,
+                                              bool copy)
+{
+  if (copy) { // rows 0 and ny-1 (and rows outside the grid): warp-uniform
+#pragma unroll
+    for (int j = 0; j < W; ++j)
+      out[j] = f[j];
+    return;
+  }
+  shapiro_pass<W, ALL, FLOATPATH>(lo, f, hi, out, s, wbits);
 }
 
 template <int W, bool ALL>
@@ -1078,11 +1125,11 @@ __device__ __forceinline__ void shapiro_band(const float* __restrict__ src, floa
       }
       // iteration 1: x pass on row r, y pass on row r-1
       float a2[W], b[W], c2[W], d[W];
-      shapiro_xpass<W, ALL>(f, a2, 0.25, mx, copybits);
-      shapiro_ypass<W, ALL>(a0, a1, a2, b, 0.25, my, r - 1 <= 0 || r - 1 >= ny - 1);
+      shapiro_xpass<W, ALL, true>(f, a2, 0.25f, mx, copybits);
+      shapiro_ypass<W, ALL, true>(a0, a1, a2, b, 0.25f, my, r - 1 <= 0 || r - 1 >= ny - 1);
       // iteration 2: x pass on row r-1, y pass on row r-2
-      shapiro_xpass<W, ALL>(b, c2, -0.25, mx_prev, copybits);
-      shapiro_ypass<W, ALL>(c0, c1, c2, d, -0.25, my_prev, r - 2 <= 0 || r - 2 >= ny - 1);
+      shapiro_xpass<W, ALL, true>(b, c2, -0.25f, mx_prev, copybits);
+      shapiro_ypass<W, ALL, false>(c0, c1, c2, d, -0.25f, my_prev, r - 2 <= 0 || r - 2 >= ny - 1);
       const int ro = r - 2;
       if (store_lane && ro >= r0 && ro < r1) {
         float* p = dst + (long long)ro * nx + x0;
