@@ -30,6 +30,7 @@ struct EnsArgs
   const int* member_flags;     // device [ntimes][M]
   const FieldMeta* meta;       // per time: all = input flag ALL_DEFINED (extremeValue), a = probability divisor lo, b = hi (double split)
   const double* prob_div;      // per time: nfields_defined / 100.0 (probability c1-3), or nullptr
+  const float* recip;          // [M]: {j+1 as float, RN(1 / (j+1))} pairs for the all-defined Welford update
   float* out;
   unsigned long long* counters;
   long long n;
@@ -41,9 +42,18 @@ struct EnsArgs
 };
 
 // W points starting at `base` of one time step: walk the members in order, then store.
-template <int MODE, int W>
-__device__ __forceinline__ void ensemble_points(const EnsArgs& a, const float* const* mptr, const int* mflag, int time, long long base, float* out,
-                                                bool in_all, unsigned& nundef)
+// FAST = every member field of this time step is flagged ALL_DEFINED (and, for extremeValue, the in/out flag
+// too): no per-point definedness test at all, like the reference's allDefined short-circuit -- and the
+// Welford divisor is the same j+1 for every point, so `delta / n` becomes a multiplication by the
+// correctly rounded reciprocal RN(1/n) plus one residual correction (Markstein):
+//   q0 = RN(delta*y), r = delta - n*q0 (exact, one fma), q = RN(q0 + r*y)
+// q is the correctly rounded quotient for normal operands: |q0 + r*y - delta/n| <= 2^-47 |delta/n| while a
+// quotient of a 24-bit float by an integer n <= 4096 that is not itself a float is at least 2^-36 away
+// (relative) from every rounding boundary, and cannot be an exact tie (n*midpoint has >= 25 significant
+// bits).  Zero, tiny, huge and non-finite deltas take the IEEE division.
+template <int MODE, int W, bool FAST>
+__device__ __forceinline__ void ensemble_points(const EnsArgs& a, const float* const* mptr, const int* mflag, const float2* recip, int time,
+                                                long long base, float* out, bool in_all, unsigned& nundef)
 {
   const float undef = a.undef;
   const int M = a.nmembers;
@@ -56,12 +66,16 @@ __device__ __forceinline__ void ensemble_points(const EnsArgs& a, const float* c
     cnt[w] = 0;
   }
   const bool want_max = (a.compute == 1 || a.compute == 3);
+  float dmax = 1.f, dmin = 1.f; // range of |delta| seen by the reciprocal-based Welford update
 
 #pragma unroll 6
   for (int j = 0; j < M; ++j) {
-    const int fl = mflag[j];
+    const int fl = FAST ? (MF_ALL | MF_NOT_NONE) : mflag[j];
     if (MODE == EN_PROB && !(fl & MF_NOT_NONE))
       continue; // a member whose FIELD flag is NONE_DEFINED is not counted (FC.cc:2841)
+    float2 ny = make_float2(0.f, 0.f);
+    if (MODE == EN_STDDEV && FAST)
+      ny = recip[j];
     float x[W];
     if constexpr (W == 4) {
       const float4 q = *reinterpret_cast<const float4*>(mptr[j] + base);
@@ -80,6 +94,14 @@ __device__ __forceinline__ void ensemble_points(const EnsArgs& a, const float* c
           cnt[w] += 1;
           acc0[w] += xv;
         }
+      } else if (MODE == EN_STDDEV && FAST) {
+        const float delta = xv - acc0[w];
+        const float q0 = delta * ny.y;
+        const float rem = __fmaf_rn(-q0, ny.x, delta);
+        acc0[w] += __fmaf_rn(rem, ny.y, q0);
+        acc1[w] += delta * (xv - acc0[w]);
+        dmax = fmaxf(dmax, fabsf(delta)); // (a NaN delta makes the result NaN on either path)
+        dmin = fminf(dmin, fabsf(delta));
       } else if (MODE == EN_STDDEV) { // FC.cc:2739-2747, Welford in float, no FMA
         if ((fl & MF_ALL) || is_def(xv, undef)) {
           const float delta = xv - acc0[w];
@@ -88,7 +110,7 @@ __device__ __forceinline__ void ensemble_points(const EnsArgs& a, const float* c
           acc1[w] += delta * (xv - acc0[w]);
         }
       } else if (MODE == EN_EXTREME) { // FC.cc:2778-2783, 2792-2798
-        if (acc0[w] == undef || ((in_all || is_def(xv, undef)) && (want_max ? (acc0[w] < xv) : (acc0[w] > xv)))) {
+        if (acc0[w] == undef || ((FAST || in_all || is_def(xv, undef)) && (want_max ? (acc0[w] < xv) : (acc0[w] > xv)))) {
           acc0[w] = xv;
           acc1[w] = (float)j;
         }
@@ -99,9 +121,17 @@ __device__ __forceinline__ void ensemble_points(const EnsArgs& a, const float* c
     }
   }
 
+  if (MODE == EN_STDDEV && FAST && !(dmin >= 1e-30f && dmax <= 1e30f)) {
+    // a zero, tiny, huge or infinite delta: the correction above is only proven for normal operands -- redo
+    // these points with the IEEE division
+    ensemble_points<MODE, W, false>(a, mptr, mflag, recip, time, base, out, in_all, nundef);
+    return;
+  }
   float r[W];
 #pragma unroll
   for (int w = 0; w < W; ++w) {
+    if ((MODE == EN_MEAN || MODE == EN_STDDEV) && FAST)
+      cnt[w] = M;
     if (MODE == EN_MEAN) {
       if (cnt[w] > 0)
         r[w] = acc0[w] / (float)cnt[w];
@@ -142,7 +172,8 @@ __global__ void __launch_bounds__(EN_THREADS) ensemble_kernel(const EnsArgs a)
 {
   extern __shared__ unsigned char smem_raw[];
   const float** mptr = reinterpret_cast<const float**>(smem_raw);
-  int* mflag = reinterpret_cast<int*>(smem_raw + sizeof(float*) * a.nmembers);
+  float2* recip = reinterpret_cast<float2*>(smem_raw + sizeof(float*) * a.nmembers);
+  int* mflag = reinterpret_cast<int*>(smem_raw + (sizeof(float*) + sizeof(float2)) * a.nmembers);
 
   const int time = blockIdx.x / a.chunks;
   const int chunk = blockIdx.x - time * a.chunks;
@@ -151,6 +182,7 @@ __global__ void __launch_bounds__(EN_THREADS) ensemble_kernel(const EnsArgs a)
   for (int j = threadIdx.x; j < M; j += EN_THREADS) {
     mptr[j] = a.members[j] + (long long)time * n;
     mflag[j] = a.member_flags[(long long)time * M + j];
+    recip[j] = reinterpret_cast<const float2*>(a.recip)[j];
   }
   __syncthreads();
 
@@ -159,11 +191,16 @@ __global__ void __launch_bounds__(EN_THREADS) ensemble_kernel(const EnsArgs a)
   const long long groups = (n - head) / W;
   float* out = a.out + (long long)time * n;
   const bool in_all = a.meta[time].all != 0;
+  const bool fast = a.meta[time].c != 0.f; // every member ALL_DEFINED (and the in/out flag for extremeValue)
   unsigned nundef = 0;
 
   const long long g = (long long)chunk * EN_THREADS + threadIdx.x;
-  if (g < groups)
-    ensemble_points<MODE, W>(a, mptr, mflag, time, head + g * W, out, in_all, nundef);
+  if (g < groups) {
+    if (fast)
+      ensemble_points<MODE, W, true>(a, mptr, mflag, recip, time, head + g * W, out, in_all, nundef);
+    else
+      ensemble_points<MODE, W, false>(a, mptr, mflag, recip, time, head + g * W, out, in_all, nundef);
+  }
 
   if (W == 4 && chunk == 0) {
     const long long tail0 = head + groups * 4;
@@ -174,7 +211,7 @@ __global__ void __launch_bounds__(EN_THREADS) ensemble_kernel(const EnsArgs a)
     else if (threadIdx.x >= 32 && (int)threadIdx.x - 32 < ntail)
       idx = tail0 + (threadIdx.x - 32);
     if (idx >= 0)
-      ensemble_points<MODE, 1>(a, mptr, mflag, time, idx, out, in_all, nundef);
+      ensemble_points<MODE, 1, false>(a, mptr, mflag, recip, time, idx, out, in_all, nundef);
   }
 
   dev::block_add_counter(nundef, a.counters + time);
@@ -229,40 +266,61 @@ int run_ensemble(const EnsHost& h)
   if (!call.ok())
     return -1;
 
-  std::vector<int> mflags((size_t)h.ntimes * (M > 0 ? M : 1), 0);
-  std::vector<double> pdiv(h.ntimes, 1.0);
-  FieldMeta* meta = call.meta_host(h.ntimes);
-  if (!call.ok())
-    return -1;
+  // every small table of the call in ONE host-to-device copy: member pointers, {n, 1/n} pairs, member flags,
+  // per-time metadata, probability divisors
+  const size_t Mp = (size_t)(M > 0 ? M : 1);
+  const size_t off_ptr = 0;
+  const size_t off_rcp = off_ptr + sizeof(float*) * Mp;
+  const size_t off_meta = (off_rcp + sizeof(float) * 2 * Mp + 15) & ~size_t(15);
+  const size_t off_div = off_meta + sizeof(FieldMeta) * (size_t)h.ntimes;
+  const size_t off_flag = off_div + sizeof(double) * (size_t)h.ntimes;
+  const size_t blob_bytes = off_flag + sizeof(int) * (size_t)h.ntimes * Mp;
+  std::vector<unsigned char> blob(blob_bytes, 0);
+  const float** b_ptr = reinterpret_cast<const float**>(blob.data() + off_ptr);
+  float* b_rcp = reinterpret_cast<float*>(blob.data() + off_rcp);
+  FieldMeta* meta = reinterpret_cast<FieldMeta*>(blob.data() + off_meta);
+  double* pdiv = reinterpret_cast<double*>(blob.data() + off_div);
+  int* mflags = reinterpret_cast<int*>(blob.data() + off_flag);
+  for (int j = 0; j < M; ++j) {
+    b_ptr[j] = dptr[j];
+    b_rcp[2 * j] = (float)(j + 1);
+    b_rcp[2 * j + 1] = 1.0f / (float)(j + 1); // IEEE: the correctly rounded reciprocal
+  }
   for (int t = 0; t < h.ntimes; ++t) {
     int counted = 0;
+    bool all_members = h.fDefinedIn != nullptr || h.mode == EN_EXTREME;
     for (int j = 0; j < M; ++j) {
       int f = 0;
       if (h.fDefinedIn) {
         const int fd = h.fDefinedIn[(size_t)t * M + j];
         if (fd == ALL_DEFINED)
           f |= MF_ALL;
+        else
+          all_members = false;
         if (fd != NONE_DEFINED) {
           f |= MF_NOT_NONE;
           counted += 1;
         }
       }
-      mflags[(size_t)t * M + j] = f;
+      mflags[(size_t)t * Mp + j] = f;
     }
     meta[t].all = (h.mode == EN_EXTREME && h.fDefinedOut[t] == ALL_DEFINED) ? 1 : 0;
+    if (h.mode == EN_EXTREME)
+      all_members = meta[t].all != 0;
     meta[t].a = 0.f;
     meta[t].b = (float)counted;
-    meta[t].c = 0.f;
+    meta[t].c = (all_members && M > 0) ? 1.f : 0.f;
     pdiv[t] = counted / 100.0; // FC.cc:2855
   }
-  a.members = static_cast<const float* const*>(call.upload_small(dptr.data(), sizeof(float*) * dptr.size()));
-  a.member_flags = static_cast<const int*>(call.upload_small(mflags.data(), sizeof(int) * mflags.size()));
-  if (h.mode == EN_PROB)
-    a.prob_div = static_cast<const double*>(call.upload_small(pdiv.data(), sizeof(double) * pdiv.size()));
-  a.meta = call.upload_meta();
+  const unsigned char* d_blob = static_cast<const unsigned char*>(call.upload_small(blob.data(), blob_bytes));
   a.counters = call.counters(h.ntimes);
-  if (!call.ok())
+  if (!call.ok() || !d_blob)
     return -1;
+  a.members = reinterpret_cast<const float* const*>(d_blob + off_ptr);
+  a.recip = reinterpret_cast<const float*>(d_blob + off_rcp);
+  a.meta = reinterpret_cast<const FieldMeta*>(d_blob + off_meta);
+  a.prob_div = reinterpret_cast<const double*>(d_blob + off_div);
+  a.member_flags = reinterpret_cast<const int*>(d_blob + off_flag);
 
   a.out = d_out;
   a.n = n;
@@ -286,7 +344,7 @@ int run_ensemble(const EnsHost& h)
     set_error("fcb200: batch too large for one launch (%lld CTAs)", grid);
     return -1;
   }
-  const size_t smem = (sizeof(float*) + sizeof(int)) * (size_t)(M > 0 ? M : 1);
+  const size_t smem = (sizeof(float*) + sizeof(float2) + sizeof(int)) * Mp;
 
 #define FCB_LAUNCH_ENS(MODE)                                                                                                                         \
   do {                                                                                                                                               \
