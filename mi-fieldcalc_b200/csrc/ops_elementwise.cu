@@ -422,26 +422,25 @@ struct AlevelChainOp
   // Straight-line code: every value is computed unconditionally (the helpers are safe on any bit
   // pattern) and the definedness tests only select between value and undef at the end, so the
   // ALL_DEFINED instantiation contains no test at all and the other one no divergent branch.
-  // SAFE = the whole warp's inputs are physically plausible (t 100..400 K, p 0.01..2000 hPa, q 0 or 1e-12..1, table
-  // lookup in range): every float division below then has operands far from subnormals / overflow and uses the
-  // check-free sequence (dev::fdiv_nocheck) -- five divisions per point, each otherwise an FCHK + branch.
-  template <bool ALL, bool SAFE>
-  __device__ __forceinline__ void point_impl(float t, float q, float p, const dev::Ewt& e, float* out, const PointCtx& c, unsigned* nundef) const
+  // (Replacing the five float divisions by a check-free reciprocal sequence behind a warp vote on "all
+  // inputs physically plausible" was measured 9 % SLOWER than the compiler's FCHK-guarded division.)
+  template <bool ALL>
+  __device__ __forceinline__ void point(const float* in, float* out, const PointCtx& c, long long, unsigned* nundef) const
   {
+    const float t = in[0], q = in[1], p = in[2];
     const float undef = c.undef;
     const bool dt = ALL || is_def(t, undef), dq = ALL || is_def(q, undef), dp = ALL || is_def(p, undef);
 
     const float pidcp = dev::pidcp_from_p(c.pw, p);
-    const float theta = SAFE ? dev::fdiv_nocheck(t, pidcp) : t / pidcp;
-    const float the_num = t * K_CP + q * K_XLH, the_den = K_CP * pidcp;
-    const float the = SAFE ? dev::fdiv_nocheck(the_num, the_den) : the_num / the_den;
+    const float theta = t / pidcp;
+    const float the = (t * K_CP + q * K_XLH) / (K_CP * pidcp);
 
+    const dev::Ewt e(t - K_T0);
     const float et = e.value(c.tab);
-    const float qs_num = dev::K_EPS * et;
-    const float qsat = SAFE ? dev::fdiv_nocheck(qs_num, p) : qs_num / p;
+    const float qsat = dev::K_EPS * et / p;
     const float rh = (float)(100. * (double)q / (double)qsat);
-    const float rhc = dev::clamp_rh(SAFE ? dev::fdiv_nocheck(q, qsat) : q / qsat);
-    const float td = e.template inverse<SAFE>(c.tab, rhc * et) + tdconv;
+    const float rhc = dev::clamp_rh(q / qsat);
+    const float td = e.inverse(c.tab, rhc * et) + tdconv;
 
     const bool ok_theta = dt && dp;            // aleveltemp tests t, p
     const bool ok_hum = dt && dq && e.defined; // alevelhum c1/c5 test t, q only; an undefined p flows into the arithmetic
@@ -454,17 +453,6 @@ struct AlevelChainOp
     nundef[1] += ok_hum ? 0u : 1u;
     nundef[2] += ok_hum ? 0u : 1u;
     nundef[3] += ok_the ? 0u : 1u;
-  }
-  template <bool ALL>
-  __device__ __forceinline__ void point(const float* in, float* out, const PointCtx& c, long long, unsigned* nundef) const
-  {
-    const float t = in[0], q = in[1], p = in[2];
-    const dev::Ewt e(t - K_T0);
-    const bool safe = (t >= 100.f && t <= 400.f) && (p >= 0.01f && p <= 2000.f) && (q == 0.f || (q >= 1e-12f && q <= 1.f)) && e.defined;
-    if (__all_sync(__activemask(), safe))
-      point_impl<ALL, true>(t, q, p, e, out, c, nundef);
-    else
-      point_impl<ALL, false>(t, q, p, e, out, c, nundef);
   }
 };
 
