@@ -43,7 +43,7 @@ BYTES_UNFUSED = {"aleveltemp": 12, "alevelhum_rh": 16, "alevelhum_td": 16, "alev
 BYTES_FUSED = 28
 # dram__bytes_read.sum + dram__bytes_write.sum of one fused-chain launch (65 levels), from the ncu --set full
 # capture committed under profiles/ (None until captured)
-TRAFFIC_NCU = None
+TRAFFIC_NCU = 1801.2e6  # profiles/r01_ncu_full_chain_summary.csv: 791.8 MB read + 1009.4 MB written (algorithmic: 1846 MB)
 
 
 def peaks():
@@ -306,7 +306,7 @@ def run_product(args):
     achieved = BYTES_FUSED * points_per_step / (kern_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "kernel": "ew_kernel<AlevelChainOp, 4> (fused chain)", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": TRAFFIC_NCU, "peak_source": peak_src, "algorithmic_bytes_per_point": BYTES_FUSED,
-                "kernel_ms": kern_ms, "note": "issue-bound, not HBM-bound: ~155 instructions per point (ncu, profiles/)"}
+                "kernel_ms": kern_ms, "note": "issue-bound, not HBM-bound: ~250 instructions per point, 72 % issue-slot utilisation (ncu, profiles/r01_ncu_full_chain_summary.csv)"}
 
     # for the record: the same step as the UNFUSED reference call sequence (four batched launches, 60 B/point)
     gpu.begin_deferred()
