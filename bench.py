@@ -215,6 +215,21 @@ def cpu_baseline_sample(nlev=6, reps=2):
             "sample": "%d of %d levels, best of %d after one warm-up pass, chain of 4 reference calls per level" % (nlev, NLEV, reps)}
 
 
+class stdout_to_stderr:
+    """NCCL prints its version banner on stdout when a communicator is created; the contract is ONE JSON line
+    on stdout, so file descriptor 1 points at stderr while the process group comes up."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+
+    def __exit__(self, *exc):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+
+
 # ------------------------------------------------------------------------------------- product arm
 def chain_calls(gpu, t, q, p, outs, flags):
     """the reference call sequence, one batched launch per operator; returns the 4 kernel names"""
@@ -237,7 +252,10 @@ def run_product(args):
         raise SystemExit("bench.py: no CUDA device -- the product has no CPU path")
     torch.cuda.set_device(local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        with stdout_to_stderr():
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+            dist.barrier()  # creates the communicator (and prints NCCL's banner) now
+            torch.cuda.synchronize()
     pkg = importlib.import_module("mi-fieldcalc_b200")
     gpu = pkg.load()
     gpu.set_device(local)

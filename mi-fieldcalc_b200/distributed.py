@@ -85,6 +85,40 @@ def exchange_halo(owned, halo: int, rank: int, world: int, group=None):
     return torch.cat(parts, dim=-2).contiguous()
 
 
+def exchange_halo_inplace(ext, halo: int, rank: int, world: int, group=None):
+    """ext: the EXTENDED slab [..., halo_up + rows + halo_down, nx] (halo_up = 0 on rank 0, halo_down = 0 on the
+    last rank) whose owned rows are already in place -- typically written there by the previous sharded
+    operator.  Only the halo rows move: each rank sends its first / last `halo` owned rows to rank-1 / rank+1
+    and receives the neighbours' straight into its halo rows.  No concatenation, no extra pass over the slab."""
+    import torch.distributed as dist
+
+    up = halo if rank > 0 else 0
+    down = halo if rank < world - 1 else 0
+    total = ext.shape[-2]
+    rows = total - up - down
+    assert rows >= halo, "a slab must own at least `halo` rows"
+    ops, stage = [], []
+    if rank > 0:
+        send = ext[..., up:up + halo, :].contiguous()
+        recv = ext[..., :up, :] if ext[..., :up, :].is_contiguous() else None
+        buf = recv if recv is not None else ext.new_empty(ext.shape[:-2] + (halo, ext.shape[-1]))
+        ops += [dist.P2POp(dist.isend, send, rank - 1, group), dist.P2POp(dist.irecv, buf, rank - 1, group)]
+        stage.append((buf, recv is None, slice(0, up)))
+    if rank < world - 1:
+        send = ext[..., up + rows - halo:up + rows, :].contiguous()
+        recv = ext[..., up + rows:, :] if ext[..., up + rows:, :].is_contiguous() else None
+        buf = recv if recv is not None else ext.new_empty(ext.shape[:-2] + (halo, ext.shape[-1]))
+        ops += [dist.P2POp(dist.isend, send, rank + 1, group), dist.P2POp(dist.irecv, buf, rank + 1, group)]
+        stage.append((buf, recv is None, slice(up + rows, total)))
+    if ops:
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+    for buf, copy_needed, where in stage:
+        if copy_needed:  # batched slabs: the halo rows of every field are strided, received via one small buffer
+            ext[..., where, :].copy_(buf)
+    return ext
+
+
 def combine_flags(local_flag: int, group=None, device=None) -> int:
     """global ValuesDefined of a slab-sharded operator from the per-rank flags (one 8-byte all-reduce)"""
     import torch

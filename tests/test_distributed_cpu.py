@@ -127,3 +127,34 @@ def test_batch_sharding_needs_no_collective():
         results = mgr.dict()
         mp.spawn(_batch_worker, args=(world, port, results), nprocs=world, join=True)
         assert results[0] == results[1] == [0, 0, 0, 1, 0, 0, 0]
+
+
+def _inplace_worker(rank, world, port, results):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    ok = True
+    for (nl, ny, nx, h) in ((1, 11, 5, 1), (3, 11, 5, 2), (4, 23, 7, 2)):
+        full = torch.arange(nl * ny * nx, dtype=torch.float32).reshape(nl, ny, nx)
+        r0, r1 = D.partition_rows(ny, world)[rank]
+        lo, hi = D.slab_bounds(r0, r1, ny, h)
+        ext = torch.full((nl, hi - lo, nx), -1.0)
+        ext[:, r0 - lo:r1 - lo] = full[:, r0:r1]
+        D.exchange_halo_inplace(ext, h, rank, world)
+        ok = ok and bool(torch.equal(ext, full[:, lo:hi]))
+        if nl == 1:  # a single field: the halo rows are contiguous and received in place
+            e2 = torch.full((hi - lo, nx), -1.0)
+            e2[r0 - lo:r1 - lo] = full[0, r0:r1]
+            D.exchange_halo_inplace(e2, h, rank, world)
+            ok = ok and bool(torch.equal(e2, full[0, lo:hi]))
+    results[rank] = ok
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_halo_exchange_in_place(world):
+    """only the halo rows move; the owned rows stay where the previous operator wrote them"""
+    port = 29300 + world + (os.getpid() % 200)
+    with mp.Manager() as mgr:
+        results = mgr.dict()
+        mp.spawn(_inplace_worker, args=(world, port, results), nprocs=world, join=True)
+        assert all(results[r] for r in range(world))
