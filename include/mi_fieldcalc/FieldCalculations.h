@@ -138,6 +138,26 @@ bool vesselIcingMincog(int nx, int ny, const float* sal, const float* wave, cons
                        const float alpha, const float zmin, const float zmax, const int alt, float* icing, ValuesDefined& fDefined,
                        float undef); /* ref:248 */
 
+/* ---- fixed-level stability indices and level-independent conversions (the rest of the Python subset) ---- */
+bool kIndex(int nx, int ny, const float* t500, const float* t700, const float* rh700, const float* t850, const float* rh850, float p500,
+            float p700, float p850, int compute, float* kfield, ValuesDefined& fDefined, float undef); /* ref:136 */
+bool ductingIndex(int nx, int ny, const float* t850, const float* rh850, float p850, int compute, float* duct, ValuesDefined& fDefined,
+                  float undef); /* ref:139 */
+bool showalterIndex(int nx, int ny, const float* t500, const float* t850, const float* rh850, float p500, float p850, int compute,
+                    float* sfield, ValuesDefined& fDefined, float undef); /* ref:141 */
+bool boydenIndex(int nx, int ny, const float* t700, const float* z700, const float* z1000, float p700, float p1000, int compute,
+                 float* bfield, ValuesDefined& fDefined, float undef); /* ref:144 */
+bool sweatIndex(int nx, int ny, const float* t850, const float* t500, const float* td850, const float* td500, const float* u850,
+                const float* v850, const float* u500, const float* v500, float* sindex, ValuesDefined& fDefined, float undef); /* ref:147 */
+bool seaSoundSpeed(int nx, int ny, const float* t, const float* s, float z, int compute, float* soundspeed, ValuesDefined& fDefined,
+                   float undef); /* ref:192 */
+bool cvtemp(int nx, int ny, const float* tinp, int compute, float* tout, ValuesDefined& fDefined, float undef); /* ref:198 */
+bool cvhum(int nx, int ny, const float* t, const float* huminp, const std::string& unit, int compute, float* humout, ValuesDefined& fDefined,
+           float undef); /* ref:200 */
+bool abshum(int nx, int ny, const float* t, const float* rhum, float* abshumout, ValuesDefined& fDefined, float undef); /* ref:202 */
+bool underCooledRain(int nx, int ny, const float* precip, const float* snow, const float* tk, float precipMin, float snowRateMax,
+                     float tcMax, float* undercooled, ValuesDefined& fDefined, float undef); /* ref:222 */
+
 /* ---- field arithmetic (compute first) ---- */
 bool fieldOPERfield(int compute, int nx, int ny, const float* field1, const float* field2, float* fres, ValuesDefined& fDefined,
                     float undef); /* ref:278 */

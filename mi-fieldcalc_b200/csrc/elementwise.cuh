@@ -22,6 +22,9 @@
 // then < 4 tail points.  The host only selects W = 4 when all arrays share the same misalignment.
 #pragma once
 
+#include <cstdlib>
+#include <type_traits>
+
 #include "device_common.cuh"
 
 namespace fcb200 {
@@ -65,92 +68,178 @@ struct PointCtx
 // counters live at counters[k*NCOUNT ...]).  ALL = the field's input flag is ALL_DEFINED: the
 // operator must then skip every is_defined test (NaN / undef flow through the arithmetic).
 
-template <class Op, int W, bool ALL>
-__device__ __forceinline__ void ew_item(const Op& op, const EwArgs<Op::NIN, Op::NOUT>& a, const PointCtx& c, int field, int chunk, unsigned* nundef)
+// Optional: `static constexpr bool QUAD = true` + quad<ALL>(const float (*in)[4], float (*out)[4], ctx, nundef)
+// evaluates the four points of one float4 group together (in[k][w] = input k of point w), so that an operator
+// can keep its common path free of branches across all four and handle rare cases afterwards.
+template <class Op, class = void>
+struct op_has_quad : std::false_type
 {
-  constexpr int NIN = Op::NIN, NOUT = Op::NOUT;
-  constexpr int U = (W == 4) ? Op::UNROLL : Op::UNROLL * 2;
+};
+template <class Op>
+struct op_has_quad<Op, std::void_t<decltype(Op::QUAD)>> : std::integral_constant<bool, Op::QUAD>
+{
+};
 
-  const float* in[NIN];
-  float* out[NOUT];
-#pragma unroll
-  for (int k = 0; k < NIN; ++k)
-    in[k] = a.in[k] + (long long)field * a.in_stride[k];
-#pragma unroll
-  for (int k = 0; k < NOUT; ++k)
-    out[k] = a.out[k] + (long long)field * a.n;
+template <class Op, int W>
+struct EwShape
+{
+  static constexpr int U = (W == 4) ? Op::UNROLL : Op::UNROLL * 2;
+};
 
-  const long long n = a.n;
-  const int head = (W == 4) ? ((4 - ((a.align0 + (int)(((long long)field * n) & 3)) & 3)) & 3) : 0;
-  const long long groups = (n - head) / W;
+// Index arithmetic of one item.  n < 2^31 (the reference's `int fsize`), so everything inside a field is
+// 32-bit; only field * stride needs 64 bits (one IMAD.WIDE).
+template <int W>
+struct EwPos
+{
+  unsigned head;   // first float4-aligned point of the field (W = 4): fields of a batch are only 4-byte aligned in general
+  unsigned groups; // number of full W-point groups after the head
+  unsigned g0;     // this thread's first group
 
-  // ---- body: all loads first, then compute + store
-  float v[U][NIN][W];
-  const long long g0 = (long long)chunk * (EW_THREADS * U) + threadIdx.x;
+  template <int NIN, int NOUT>
+  __device__ __forceinline__ EwPos(const EwArgs<NIN, NOUT>& a, unsigned field, unsigned chunk, int U)
+  {
+    const unsigned n = (unsigned)a.n;
+    head = (W == 4) ? ((4u - (((unsigned)a.align0 + field * n) & 3u)) & 3u) : 0u;
+    groups = (n - head) / W;
+    g0 = chunk * (unsigned)(EW_THREADS * U) + threadIdx.x;
+  }
+  __device__ __forceinline__ unsigned group(int u) const { return g0 + (unsigned)u * EW_THREADS; }
+  __device__ __forceinline__ unsigned first_point(int u) const { return head + group(u) * W; }
+};
+
+// ---- the loads of group u of one item
+template <class Op, int W>
+__device__ __forceinline__ void ew_load_group(const EwArgs<Op::NIN, Op::NOUT>& a, unsigned field, const EwPos<W>& pos, int u, float (&v)[Op::NIN][W])
+{
+  if (pos.group(u) < pos.groups) {
+    const unsigned e = pos.first_point(u);
 #pragma unroll
-  for (int u = 0; u < U; ++u) {
-    const long long g = g0 + (long long)u * EW_THREADS;
-    if (g < groups) {
-#pragma unroll
-      for (int k = 0; k < NIN; ++k) {
-        if constexpr (W == 4) {
-          const float4 q = *reinterpret_cast<const float4*>(in[k] + head + g * 4);
-          v[u][k][0] = q.x;
-          v[u][k][1] = q.y;
-          v[u][k][2] = q.z;
-          v[u][k][3] = q.w;
-        } else {
-          v[u][k][0] = in[k][g];
-        }
+    for (int k = 0; k < Op::NIN; ++k) {
+      const float* in = a.in[k] + ((unsigned long long)field * (unsigned)a.in_stride[k] + e);
+      if constexpr (W == 4) {
+        const float4 q = *reinterpret_cast<const float4*>(in);
+        v[k][0] = q.x;
+        v[k][1] = q.y;
+        v[k][2] = q.z;
+        v[k][3] = q.w;
+      } else {
+        v[k][0] = in[0];
       }
     }
   }
+}
+
+template <class Op, int W>
+__device__ __forceinline__ void ew_load(const EwArgs<Op::NIN, Op::NOUT>& a, unsigned field, unsigned chunk, float (&v)[EwShape<Op, W>::U][Op::NIN][W])
+{
+  constexpr int U = EwShape<Op, W>::U;
+  const EwPos<W> pos(a, field, chunk, U);
 #pragma unroll
-  for (int u = 0; u < U; ++u) {
-    const long long g = g0 + (long long)u * EW_THREADS;
-    if (g < groups) {
-      float r[NOUT][W];
+  for (int u = 0; u < U; ++u)
+    ew_load_group<Op, W>(a, field, pos, u, v[u]);
+}
+
+// ---- compute + store of group u of one item whose inputs are in registers
+template <class Op, int W, bool ALL>
+__device__ __forceinline__ void ew_compute_group(const Op& op, const EwArgs<Op::NIN, Op::NOUT>& a, const PointCtx& c, unsigned field, const EwPos<W>& pos, int u,
+                                                 const float (&v)[Op::NIN][W], unsigned* nundef)
+{
+  constexpr int NIN = Op::NIN, NOUT = Op::NOUT;
+  if (pos.group(u) < pos.groups) {
+    const unsigned e = pos.first_point(u);
+    float r[NOUT][W];
+    if constexpr (W == 4 && op_has_quad<Op>::value) {
+      op.template quad<ALL>(v, r, c, nundef);
+    } else {
 #pragma unroll
       for (int w = 0; w < W; ++w) {
         float pin[NIN], pout[NOUT];
 #pragma unroll
         for (int k = 0; k < NIN; ++k)
-          pin[k] = v[u][k][w];
-        op.template point<ALL>(pin, pout, c, head + g * W + w, nundef);
+          pin[k] = v[k][w];
+        op.template point<ALL>(pin, pout, c, (long long)(e + w), nundef);
 #pragma unroll
         for (int k = 0; k < NOUT; ++k)
           r[k][w] = pout[k];
       }
+    }
+    const unsigned long long off = (unsigned long long)field * (unsigned)a.n + e;
 #pragma unroll
-      for (int k = 0; k < NOUT; ++k) {
-        if constexpr (W == 4)
-          *reinterpret_cast<float4*>(out[k] + head + g * 4) = make_float4(r[k][0], r[k][1], r[k][2], r[k][3]);
-        else
-          out[k][g] = r[k][0];
-      }
+    for (int k = 0; k < NOUT; ++k) {
+      if constexpr (W == 4)
+        *reinterpret_cast<float4*>(a.out[k] + off) = make_float4(r[k][0], r[k][1], r[k][2], r[k][3]);
+      else
+        a.out[k][off] = r[k][0];
     }
   }
+}
 
-  // ---- peel: < 4 head points and < 4 tail points of the field, done with its first item
+// ---- the < 4 head and < 4 tail points of a field, done (with their own scalar loads) together with its first item
+template <class Op, int W, bool ALL>
+__device__ __forceinline__ void ew_peel(const Op& op, const EwArgs<Op::NIN, Op::NOUT>& a, const PointCtx& c, unsigned field, unsigned chunk, const EwPos<W>& pos,
+                                        unsigned* nundef)
+{
+  constexpr int NIN = Op::NIN, NOUT = Op::NOUT;
   if (W == 4 && chunk == 0) {
-    const long long tail0 = head + groups * 4;
-    const int ntail = (int)(n - tail0);
+    const unsigned n = (unsigned)a.n;
+    const unsigned tail0 = pos.head + pos.groups * 4;
+    const unsigned ntail = n - tail0;
     long long idx = -1;
-    if ((int)threadIdx.x < head)
+    if (threadIdx.x < pos.head)
       idx = threadIdx.x;
-    else if (threadIdx.x >= 32 && (int)threadIdx.x - 32 < ntail)
+    else if (threadIdx.x >= 32 && threadIdx.x - 32 < ntail)
       idx = tail0 + (threadIdx.x - 32);
     if (idx >= 0) {
       float pin[NIN], pout[NOUT];
 #pragma unroll
       for (int k = 0; k < NIN; ++k)
-        pin[k] = in[k][idx];
+        pin[k] = (a.in[k] + (unsigned long long)field * (unsigned)a.in_stride[k])[idx];
       op.template point<ALL>(pin, pout, c, idx, nundef);
 #pragma unroll
       for (int k = 0; k < NOUT; ++k)
-        out[k][idx] = pout[k];
+        (a.out[k] + (unsigned long long)field * n)[idx] = pout[k];
     }
   }
+}
+
+template <class Op, int W, bool ALL>
+__device__ __forceinline__ void ew_compute(const Op& op, const EwArgs<Op::NIN, Op::NOUT>& a, const PointCtx& c, unsigned field, unsigned chunk,
+                                           const float (&v)[EwShape<Op, W>::U][Op::NIN][W], unsigned* nundef)
+{
+  constexpr int U = EwShape<Op, W>::U;
+  const EwPos<W> pos(a, field, chunk, U);
+#pragma unroll
+  for (int u = 0; u < U; ++u)
+    ew_compute_group<Op, W, ALL>(op, a, c, field, pos, u, v[u], nundef);
+  ew_peel<Op, W, ALL>(op, a, c, field, chunk, pos, nundef);
+}
+
+// Persistent kernel, U >= 2: group u of the NEXT item is requested right after group u of the current item has
+// been consumed, into the same registers -- every load has the compute time of the other U - 1 groups plus the
+// loop turn-around to arrive, and no register is copied.
+template <class Op, int W, bool ALL>
+__device__ __forceinline__ void ew_compute_and_refill(const Op& op, const EwArgs<Op::NIN, Op::NOUT>& a, const PointCtx& c, unsigned field, unsigned chunk,
+                                                      bool has_next, unsigned nfield, unsigned nchunk, float (&v)[EwShape<Op, W>::U][Op::NIN][W],
+                                                      unsigned* nundef)
+{
+  constexpr int U = EwShape<Op, W>::U;
+  const EwPos<W> pos(a, field, chunk, U);
+  const EwPos<W> npos(a, nfield, nchunk, U);
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    ew_compute_group<Op, W, ALL>(op, a, c, field, pos, u, v[u], nundef);
+    if (has_next)
+      ew_load_group<Op, W>(a, nfield, npos, u, v[u]);
+  }
+  ew_peel<Op, W, ALL>(op, a, c, field, chunk, pos, nundef);
+}
+
+template <class Op, int W, bool ALL>
+__device__ __forceinline__ void ew_item(const Op& op, const EwArgs<Op::NIN, Op::NOUT>& a, const PointCtx& c, int field, int chunk, unsigned* nundef)
+{
+  float v[EwShape<Op, W>::U][Op::NIN][W];
+  ew_load<Op, W>(a, (unsigned)field, (unsigned)chunk, v);
+  ew_compute<Op, W, ALL>(op, a, c, (unsigned)field, (unsigned)chunk, v, nundef);
 }
 
 template <int NCOUNT>
@@ -208,6 +297,14 @@ __global__ void __launch_bounds__(EW_THREADS, Op::MIN_BLOCKS) ew_kernel(const Op
   unsigned item = blockIdx.x;
   unsigned field = item / chunks, chunk = item - field * chunks;
   FieldMeta m = a.meta[field < (unsigned)a.nfields ? field : 0];
+  // The inputs of item i+1 are requested before item i is computed (one register buffer ahead): the
+  // kernels on this path spend ~150 issue slots per point, and without the prefetch a warp sits on its
+  // loads while too few other warps are resident to fill the issue slots (ncu: long_scoreboard).
+  constexpr int U = EwShape<Op, W>::U;
+  float v[U][Op::NIN][W];
+  float vn[U >= 2 ? 1 : U][Op::NIN][W]; // only U == 1 needs a second buffer (and a register copy per item)
+  if (item < items)
+    ew_load<Op, W>(a, field, chunk, v);
   while (item < items) {
     const unsigned nitem = item + grid;
     unsigned nfield = field + step_f, nchunk = chunk + step_c;
@@ -215,15 +312,30 @@ __global__ void __launch_bounds__(EW_THREADS, Op::MIN_BLOCKS) ew_kernel(const Op
       nchunk -= chunks;
       nfield += 1;
     }
+    const bool has_next = nitem < items;
     FieldMeta mn = m;
-    if (nitem < items && nfield != field)
+    if (has_next && nfield != field)
       mn = a.meta[nfield];
     const PointCtx c{tab, pw, m, a.undef, a.nx};
-    if (m.all == 1)
-      ew_item<Op, W, true>(op, a, c, (int)field, (int)chunk, nundef);
-    else
-      ew_item<Op, W, false>(op, a, c, (int)field, (int)chunk, nundef);
-    if (Op::NCOUNT > 0 && (nfield != field || nitem >= items))
+    if constexpr (U >= 2) {
+      if (m.all == 1)
+        ew_compute_and_refill<Op, W, true>(op, a, c, field, chunk, has_next, nfield, nchunk, v, nundef);
+      else
+        ew_compute_and_refill<Op, W, false>(op, a, c, field, chunk, has_next, nfield, nchunk, v, nundef);
+    } else {
+      if (has_next)
+        ew_load<Op, W>(a, nfield, nchunk, vn);
+      if (m.all == 1)
+        ew_compute<Op, W, true>(op, a, c, field, chunk, v, nundef);
+      else
+        ew_compute<Op, W, false>(op, a, c, field, chunk, v, nundef);
+#pragma unroll
+      for (int k = 0; k < Op::NIN; ++k)
+#pragma unroll
+        for (int w = 0; w < W; ++w)
+          v[0][k][w] = vn[0][k][w];
+    }
+    if (Op::NCOUNT > 0 && (nfield != field || !has_next))
       ew_flush<Op::NCOUNT>(nundef, a.counters, (int)field);
     item = nitem;
     field = nfield;
@@ -300,7 +412,7 @@ bool launch_elementwise(Call& call, const Op& op, const float* const* in, const 
   // Operators that stage tables in shared memory run a persistent grid (as many CTAs as stay
   // resident: occupancy x SM count) so that the staging is paid once per CTA; pure streaming and
   // compute-heavy operators get one CTA per item and leave load balancing to the hardware scheduler.
-  const bool persistent = (Op::USES_EWT || Op::USES_POW) && !Op::HEAVY;
+  const bool persistent = (Op::USES_EWT || Op::USES_POW) && !Op::HEAVY && !getenv("FCB200_EW_ONCE"); // TEMPORARY (tuning)
   if (!persistent) {
     if (vec)
       ew_kernel_once<Op, 4><<<(unsigned)a.items, EW_THREADS, 0, call.stream()>>>(op, a);

@@ -5,7 +5,7 @@
 // `compute` / `unit` and validates arguments with the reference's exact early-return rules, then
 // launches one kernel for the whole batch.  Citations: FC.cc = the reference's
 // src/mi_fieldcalc/FieldCalculations.cc.
-#include "ew_driver.cuh"
+#include "ew_host.cuh"
 
 #include "../../include/fcb200.h"
 
@@ -23,23 +23,9 @@ using dev::K_XLH;
 
 enum Kind { PLEVEL = 0, HLEVEL = 1, ALEVEL = 2 };
 
-// host copies of MC.h:39-49 (same float values as the device constexprs)
-const float H_CP = 1004.f, H_P0INV = (float)(1. / 1000.f), H_KAPPA = 287.f / 1004.f, H_T0 = (float)273.15;
-
-inline float host_pidcp(float p)
-{ // FC.cc:308-311, evaluated once per field on the host with glibc powf -- exactly what the reference
-  // does for every plevel* operator (FC.cc:347, 434), so these operators carry no device-powf ulps
-  return powf(p * H_P0INV, H_KAPPA);
-}
-
 inline bool bad_hlevel(float a, float b)
 { // FC.cc:298-301
   return (a < 0.0) || (b < 0.0) || (a == 0.0 && b == 0.0) || (b > 1.0);
-}
-
-inline bool unit_is(const char* unit, const char* what)
-{
-  return unit && strcmp(unit, what) == 0;
 }
 
 int temp_compute(int compute, const char* unit)
@@ -323,7 +309,7 @@ struct WindCoolingOp
     if (ALL || (is_def(in[0], c.undef) && is_def(in[1], c.undef) && is_def(in[2], c.undef))) {
       const float tc = in[0] - tconv;
       const float ff = (float)((double)dev::absval(in[1], in[2]) * 3.6);
-      const float ffpow = c.pw.pow(ff, (double)(float)0.16);
+      const float ffpow = c.pw.pow<dev::POW_WINDCHILL>(ff);
       float d = (float)(13.12 + 0.6215 * (double)tc - 11.37 * (double)ffpow + 0.3965 * (double)tc * (double)ffpow);
       if ((double)d > 0.)
         d = 0.f;
@@ -411,99 +397,159 @@ struct MomentumOp
 // Each output keeps its own definedness test and its own undefined counter, so values, masks and
 // the four flags are exactly those of the four separate calls.  The Exner function and the
 // saturation-table lookup are evaluated once per point instead of three / two times.
-struct AlevelChainOp
+template <int U_, int MB_>
+struct AlevelChainOpT
 {
-  static constexpr int NIN = 3, NOUT = 4, UNROLL = 1;
+  static constexpr int NIN = 3, NOUT = 4, UNROLL = U_;
   static constexpr int NCOUNT = 4;
-  static constexpr int MIN_BLOCKS = 4;
+  static constexpr int MIN_BLOCKS = MB_;
   static constexpr bool HEAVY = false;
   static constexpr bool USES_EWT = true, USES_POW = true;
+  static constexpr bool QUAD = true;
   float tdconv;
-  // Straight-line code: every value is computed unconditionally (the helpers are safe on any bit
-  // pattern) and the definedness tests only select between value and undef at the end, so the
-  // ALL_DEFINED instantiation contains no test at all and the other one no divergent branch.
-  // (Replacing the five float divisions by a check-free reciprocal sequence behind a warp vote on "all
-  // inputs physically plausible" was measured 9 % SLOWER than the compiler's FCHK-guarded division.)
-  template <bool ALL>
-  __device__ __forceinline__ void point(const float* in, float* out, const PointCtx& c, long long, unsigned* nundef) const
+
+  struct Raw
   {
-    const float t = in[0], q = in[1], p = in[2];
-    const float undef = c.undef;
-    const bool dt = ALL || is_def(t, undef), dq = ALL || is_def(q, undef), dp = ALL || is_def(p, undef);
+    float theta, rh, td, the;
+    bool edef; // the saturation-table lookup of t was in range
+  };
 
-    const float pidcp = dev::pidcp_from_p(c.pw, p);
-    const float theta = t / pidcp;
-    const float the = (t * K_CP + q * K_XLH) / (K_CP * pidcp);
-
+  // The reference's expressions with ordinary IEEE operators: correct for ANY bit pattern.  Not inlined: it
+  // only runs for points whose inputs fail the plausibility test of `fast` (undefined values that flow into
+  // the arithmetic, NaN, zero or negative pressure, ...).
+  __device__ __noinline__ static void ieee_raw(float t, float q, float p, const dev::EwtTable& tab, const dev::PowTable& pw, float tdconv, Raw& r)
+  {
+    const float pidcp = dev::pidcp_from_p(pw, p);
+    r.theta = t / pidcp;
+    r.the = (t * K_CP + q * K_XLH) / (K_CP * pidcp);
     const dev::Ewt e(t - K_T0);
-    const float et = e.value(c.tab);
+    const float et = e.value(tab);
     const float qsat = dev::K_EPS * et / p;
-    const float rh = (float)(100. * (double)q / (double)qsat);
+    r.rh = (float)(100. * (double)q / (double)qsat);
     const float rhc = dev::clamp_rh(q / qsat);
-    const float td = e.inverse(c.tab, rhc * et) + tdconv;
+    r.td = e.inverse(tab, rhc * et) + tdconv;
+    r.edef = e.defined;
+  }
+  // `out` of the non-inlined call lives in local memory; copying it keeps the caller's own Raw in registers
+  __device__ __forceinline__ static void ieee(float t, float q, float p, const dev::EwtTable& tab, const dev::PowTable& pw, float tdconv, Raw& r)
+  {
+    Raw tmp;
+    ieee_raw(t, q, p, tab, pw, tdconv, tmp);
+    r.theta = tmp.theta;
+    r.rh = tmp.rh;
+    r.td = tmp.td;
+    r.the = tmp.the;
+    r.edef = tmp.edef;
+  }
 
-    const bool ok_theta = dt && dp;            // aleveltemp tests t, p
-    const bool ok_hum = dt && dq && e.defined; // alevelhum c1/c5 test t, q only; an undefined p flows into the arithmetic
-    const bool ok_the = dt && dq && dp;        // alevelthe tests t, q, p
-    out[0] = ok_theta ? theta : undef;
-    out[1] = ok_hum ? rh : undef;
-    out[2] = ok_hum ? td : undef;
-    out[3] = ok_the ? the : undef;
+  // Same expressions, same roundings, for PLAUSIBLE inputs: saturation-table position x in [0, 40)
+  // (-100 <= t - 273.15 < 100 degC), p in [2^-7, 2^11) hPa, q = +0 or 2^-90 <= |q| < 2^20.  Then every divisor,
+  // quotient and remainder below is a normal number far from the ends of the exponent range, the six divisions
+  // can use the guard-free sequences of device_common.cuh, the Exner function needs no classification of its
+  // argument and the table indices need no clamps -- straight-line code without a single branch, so the
+  // compiler interleaves the four points of a thread.  Returns false (after computing harmless garbage) when
+  // the inputs are not plausible; the caller then redoes the point with `ieee`.
+  __device__ __forceinline__ bool fast(float t, float q, float p, const dev::EwtTable& tab, const dev::PowTable& pw, Raw& r) const
+  {
+    const float x = (float)(((double)(t - K_T0) + 100.) * dev::c_dconst[0]); // Ewt::Ewt, MC.h:66
+    const unsigned uq = __float_as_uint(q) & 0x7fffffffu;
+    const bool plausible = (__float_as_uint(x) < 0x42200000u)                        // +0 <= x < 40
+                           && (__float_as_uint(p) - 0x3c000000u < 0x09000000u)       // 2^-7 <= p < 2^11
+                           && ((uq - 0x12800000u < 0x37000000u) || __float_as_uint(q) == 0u); // 2^-90 <= |q| < 2^20, or +0
+    const int l = plausible ? (int)x : 0;
+
+    const float pidcp = pw.pow_normal<dev::POW_KAPPA>(p * dev::K_P0INV); // FC.cc:308-311
+    r.theta = dev::div_midrange(t, pidcp);
+    r.the = dev::div_midrange(t * K_CP + q * K_XLH, K_CP * pidcp);
+
+    const float2 e = tab.e[l];
+    const float et = e.x + e.y * (x - (float)l); // MC.h:78
+    const float qsat = dev::div_midrange(dev::K_EPS * et, p);
+    r.rh = (float)dev::div_midrange(100. * (double)q, (double)qsat); // FC.cc:229
+    const float rq = dev::div_midrange(q, qsat);
+    const float rhc = rq < dev::K_RHMIN ? dev::K_RHMIN : (rq > dev::K_RHMAX ? dev::K_RHMAX : rq); // clamp_rh, FC.cc:186-194
+    const float etd = rhc * et;
+    // Ewt::inverse (MC.cc:37-45) with the bucket table; 0.02 * ewt[0] < 2^-15 lands below the first bucket -> index 0
+    int b = (int)(__float_as_uint(etd) >> 21) - dev::EWT_LUT0;
+    b = min(max(b, 0), dev::EWT_NLUT - 1);
+    int ll = min((int)tab.lut[b], l);
+    const int k = min(ll + 1, l); // the bucket index is the answer or one below it; k == ll when the walk may not go up
+    ll = (tab.e[k].x > etd) ? ll : k;
+    const float2 e2 = tab.e[ll];
+    const float y = (float)ll + dev::div_midrange(etd - e2.x, e2.y);
+    // (float)(-100. + (double)y * 5.): for |y| < 64 the double expression is exact (5y has at most 27
+    // significant bits and -100 + 5y at most 7 + 46) or, for |y| < 2^-23, rounds to -100 either way -> one fmaf
+    r.td = fmaf(5.f, y, -100.f) + tdconv;
+    r.edef = true;
+    return plausible;
+  }
+
+  // definedness tests of the four reference calls + their four counters
+  template <bool ALL>
+  __device__ __forceinline__ void finish(float t, float q, float p, const Raw& r, float undef, float* out, unsigned* nundef) const
+  {
+    const bool dt = ALL || is_def(t, undef), dq = ALL || is_def(q, undef), dp = ALL || is_def(p, undef);
+    const bool ok_theta = dt && dp;          // aleveltemp tests t, p
+    const bool ok_hum = dt && dq && r.edef;  // alevelhum c1/c5 test t, q only; an undefined p flows into the arithmetic
+    const bool ok_the = dt && dq && dp;      // alevelthe tests t, q, p
+    out[0] = ok_theta ? r.theta : undef;
+    out[1] = ok_hum ? r.rh : undef;
+    out[2] = ok_hum ? r.td : undef;
+    out[3] = ok_the ? r.the : undef;
     nundef[0] += ok_theta ? 0u : 1u;
     nundef[1] += ok_hum ? 0u : 1u;
     nundef[2] += ok_hum ? 0u : 1u;
     nundef[3] += ok_the ? 0u : 1u;
   }
+
+  // For a field that is not ALL_DEFINED: an undefined q only reaches outputs that are undefined anyway, so
+  // it is replaced by +0 (plausible) for the arithmetic; a point with an undefined t has no defined output at
+  // all and never needs the IEEE redo.  An undefined p with defined t, q DOES flow into RH and Td (FC.cc:1429).
+  template <bool ALL>
+  __device__ __forceinline__ bool eval(float t, float q, float p, const PointCtx& c, Raw& r) const
+  {
+    const float qe = (ALL || is_def(q, c.undef)) ? q : 0.f;
+    const bool plausible = fast(t, qe, p, c.tab, c.pw, r);
+    return plausible || !(ALL || is_def(t, c.undef));
+  }
+
+  template <bool ALL>
+  __device__ __forceinline__ void point(const float* in, float* out, const PointCtx& c, long long, unsigned* nundef) const
+  {
+    Raw r;
+    if (!eval<ALL>(in[0], in[1], in[2], c, r))
+      ieee(in[0], in[1], in[2], c.tab, c.pw, tdconv, r);
+    finish<ALL>(in[0], in[1], in[2], r, c.undef, out, nundef);
+  }
+
+  // four consecutive points of one thread: all fast evaluations first (one basic block), the rare IEEE redo after
+  template <bool ALL>
+  __device__ __forceinline__ void quad(const float (*in)[4], float (*out)[4], const PointCtx& c, unsigned* nundef) const
+  {
+    Raw r[4];
+    unsigned bad = 0;
+#pragma unroll
+    for (int w = 0; w < 4; ++w)
+      bad |= eval<ALL>(in[0][w], in[1][w], in[2][w], c, r[w]) ? 0u : (1u << w);
+    if (bad) {
+#pragma unroll
+      for (int w = 0; w < 4; ++w)
+        if (bad & (1u << w))
+          ieee(in[0][w], in[1][w], in[2][w], c.tab, c.pw, tdconv, r[w]);
+    }
+#pragma unroll
+    for (int w = 0; w < 4; ++w) {
+      float o[4];
+      finish<ALL>(in[0][w], in[1][w], in[2][w], r[w], c.undef, o, nundef);
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        out[k][w] = o[k];
+    }
+  }
 };
 
 // ------------------------------------------------------------------------------------ host drivers
 
-struct Batch
-{
-  int nx, ny, nfields;
-  long long n;
-  bool valid() const { return nx > 0 && ny > 0 && nfields > 0 && (long long)nx * ny < 0x7fffffffLL; }
-};
-
-Batch make_batch(int nx, int ny, int nfields)
-{
-  Batch b;
-  b.nx = nx;
-  b.ny = ny;
-  b.nfields = nfields;
-  b.n = (long long)nx * ny;
-  return b;
-}
-
-enum FlagRule { FLAG_FROM_COUNT, FLAG_UNCHANGED };
-
-// Runs one elementwise operator over a batch.  `stride[k]` = 1 for per-field arrays, 0 for arrays shared
-// by the batch.  `fill_meta(k, meta)` sets the per-field scalars.  The output may alias an input.
-// Adapter from the argument lists of the entry points to an EwJob (single output, one counter).
-template <class Op, class FillMeta>
-int run_elementwise(const Batch& b, const Op& op, const float* const* host_in, const int* per_field, float* host_out, int* fDefined, float undef,
-                    FlagRule rule, FillMeta fill_meta)
-{
-  EwJob<Op> job;
-  job.nx = b.nx;
-  job.ny = b.ny;
-  job.nfields = b.nfields;
-  for (int k = 0; k < Op::NIN; ++k) {
-    job.in[k] = host_in[k];
-    job.per_field[k] = per_field[k] != 0;
-  }
-  job.out[0] = host_out;
-  job.flags_in = fDefined;
-  job.flags_out[0] = (rule == FLAG_FROM_COUNT && Op::NCOUNT) ? fDefined : nullptr;
-  job.undef = undef;
-  job.fill_meta = fill_meta;
-  return run_ew_job(op, job);
-}
-
-struct NoMeta
-{
-  void operator()(int, FieldMeta&) const {}
-};
 
 // ---- pressure levels --------------------------------------------------------------------------------
 
@@ -869,25 +915,41 @@ int fcb200_alevel_chain_batched(int nx, int ny, int nfields, const float* t, con
                                 float* rh, float* td, float* thetae, const int* fDefinedIn, int* fDefinedOut, float undef)
 { // = aleveltemp(c=3) + alevelhum(c=1) + alevelhum(c=5, unit) + alevelthe(c=1) on the same inputs
   const int td_compute = hum_compute(5, td_unit); // 5 (Celsius) or 9 (Kelvin), FC.cc:1417-1420
-  AlevelChainOp op{(td_compute >= 9) ? H_T0 : 0.f};
-  EwJob<AlevelChainOp> job;
-  job.nx = nx;
-  job.ny = ny;
-  job.nfields = nfields;
-  job.in[0] = t;
-  job.in[1] = q;
-  job.in[2] = p;
-  for (int k = 0; k < 3; ++k)
-    job.per_field[k] = true;
-  job.out[0] = theta;
-  job.out[1] = rh;
-  job.out[2] = td;
-  job.out[3] = thetae;
-  job.flags_in = fDefinedIn;
-  for (int o = 0; o < 4; ++o)
-    job.flags_out[o] = fDefinedOut + (size_t)o * (nfields > 0 ? nfields : 0);
-  job.undef = undef;
-  return run_ew_job(op, job);
+  const float tdconv = (td_compute >= 9) ? H_T0 : 0.f;
+  auto run = [&](auto op) {
+    EwJob<decltype(op)> job;
+    job.nx = nx;
+    job.ny = ny;
+    job.nfields = nfields;
+    job.in[0] = t;
+    job.in[1] = q;
+    job.in[2] = p;
+    for (int k = 0; k < 3; ++k)
+      job.per_field[k] = true;
+    job.out[0] = theta;
+    job.out[1] = rh;
+    job.out[2] = td;
+    job.out[3] = thetae;
+    job.flags_in = fDefinedIn;
+    for (int o = 0; o < 4; ++o)
+      job.flags_out[o] = fDefinedOut + (size_t)o * (nfields > 0 ? nfields : 0);
+    job.undef = undef;
+    return run_ew_job(op, job);
+  };
+  // TEMPORARY (tuning): kernel shape selected at run time
+  const char* v = getenv("FCB200_CHAIN_VARIANT");
+  switch (v ? atoi(v) : 0) {
+  case 1:
+    return run(AlevelChainOpT<2, 2>{tdconv});
+  case 2:
+    return run(AlevelChainOpT<2, 3>{tdconv});
+  case 3:
+    return run(AlevelChainOpT<1, 3>{tdconv});
+  case 4:
+    return run(AlevelChainOpT<1, 2>{tdconv});
+  default:
+    return run(AlevelChainOpT<1, 4>{tdconv});
+  }
 }
 
 } // extern "C"

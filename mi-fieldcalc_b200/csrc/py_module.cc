@@ -9,9 +9,9 @@
 //     the order does not matter);
 //   * the ValuesDefined flag handed to the operator is SOME_DEFINED (:90); it is not returned;
 //   * the GIL is released for the call (:75); a `false` from the operator becomes None (:92-93).
-// Functions of the reference subset whose operators are outside SURVEY.md 8(a) (kIndex, ductingIndex,
-// showalterIndex, boydenIndex, sweatIndex, seaSoundSpeed, cvtemp, cvhum, abshum, underCooledRain) are
-// listed in 8(f) rank 1 and exported here as soon as their kernels exist (FCB200_HAVE_* below).
+// All 15 functions of the reference module are exported.  showalterIndex leaves output points with an
+// undefined input untouched (FC.cc:966-968); like the reference module, the output array is freshly
+// allocated, so those points hold whatever the allocation held.
 #include <pybind11/numpy.h>
 #include <pybind11/pybind11.h>
 
@@ -105,7 +105,6 @@ PYBIND11_MODULE(mi_fieldcalc, m)
                                 farray aice, farray depth, float vs, float alpha, float zmin, float zmax, int alt, float undef) {
     return apply(fc::vesselIcingMincog, undef, sal, wave, x_wind, y_wind, airtemp, rh, sst, p, Pw, aice, depth, vs, alpha, zmin, zmax, alt);
   });
-#ifdef FCB200_HAVE_PYBIND_SIBLINGS
   m.def("kIndex", [](farray t500, farray t700, farray rh700, farray t850, farray rh850, float p500, float p700, float p850, int compute, float undef) {
     return apply(fc::kIndex, undef, t500, t700, rh700, t850, rh850, p500, p700, p850, compute);
   });
@@ -126,5 +125,4 @@ PYBIND11_MODULE(mi_fieldcalc, m)
   m.def("underCooledRain", [](farray precip, farray snow, farray tk, float precipMin, float snowRateMax, float tcMax, float undef) {
     return apply(fc::underCooledRain, undef, precip, snow, tk, precipMin, snowRateMax, tcMax);
   });
-#endif
 }

@@ -212,6 +212,72 @@ bool shapiro2_filter(int nx, int ny, float* field, float* fsmooth, ValuesDefined
   return done(fcb200_shapiro2_filter(nx, ny, field, fsmooth, &f, undef), f, fDefined);
 }
 
+bool kIndex(int nx, int ny, const float* t500, const float* t700, const float* rh700, const float* t850, const float* rh850, float p500, float p700,
+            float p850, int compute, float* kfield, ValuesDefined& fDefined, float undef)
+{
+  FCB_FLAG;
+  return done(fcb200_kIndex(nx, ny, t500, t700, rh700, t850, rh850, p500, p700, p850, compute, kfield, &f, undef), f, fDefined);
+}
+
+bool ductingIndex(int nx, int ny, const float* t850, const float* rh850, float p850, int compute, float* duct, ValuesDefined& fDefined, float undef)
+{
+  FCB_FLAG;
+  return done(fcb200_ductingIndex(nx, ny, t850, rh850, p850, compute, duct, &f, undef), f, fDefined);
+}
+
+bool showalterIndex(int nx, int ny, const float* t500, const float* t850, const float* rh850, float p500, float p850, int compute, float* sfield,
+                    ValuesDefined& fDefined, float undef)
+{
+  FCB_FLAG;
+  return done(fcb200_showalterIndex(nx, ny, t500, t850, rh850, p500, p850, compute, sfield, &f, undef), f, fDefined);
+}
+
+bool boydenIndex(int nx, int ny, const float* t700, const float* z700, const float* z1000, float p700, float p1000, int compute, float* bfield,
+                 ValuesDefined& fDefined, float undef)
+{
+  FCB_FLAG;
+  return done(fcb200_boydenIndex(nx, ny, t700, z700, z1000, p700, p1000, compute, bfield, &f, undef), f, fDefined);
+}
+
+bool sweatIndex(int nx, int ny, const float* t850, const float* t500, const float* td850, const float* td500, const float* u850, const float* v850,
+                const float* u500, const float* v500, float* sindex, ValuesDefined& fDefined, float undef)
+{
+  FCB_FLAG;
+  return done(fcb200_sweatIndex(nx, ny, t850, t500, td850, td500, u850, v850, u500, v500, sindex, &f, undef), f, fDefined);
+}
+
+bool seaSoundSpeed(int nx, int ny, const float* t, const float* s, float z, int compute, float* soundspeed, ValuesDefined& fDefined, float undef)
+{
+  FCB_FLAG;
+  return done(fcb200_seaSoundSpeed(nx, ny, t, s, z, compute, soundspeed, &f, undef), f, fDefined);
+}
+
+bool cvtemp(int nx, int ny, const float* tinp, int compute, float* tout, ValuesDefined& fDefined, float undef)
+{
+  FCB_FLAG;
+  return done(fcb200_cvtemp(nx, ny, tinp, compute, tout, &f, undef), f, fDefined);
+}
+
+bool cvhum(int nx, int ny, const float* t, const float* huminp, const std::string& unit, int compute, float* humout, ValuesDefined& fDefined,
+           float undef)
+{
+  FCB_FLAG;
+  return done(fcb200_cvhum(nx, ny, t, huminp, unit.c_str(), compute, humout, &f, undef), f, fDefined);
+}
+
+bool abshum(int nx, int ny, const float* t, const float* rhum, float* abshumout, ValuesDefined& fDefined, float undef)
+{
+  FCB_FLAG;
+  return done(fcb200_abshum(nx, ny, t, rhum, abshumout, &f, undef), f, fDefined);
+}
+
+bool underCooledRain(int nx, int ny, const float* precip, const float* snow, const float* tk, float precipMin, float snowRateMax, float tcMax,
+                     float* undercooled, ValuesDefined& fDefined, float undef)
+{
+  FCB_FLAG;
+  return done(fcb200_underCooledRain(nx, ny, precip, snow, tk, precipMin, snowRateMax, tcMax, undercooled, &f, undef), f, fDefined);
+}
+
 bool windCooling(int nx, int ny, const float* t, const float* u, const float* v, int compute, float* dtcool, ValuesDefined& fDefined, float undef)
 {
   FCB_FLAG;

@@ -1459,3 +1459,377 @@ int fco_probability(int compute, int nx, int ny, const float* const* fields, int
   *fDefinedOut = check_defined(nundef, n);
   return 1;
 }
+
+/* ================================================================================================
+ * The rest of the reference's Python subset (python/py_mi_fieldcalc.cc:189-207)
+ * ================================================================================================ */
+
+/* MC.h:42, :53 */
+#define K_RCP (K_R / K_CP)
+#define K_CPLR (K_XLH / K_RCP)
+#define K_EXL (K_EPS * K_XLH)
+static const double K_MS2KNOTS = 3600.0 / 1852.0;
+
+static inline float ms2knots(float ff)
+{ /* MC.h:132-135: float * double -> float */
+  return (float)(ff * K_MS2KNOTS);
+}
+
+int fco_kIndex(int nx, int ny, const float* t500, const float* t700, const float* rh700, const float* t850, const float* rh850, float p500, float p700,
+               float p850, int compute, float* kfield, int* fDefined, float undef)
+{ /* FC.cc:745-814 */
+  if (p500 <= 0.0 || p500 >= p700 || p700 >= p850)
+    return 0;
+  float cvt500, cvt700, cvt850;
+  if (compute == 1) {
+    cvt500 = cvt700 = cvt850 = 1.f;
+  } else if (compute == 2) {
+    cvt500 = pidcp_from_p(p500);
+    cvt700 = pidcp_from_p(p700);
+    cvt850 = pidcp_from_p(p850);
+  } else
+    return 0;
+  const size_t n = (size_t)nx * ny;
+  const int all = *fDefined == ALL_DEFINED;
+  size_t nu = 0;
+  for (size_t i = 0; i < n; ++i) {
+    if (all || (is_def(t500[i], undef) && is_def(t700[i], undef) && is_def(rh700[i], undef) && is_def(t850[i], undef) && is_def(rh850[i], undef))) {
+      const float rh8 = clamp_rh((float)(0.01 * rh850[i]));
+      const float tc850 = cvt850 * t850[i] - K_T0;
+      const float tc700 = cvt700 * t700[i] - K_T0;
+      const ewt_t e850 = ewt_make(tc850), e700 = ewt_make(tc700);
+      if (!(ewt_defined(e850) && ewt_defined(e700))) {
+        kfield[i] = undef;
+        nu += 1;
+      } else {
+        const float etd850 = ewt_value(e850) * rh8;
+        const float tdc850 = ewt_inverse(e850, etd850);
+        const float rh7 = clamp_rh((float)(0.01 * rh700[i]));
+        const float etd700 = ewt_value(e700) * rh7;
+        const float tdc700 = ewt_inverse(e700, etd700);
+        const float tc500 = cvt500 * t500[i] - K_T0;
+        kfield[i] = (tc850 + tdc850) - (tc700 - tdc700) - tc500;
+      }
+    } else {
+      kfield[i] = undef;
+      nu += 1;
+    }
+  }
+  *fDefined = check_defined(nu, n);
+  return 1;
+}
+
+int fco_ductingIndex(int nx, int ny, const float* t850, const float* rh850, float p850, int compute, float* duct, int* fDefined, float undef)
+{ /* FC.cc:816-870 */
+  const float bduct = (float)3.8e+5;
+  if (p850 <= 0.0)
+    return 0;
+  float tconvert;
+  if (compute == 1)
+    tconvert = 1.f;
+  else if (compute == 2)
+    tconvert = pidcp_from_p(p850);
+  else
+    return 0;
+  const size_t n = (size_t)nx * ny;
+  const int all = *fDefined == ALL_DEFINED;
+  size_t nu = 0;
+  for (size_t i = 0; i < n; ++i) {
+    if (all || (is_def(t850[i], undef) && is_def(rh850[i], undef))) {
+      const float rh = clamp_rh((float)(0.01 * rh850[i]));
+      const float tk = t850[i] * tconvert;
+      const ewt_t e = ewt_make(tk - K_T0);
+      if (!ewt_defined(e)) {
+        duct[i] = undef;
+        nu += 1;
+      } else {
+        const float et = ewt_value(e);
+        const float etd = et * rh;
+        const float tdk = ewt_inverse(e, etd) + K_T0;
+        duct[i] = bduct * (et / (tk * tk) - etd / (tdk * tdk));
+      }
+    } else {
+      duct[i] = undef;
+      nu += 1;
+    }
+  }
+  *fDefined = check_defined(nu, n);
+  return 1;
+}
+
+int fco_showalterIndex(int nx, int ny, const float* t500, const float* t850, const float* rh850, float p500, float p850, int compute, float* sfield,
+                       int* fDefined, float undef)
+{ /* FC.cc:872-971: moist adiabat by 7 adjustment iterations; an undefined input point is counted but its
+   * output point is NOT written (:966-968) */
+  if (p500 <= 0.0 || p500 >= p850)
+    return 0;
+  const float pi500 = pi_from_p(p500);
+  const float pi850 = pi_from_p(p850);
+  float cvt500, cvt850, dryadiabat;
+  if (compute == 1) {
+    cvt500 = 1.f;
+    cvt850 = 1.f;
+    dryadiabat = K_CP * (K_CP / pi850) * (pi500 / K_CP);
+  } else if (compute == 2) {
+    cvt500 = pi500 / K_CP;
+    cvt850 = pi850 / K_CP;
+    dryadiabat = K_CP * (pi500 / K_CP);
+  } else
+    return 0;
+  const float cplr = K_CPLR, exl = K_EXL;
+  const size_t n = (size_t)nx * ny;
+  const int all = *fDefined == ALL_DEFINED;
+  size_t nu = 0;
+  for (size_t i = 0; i < n; ++i) {
+    if (all || (is_def(t500[i], undef) && is_def(t850[i], undef) && is_def(rh850[i], undef))) {
+      const float tk500 = cvt500 * t500[i];
+      const float tk850 = cvt850 * t850[i];
+      const float rh = clamp_rh((float)(0.01 * rh850[i]));
+      const ewt_t e = ewt_make(tk850 - K_T0);
+      if (!ewt_defined(e)) {
+        sfield[i] = undef;
+        nu += 1;
+      } else {
+        const float etd = ewt_value(e) * rh;
+        float tcl = dryadiabat * t850[i];
+        float qcl = K_EPS * etd / p850;
+        for (int it = 0; it < 7; ++it) {
+          const ewt_t e2 = ewt_make(tcl / K_CP - K_T0);
+          if (!ewt_defined(e2))
+            break;
+          const float esat = ewt_value(e2);
+          const float qsat = K_EPS * esat / p500;
+          float dq = qcl - qsat;
+          const float a1 = cplr * qcl / tcl;
+          const float a2 = exl / tcl;
+          dq = (float)(dq / (1. + a1 * a2));
+          qcl = qcl - dq;
+          tcl = tcl + dq * K_XLH;
+        }
+        const float tx500 = tcl / K_CP;
+        sfield[i] = tk500 - tx500;
+      }
+    } else {
+      nu += 1;
+    }
+  }
+  *fDefined = check_defined(nu, n);
+  return 1;
+}
+
+int fco_boydenIndex(int nx, int ny, const float* t700, const float* z700, const float* z1000, float p700, float p1000, int compute, float* bfield,
+                    int* fDefined, float undef)
+{ /* FC.cc:973-1014 */
+  if (compute <= 0 || compute >= 3)
+    return 0;
+  if (p700 <= 0.0 || p700 >= p1000)
+    return 0;
+  const float pi700 = K_CP * powf(p700 / K_P0, K_R / K_CP);
+  const float tconv = (compute == 2) ? pi700 / K_CP : 1.f;
+  const size_t n = (size_t)nx * ny;
+  const int all = *fDefined == ALL_DEFINED;
+  size_t nu = 0;
+  for (size_t i = 0; i < n; ++i) {
+    if (all || (is_def(t700[i], undef) && is_def(z700[i], undef) && is_def(z1000[i], undef))) {
+      const float tc700 = t700[i] * tconv - K_T0;
+      bfield[i] = (float)((z700[i] - z1000[i]) / 10. - tc700 - 200.);
+    } else {
+      bfield[i] = undef;
+      nu += 1;
+    }
+  }
+  *fDefined = check_defined(nu, n);
+  return 1;
+}
+
+int fco_sweatIndex(int nx, int ny, const float* t850, const float* t500, const float* td850, const float* td500, const float* u850, const float* v850,
+                   const float* u500, const float* v500, float* sindex, int* fDefined, float undef)
+{ /* FC.cc:1016-1040: the float terms are summed left to right in float, the last term is double */
+  const size_t n = (size_t)nx * ny;
+  const int all = *fDefined == ALL_DEFINED;
+  size_t nu = 0;
+  for (size_t i = 0; i < n; ++i) {
+    if (all || (is_def(t850[i], undef) && is_def(t500[i], undef) && is_def(td850[i], undef) && is_def(td500[i], undef) && is_def(u850[i], undef) &&
+                is_def(v850[i], undef) && is_def(u500[i], undef) && is_def(v500[i], undef))) {
+      const float ff850 = sqrtf(u850[i] * u850[i] + v850[i] * v850[i]);
+      const float ff500 = sqrtf(u500[i] * u500[i] + v500[i] * v500[i]);
+      const float sind = (u500[i] * v850[i] - v500[i] * u850[i]) / (ff850 * ff500);
+      const float lhs = 32 * td850[i] + 20 * t850[i] - 40 * t500[i] - 20 * 49 + 2 * ms2knots(ff850) + ms2knots(ff500);
+      sindex[i] = (float)(lhs + 125 * (sind + 0.2));
+    } else {
+      sindex[i] = undef;
+      nu += 1;
+    }
+  }
+  *fDefined = check_defined(nu, n);
+  return 1;
+}
+
+int fco_seaSoundSpeed(int nx, int ny, const float* t, const float* s, float z_, int compute, float* soundspeed, int* fDefined, float undef)
+{ /* FC.cc:1555-1602 */
+  if (compute != 1 && compute != 2)
+    return 0;
+  const float tconv = (compute == 1) ? 0.f : K_T0;
+  const double Z = fabsf(z_);
+  const double Cz = 0.01635 * Z + 0.000000175 * Z * Z;
+  const size_t n = (size_t)nx * ny;
+  const int all = *fDefined == ALL_DEFINED;
+  size_t nu = 0;
+  for (size_t i = 0; i < n; ++i) {
+    if (all || (is_def(t[i], undef) && is_def(s[i], undef))) {
+      const float T = t[i] - tconv;
+      const float S = s[i];
+      const double Ct = 4.565 * T - 0.0517 * T * T + 0.000221 * T * T * T;
+      const double Cs = (1.338 - 0.013 * T + 0.0001 * T * T) * (S - 35.0);
+      const double speed = 1449.1 + Ct + Cs + Cz;
+      soundspeed[i] = (float)speed;
+    } else {
+      soundspeed[i] = undef;
+      nu += 1;
+    }
+  }
+  *fDefined = check_defined(nu, n);
+  return 1;
+}
+
+int fco_cvtemp(int nx, int ny, const float* tinp, int compute, float* tout, int* fDefined, float undef)
+{ /* FC.cc:1608-1674 (serial build: the average is a float accumulation in index order) */
+  float tconvert;
+  switch (compute) {
+  case 1:
+  case 3:
+    tconvert = -K_T0;
+    break;
+  case 2:
+  case 4:
+    tconvert = +K_T0;
+    break;
+  default:
+    return 0;
+  }
+  const size_t n = (size_t)((long long)nx * ny > 0 ? (long long)nx * ny : 0);
+  const int all = *fDefined == ALL_DEFINED;
+  if (compute == 3 || compute == 4) {
+    float tavg = 0.f;
+    int navg = 0;
+    for (size_t i = 0; i < n; ++i)
+      if (all || is_def(tinp[i], undef)) {
+        tavg += tinp[i];
+        navg += 1;
+      }
+    if (navg > 0)
+      tavg /= (float)navg;
+    if ((compute == 3 && tavg < K_T0 / 2.) || (compute == 4 && tavg > K_T0 / 2.)) {
+      if (tout != tinp)
+        for (size_t i = 0; i < n; ++i)
+          tout[i] = tinp[i];
+      return 1;
+    }
+  }
+  size_t nu = 0;
+  for (size_t i = 0; i < n; ++i) {
+    if (all || is_def(tinp[i], undef))
+      tout[i] = tinp[i] + tconvert;
+    else {
+      tout[i] = undef;
+      nu += 1;
+    }
+  }
+  *fDefined = check_defined(nu, n);
+  return 1;
+}
+
+int fco_cvhum(int nx, int ny, const float* t, const float* huminp, const char* unit, int compute, float* humout, int* fDefined, float undef)
+{ /* FC.cc:1738-1817 */
+  float unit_scale = 100.f;
+  if (compute == 1 && strcmp(unit, "celsius") == 0)
+    compute = 2;
+  if ((compute == 4 || compute == 5) && strcmp(unit, "1") == 0)
+    unit_scale = 1.f;
+  const size_t n = (size_t)nx * ny;
+  const float tconv = (compute == 1 || compute == 2 || compute == 4) ? K_T0 : 0.f;
+  const float tdconv = (compute == 1) ? K_T0 : 0.f;
+  const int all = *fDefined == ALL_DEFINED;
+  size_t nu = 0;
+  if (compute >= 1 && compute <= 3) {
+    for (size_t i = 0; i < n; ++i) {
+      if (all || (is_def(t[i], undef) && is_def(huminp[i], undef))) {
+        const ewt_t e = ewt_make(t[i] - tconv);
+        if (!ewt_defined(e)) {
+          humout[i] = undef;
+          nu += 1;
+        } else {
+          const float et = ewt_value(e);
+          const float rh = clamp_rh((float)(0.01 * huminp[i]));
+          const float etd = rh * et;
+          humout[i] = ewt_inverse(e, etd) + tdconv;
+        }
+      } else {
+        humout[i] = undef;
+        nu += 1;
+      }
+    }
+  } else if (compute == 4 || compute == 5) {
+    for (size_t i = 0; i < n; ++i) {
+      if (all || (is_def(t[i], undef) && is_def(huminp[i], undef))) {
+        const ewt_t e = ewt_make(t[i] - tconv), e2 = ewt_make(huminp[i] - tconv);
+        if (!(ewt_defined(e) && ewt_defined(e2))) {
+          humout[i] = undef;
+          nu += 1;
+        } else {
+          const float rh = ewt_value(e2) / ewt_value(e);
+          humout[i] = rh * unit_scale;
+        }
+      } else {
+        humout[i] = undef;
+        nu += 1;
+      }
+    }
+  } else
+    return 0;
+  *fDefined = check_defined(nu, n);
+  return 1;
+}
+
+int fco_abshum(int nx, int ny, const float* t, const float* rhum, float* abshumout, int* fDefined, float undef)
+{ /* FC.cc:1676-1736.  <cmath> without `using namespace std`: the unqualified sqrt(v) and exp(x) with float
+   * arguments bind to the C library's double functions */
+  const float C = (float)2.16679, C1 = (float)-7.85951783, C2 = (float)1.84408259, C3 = (float)-11.7866497, C4 = (float)22.6807411,
+              C5 = (float)-15.9618719, C6 = (float)1.80122502, Tc = (float)647.096, Pc = 220640.f;
+  const size_t n = (size_t)nx * ny;
+  const int all = *fDefined == ALL_DEFINED;
+  size_t nu = 0;
+  for (size_t i = 0; i < n; ++i) {
+    if (all || (is_def(t[i], undef) && is_def(rhum[i], undef))) {
+      const float v = 1 - t[i] / Tc, tii = 1 / t[i];
+      const float v2 = v * v, v3 = v * v2, v4 = v2 * v2, v1_5 = (float)(v * sqrt((double)v)), v3_5 = v2 * v1_5, v7_5 = v4 * v3_5;
+      const float Pws = (float)(Pc * exp((double)(Tc * tii * (C1 * v + C2 * v1_5 + C3 * v3 + C4 * v3_5 + C5 * v4 + C6 * v7_5))));
+      const float Pw = Pws * rhum[i];
+      abshumout[i] = C * Pw * 100 * tii;
+    } else {
+      abshumout[i] = undef;
+      nu += 1;
+    }
+  }
+  *fDefined = check_defined(nu, n);
+  return 1;
+}
+
+int fco_underCooledRain(int nx, int ny, const float* precip, const float* snow, const float* tk, float precipMin, float snowRateMax, float tcMax,
+                        float* undercooled, int* fDefined, float undef)
+{ /* FC.cc:2231-2264 */
+  const size_t n = (size_t)nx * ny;
+  const float tkMax = tcMax + K_T0;
+  const int all = *fDefined == ALL_DEFINED;
+  size_t nu = 0;
+  for (size_t i = 0; i < n; ++i) {
+    if (all || (is_def(precip[i], undef) && is_def(snow[i], undef) && is_def(tk[i], undef))) {
+      undercooled[i] = (precip[i] >= precipMin && tk[i] <= tkMax && snow[i] <= precip[i] * snowRateMax) ? 1.f : 0.f;
+    } else {
+      undercooled[i] = undef;
+      nu += 1;
+    }
+  }
+  *fDefined = check_defined(nu, n);
+  return 1;
+}

@@ -278,4 +278,70 @@ int fcref_probability(int compute, int nx, int ny, const float* const* fields, i
   return fc::probability(compute, nx, ny, as_vector(fields, nfields), as_flags(fDefinedIn, nfields), lim, fres, f, undef);
 }
 
+// ---- the rest of the reference's Python subset
+int fcref_kIndex(int nx, int ny, const float* t500, const float* t700, const float* rh700, const float* t850, const float* rh850, float p500, float p700,
+                 float p850, int compute, float* kfield, int* fDefined, float undef)
+{
+  Flag f(fDefined);
+  return fc::kIndex(nx, ny, t500, t700, rh700, t850, rh850, p500, p700, p850, compute, kfield, f, undef);
+}
+
+int fcref_ductingIndex(int nx, int ny, const float* t850, const float* rh850, float p850, int compute, float* duct, int* fDefined, float undef)
+{
+  Flag f(fDefined);
+  return fc::ductingIndex(nx, ny, t850, rh850, p850, compute, duct, f, undef);
+}
+
+int fcref_showalterIndex(int nx, int ny, const float* t500, const float* t850, const float* rh850, float p500, float p850, int compute, float* sfield,
+                         int* fDefined, float undef)
+{
+  Flag f(fDefined);
+  return fc::showalterIndex(nx, ny, t500, t850, rh850, p500, p850, compute, sfield, f, undef);
+}
+
+int fcref_boydenIndex(int nx, int ny, const float* t700, const float* z700, const float* z1000, float p700, float p1000, int compute, float* bfield,
+                      int* fDefined, float undef)
+{
+  Flag f(fDefined);
+  return fc::boydenIndex(nx, ny, t700, z700, z1000, p700, p1000, compute, bfield, f, undef);
+}
+
+int fcref_sweatIndex(int nx, int ny, const float* t850, const float* t500, const float* td850, const float* td500, const float* u850, const float* v850,
+                     const float* u500, const float* v500, float* sindex, int* fDefined, float undef)
+{
+  Flag f(fDefined);
+  return fc::sweatIndex(nx, ny, t850, t500, td850, td500, u850, v850, u500, v500, sindex, f, undef);
+}
+
+int fcref_seaSoundSpeed(int nx, int ny, const float* t, const float* s, float z, int compute, float* soundspeed, int* fDefined, float undef)
+{
+  Flag f(fDefined);
+  return fc::seaSoundSpeed(nx, ny, t, s, z, compute, soundspeed, f, undef);
+}
+
+int fcref_cvtemp(int nx, int ny, const float* tinp, int compute, float* tout, int* fDefined, float undef)
+{
+  Flag f(fDefined);
+  return fc::cvtemp(nx, ny, tinp, compute, tout, f, undef);
+}
+
+int fcref_cvhum(int nx, int ny, const float* t, const float* huminp, const char* unit, int compute, float* humout, int* fDefined, float undef)
+{
+  Flag f(fDefined);
+  return fc::cvhum(nx, ny, t, huminp, std::string(unit), compute, humout, f, undef);
+}
+
+int fcref_abshum(int nx, int ny, const float* t, const float* rhum, float* abshumout, int* fDefined, float undef)
+{
+  Flag f(fDefined);
+  return fc::abshum(nx, ny, t, rhum, abshumout, f, undef);
+}
+
+int fcref_underCooledRain(int nx, int ny, const float* precip, const float* snow, const float* tk, float precipMin, float snowRateMax, float tcMax,
+                          float* undercooled, int* fDefined, float undef)
+{
+  Flag f(fDefined);
+  return fc::underCooledRain(nx, ny, precip, snow, tk, precipMin, snowRateMax, tcMax, undercooled, f, undef);
+}
+
 } // extern "C"

@@ -58,6 +58,9 @@ FIELD_RANGES = {
     "pw": (3.0, 12.0),
     "depth": (20.0, 3000.0),
     "any": (-50.0, 50.0),
+    "precip": (0.0, 5.0),      # mm
+    "snow": (0.0, 0.6),        # mm water
+    "tc30": (-40.0, 35.0),     # temperature, deg C (cvtemp / cvhum Celsius modes)
 }
 
 
@@ -69,7 +72,7 @@ def field(rng, kind, nx, ny):
     if kind == "fc0":  # Coriolis field crossing zero (momentum coordinates clamp)
         return smooth(rng, nx, ny, -3e-5, 1.4e-4, noise=0.0)
     lo, hi = FIELD_RANGES[kind]
-    if kind in ("aice", "wave", "pw", "depth", "sal"):
+    if kind in ("aice", "wave", "pw", "depth", "sal", "precip", "snow"):
         return uniform(rng, nx, ny, lo, hi)
     return smooth(rng, nx, ny, lo, hi)
 
@@ -160,6 +163,22 @@ SPECS = {
     "stddevValue": ["nx", "ny", ("members", "tk"), "flags_in", "out", "flag", "undef"],
     "extremeValue": [("i", "compute", 1), "nx", "ny", ("members", "tk"), "out", "flag", "undef"],
     "probability": [("i", "compute", 1), "nx", "ny", ("members", "tk"), "flags_in", ("limits", (262.0, 280.0)), "out", "flag", "undef"],
+    # the rest of the reference's Python subset
+    "kIndex": ["nx", "ny", ("in", "tk"), ("in", "tk"), ("in", "rh"), ("in", "tk"), ("in", "rh"), ("f", "p500", 500.0), ("f", "p700", 700.0),
+               ("f", "p850", 850.0), ("i", "compute", 1), "out", "flag", "undef"],
+    "ductingIndex": ["nx", "ny", ("in", "tk"), ("in", "rh"), ("f", "p850", 850.0), ("i", "compute", 1), "out", "flag", "undef"],
+    "showalterIndex": ["nx", "ny", ("in", "tk"), ("in", "tk"), ("in", "rh"), ("f", "p500", 500.0), ("f", "p850", 850.0), ("i", "compute", 1), "out",
+                       "flag", "undef"],
+    "boydenIndex": ["nx", "ny", ("in", "tk"), ("in", "z"), ("in", "z"), ("f", "p700", 700.0), ("f", "p1000", 1000.0), ("i", "compute", 1), "out",
+                    "flag", "undef"],
+    "sweatIndex": ["nx", "ny", ("in", "tk"), ("in", "tk"), ("in", "tk"), ("in", "tk"), ("in", "wind"), ("in", "wind"), ("in", "wind"), ("in", "wind"),
+                   "out", "flag", "undef"],
+    "seaSoundSpeed": ["nx", "ny", ("in", "sst"), ("in", "sal"), ("f", "z", 50.0), ("i", "compute", 1), "out", "flag", "undef"],
+    "cvtemp": ["nx", "ny", ("in", "tk"), ("i", "compute", 1), "out", "flag", "undef"],
+    "cvhum": ["nx", "ny", ("in", "tk"), ("in", "rh"), ("s", "unit", "kelvin"), ("i", "compute", 1), "out", "flag", "undef"],
+    "abshum": ["nx", "ny", ("in", "tk"), ("in", "rh"), "out", "flag", "undef"],
+    "underCooledRain": ["nx", "ny", ("in", "precip"), ("in", "snow"), ("in", "tk"), ("f", "precipMin", 0.5), ("f", "snowRateMax", 0.1),
+                        ("f", "tcMax", 0.0), "out", "flag", "undef"],
 }
 
 # operators whose device result may differ from the CPU by transcendental ulps (powf/expf/exp/pow/tanh);
@@ -168,6 +187,7 @@ TRANSCENDENTAL = {
     "hleveltemp": 1e-5, "hlevelthe": 1e-5, "hlevelhum": 1e-5, "hlevelducting": 1e-5,
     "aleveltemp": 1e-5, "alevelthe": 1e-5, "alevelhum": 1e-5, "alevelducting": 1e-5,
     "windCooling": 1e-5, "vesselIcingModStall": 1e-5, "vesselIcingMincog": 1e-4,
+    "abshum": 1e-6,  # double exp(): CUDA's is within 1 ulp of a double, the float result differs about once in 2^29
 }
 
 
@@ -249,8 +269,9 @@ def build(name, nx, ny, seed=0, undef=UNDEF, flag_in=SOME, mask="none", nmembers
             mf = member_flags if member_flags is not None else [flag_in] * nmembers
             args.append(np.array(mf, dtype=np.int32))
         elif d[0] in ("in", "in!", "inout"):
-            in_fields.append((len(args), d[1], d[0] != "in!"))
-            args.append(field(rng, d[1], nx, ny))
+            kind = params.get("kinds", {}).get(len(in_fields), d[1])  # kinds={position: kind} overrides the spec's field kind
+            in_fields.append((len(args), kind, d[0] != "in!"))
+            args.append(field(rng, kind, nx, ny))
         elif d[0] in ("f", "i", "s"):
             args.append(full[d[1]])
         elif d[0] == "members":

@@ -40,6 +40,19 @@ VARIANTS = {
     "stddevValue": [dict()],
     "extremeValue": [dict(compute=c) for c in (1, 2, 3, 4, 5)],
     "probability": [dict(compute=c) for c in (1, 2, 3, 4, 5, 6)] + [dict(compute=3, limits=(270.0,)), dict(compute=1, limits=()), dict(compute=7)],
+    "kIndex": [dict(compute=1), dict(compute=2), dict(compute=3), dict(compute=1, p500=700.0), dict(compute=1, p500=0.0), dict(compute=2, p850=925.0)],
+    "ductingIndex": [dict(compute=1), dict(compute=2), dict(compute=0), dict(compute=1, p850=-1.0)],
+    "showalterIndex": [dict(compute=1), dict(compute=2), dict(compute=3), dict(compute=1, p500=900.0), dict(compute=2, p500=400.0, p850=925.0)],
+    "boydenIndex": [dict(compute=1), dict(compute=2), dict(compute=3), dict(compute=1, p700=1000.0)],
+    "sweatIndex": [dict()],
+    "seaSoundSpeed": [dict(compute=1), dict(compute=2, kinds={0: "tk"}), dict(compute=3), dict(compute=1, z=-1200.0)],
+    "cvtemp": [dict(compute=1), dict(compute=2, kinds={0: "tc30"}), dict(compute=3), dict(compute=3, kinds={0: "tc30"}), dict(compute=4),
+               dict(compute=4, kinds={0: "tc30"}), dict(compute=5)],
+    "cvhum": [dict(compute=1, unit="kelvin"), dict(compute=1, unit="celsius"), dict(compute=2, unit=""), dict(compute=3, unit="", kinds={0: "tc30"}),
+              dict(compute=4, unit="", kinds={1: "tk"}), dict(compute=4, unit="1", kinds={1: "tk"}), dict(compute=5, unit="1", kinds={0: "tc30", 1: "tc30"}),
+              dict(compute=6, unit="")],
+    "abshum": [dict()],
+    "underCooledRain": [dict(), dict(precipMin=0.0, snowRateMax=0.5, tcMax=20.0)],
 }
 
 STENCILS = {"ilevelgwind", "relvort", "absvort", "divergence", "advection", "gradient", "shapiro2_filter", "thermalFrontParameter", "jacobian"}
