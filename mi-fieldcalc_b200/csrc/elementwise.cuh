@@ -80,10 +80,23 @@ struct op_has_quad<Op, std::void_t<decltype(Op::QUAD)>> : std::integral_constant
 {
 };
 
+// Optional: `static constexpr int ITEM_ROUNDS = J` makes an item of the PERSISTENT kernel J times larger (J rounds
+// of U groups per thread): the per-item bookkeeping (next item, field metadata, counters, index arithmetic) is
+// ~100 issue slots and only pays for itself when spread over enough points.
+template <class Op, class = void>
+struct op_item_rounds : std::integral_constant<int, 1>
+{
+};
+template <class Op>
+struct op_item_rounds<Op, std::void_t<decltype(Op::ITEM_ROUNDS)>> : std::integral_constant<int, Op::ITEM_ROUNDS>
+{
+};
+
 template <class Op, int W>
 struct EwShape
 {
   static constexpr int U = (W == 4) ? Op::UNROLL : Op::UNROLL * 2;
+  static constexpr int J = (U >= 2) ? op_item_rounds<Op>::value : 1; // rounds per item in the persistent kernel
 };
 
 // Index arithmetic of one item.  n < 2^31 (the reference's `int fsize`), so everything inside a field is
@@ -130,10 +143,11 @@ __device__ __forceinline__ void ew_load_group(const EwArgs<Op::NIN, Op::NOUT>& a
 }
 
 template <class Op, int W>
-__device__ __forceinline__ void ew_load(const EwArgs<Op::NIN, Op::NOUT>& a, unsigned field, unsigned chunk, float (&v)[EwShape<Op, W>::U][Op::NIN][W])
+__device__ __forceinline__ void ew_load(const EwArgs<Op::NIN, Op::NOUT>& a, unsigned field, unsigned chunk, float (&v)[EwShape<Op, W>::U][Op::NIN][W],
+                                        int groups_per_item = EwShape<Op, W>::U)
 {
   constexpr int U = EwShape<Op, W>::U;
-  const EwPos<W> pos(a, field, chunk, U);
+  const EwPos<W> pos(a, field, chunk, groups_per_item);
 #pragma unroll
   for (int u = 0; u < U; ++u)
     ew_load_group<Op, W>(a, field, pos, u, v[u]);
@@ -214,22 +228,28 @@ __device__ __forceinline__ void ew_compute(const Op& op, const EwArgs<Op::NIN, O
   ew_peel<Op, W, ALL>(op, a, c, field, chunk, pos, nundef);
 }
 
-// Persistent kernel, U >= 2: group u of the NEXT item is requested right after group u of the current item has
-// been consumed, into the same registers -- every load has the compute time of the other U - 1 groups plus the
-// loop turn-around to arrive, and no register is copied.
+// Persistent kernel, U >= 2: an item is J rounds of U groups per thread.  The group that will reuse a register
+// buffer (same u, next round -- or round 0 of the NEXT item) is requested right after the buffer has been
+// consumed: every load has the compute time of the other U - 1 groups plus the loop turn-around to arrive, and
+// no register is copied.
 template <class Op, int W, bool ALL>
 __device__ __forceinline__ void ew_compute_and_refill(const Op& op, const EwArgs<Op::NIN, Op::NOUT>& a, const PointCtx& c, unsigned field, unsigned chunk,
                                                       bool has_next, unsigned nfield, unsigned nchunk, float (&v)[EwShape<Op, W>::U][Op::NIN][W],
                                                       unsigned* nundef)
 {
-  constexpr int U = EwShape<Op, W>::U;
-  const EwPos<W> pos(a, field, chunk, U);
-  const EwPos<W> npos(a, nfield, nchunk, U);
+  constexpr int U = EwShape<Op, W>::U, J = EwShape<Op, W>::J;
+  const EwPos<W> pos(a, field, chunk, U * J);
+  const EwPos<W> npos(a, nfield, nchunk, U * J);
+#pragma unroll 1
+  for (int j = 0; j < J; ++j) {
 #pragma unroll
-  for (int u = 0; u < U; ++u) {
-    ew_compute_group<Op, W, ALL>(op, a, c, field, pos, u, v[u], nundef);
-    if (has_next)
-      ew_load_group<Op, W>(a, nfield, npos, u, v[u]);
+    for (int u = 0; u < U; ++u) {
+      ew_compute_group<Op, W, ALL>(op, a, c, field, pos, j * U + u, v[u], nundef);
+      if (j + 1 < J)
+        ew_load_group<Op, W>(a, field, pos, (j + 1) * U + u, v[u]);
+      else if (has_next)
+        ew_load_group<Op, W>(a, nfield, npos, u, v[u]);
+    }
   }
   ew_peel<Op, W, ALL>(op, a, c, field, chunk, pos, nundef);
 }
@@ -304,7 +324,7 @@ __global__ void __launch_bounds__(EW_THREADS, Op::MIN_BLOCKS) ew_kernel(const Op
   float v[U][Op::NIN][W];
   float vn[U >= 2 ? 1 : U][Op::NIN][W]; // only U == 1 needs a second buffer (and a register copy per item)
   if (item < items)
-    ew_load<Op, W>(a, field, chunk, v);
+    ew_load<Op, W>(a, field, chunk, v, U * EwShape<Op, W>::J); // round 0 of the first item
   while (item < items) {
     const unsigned nitem = item + grid;
     unsigned nfield = field + step_f, nchunk = chunk + step_c;
@@ -399,9 +419,14 @@ bool launch_elementwise(Call& call, const Op& op, const float* const* in, const 
   a.undef = undef;
   a.meta = meta;
   a.counters = counters;
+  // Operators that stage tables in shared memory run a persistent grid (as many CTAs as stay
+  // resident: occupancy x SM count) so that the staging is paid once per CTA; pure streaming and
+  // compute-heavy operators get one CTA per item and leave load balancing to the hardware scheduler.
+  constexpr bool persistent = (Op::USES_EWT || Op::USES_POW) && !Op::HEAVY;
   const int width = vec ? 4 : 1;
   const int unroll = vec ? Op::UNROLL : Op::UNROLL * 2;
-  const long long per_item = (long long)EW_THREADS * unroll * width;
+  const int rounds = !persistent ? 1 : (vec ? EwShape<Op, 4>::J : EwShape<Op, 1>::J);
+  const long long per_item = (long long)EW_THREADS * unroll * width * rounds;
   a.chunks = (int)((n + per_item - 1) / per_item);
   a.items = (long long)a.chunks * nfields;
 
@@ -409,10 +434,6 @@ bool launch_elementwise(Call& call, const Op& op, const float* const* in, const 
     set_error("fcb200: batch too large for one launch (%lld work items)", a.items);
     return false;
   }
-  // Operators that stage tables in shared memory run a persistent grid (as many CTAs as stay
-  // resident: occupancy x SM count) so that the staging is paid once per CTA; pure streaming and
-  // compute-heavy operators get one CTA per item and leave load balancing to the hardware scheduler.
-  const bool persistent = (Op::USES_EWT || Op::USES_POW) && !Op::HEAVY && !getenv("FCB200_EW_ONCE"); // TEMPORARY (tuning)
   if (!persistent) {
     if (vec)
       ew_kernel_once<Op, 4><<<(unsigned)a.items, EW_THREADS, 0, call.stream()>>>(op, a);

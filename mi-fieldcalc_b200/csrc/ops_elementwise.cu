@@ -397,9 +397,10 @@ struct MomentumOp
 // Each output keeps its own definedness test and its own undefined counter, so values, masks and
 // the four flags are exactly those of the four separate calls.  The Exner function and the
 // saturation-table lookup are evaluated once per point instead of three / two times.
-template <int U_, int MB_>
+template <int U_, int MB_, int J_ = 1>
 struct AlevelChainOpT
 {
+  static constexpr int ITEM_ROUNDS = J_;
   static constexpr int NIN = 3, NOUT = 4, UNROLL = U_;
   static constexpr int NCOUNT = 4;
   static constexpr int MIN_BLOCKS = MB_;
@@ -465,6 +466,8 @@ struct AlevelChainOpT
     const float2 e = tab.e[l];
     const float et = e.x + e.y * (x - (float)l); // MC.h:78
     const float qsat = dev::div_midrange(dev::K_EPS * et, p);
+    // (Evaluating this double quotient in float-float arithmetic with a midpoint test -- no conversions, no FP64 -- was
+    // measured 8 % SLOWER: the test's dependent chain costs more than the nine DFMA it replaces.)
     r.rh = (float)dev::div_midrange(100. * (double)q, (double)qsat); // FC.cc:229
     const float rq = dev::div_midrange(q, qsat);
     const float rhc = rq < dev::K_RHMIN ? dev::K_RHMIN : (rq > dev::K_RHMAX ? dev::K_RHMAX : rq); // clamp_rh, FC.cc:186-194
@@ -936,20 +939,10 @@ int fcb200_alevel_chain_batched(int nx, int ny, int nfields, const float* t, con
     job.undef = undef;
     return run_ew_job(op, job);
   };
-  // TEMPORARY (tuning): kernel shape selected at run time
-  const char* v = getenv("FCB200_CHAIN_VARIANT");
-  switch (v ? atoi(v) : 0) {
-  case 1:
-    return run(AlevelChainOpT<2, 2>{tdconv});
-  case 2:
-    return run(AlevelChainOpT<2, 3>{tdconv});
-  case 3:
-    return run(AlevelChainOpT<1, 3>{tdconv});
-  case 4:
-    return run(AlevelChainOpT<1, 2>{tdconv});
-  default:
-    return run(AlevelChainOpT<1, 4>{tdconv});
-  }
+  // Kernel shape (measured on B200, profiles/r01_chain_tuning.txt): 2 float4 groups per thread and round, 4 rounds per
+  // item, 2 CTAs of 256 threads per SM (<= 128 registers: the straight-line code of 8 interleaved points needs
+  // them; 64- and 80-register builds spill and lose 10-15 %).
+  return run(AlevelChainOpT<2, 2, 4>{tdconv});
 }
 
 } // extern "C"

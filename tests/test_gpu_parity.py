@@ -109,8 +109,18 @@ def test_full_size_fields(gpu, name, grid):
 @pytest.mark.parametrize("unit", ["celsius", "kelvin"])
 def test_fused_alevel_chain_equals_four_reference_calls(gpu, mask, flag, unit):
     """fcb200_alevel_chain_batched == aleveltemp(c3) + alevelhum(c1) + alevelhum(c5/9) + alevelthe(c1), field by field"""
+    _chain_against_reference_calls(gpu, 949, 23, 5, mask, flag, unit, (False, True))
+
+
+@pytest.mark.parametrize("mask,flag", [("none", cases.ALL), ("sparse", cases.SOME)])
+def test_fused_alevel_chain_full_size_batch(gpu, mask, flag):
+    """14 full MEPS levels: far more work items than resident CTAs, so every CTA of the persistent kernel walks
+    through several items and fields (prefetch across item and field boundaries, counters per field)"""
+    _chain_against_reference_calls(gpu, 949, 1069, 14, mask, flag, "celsius", (True,))
+
+
+def _chain_against_reference_calls(gpu, nx, ny, nf, mask, flag, unit, devices):
     arb = _arbiter()
-    nx, ny, nf = 949, 23, 5
     rng = np.random.default_rng(42)
     t = np.stack([cases.field(rng, "tk", nx, ny) for _ in range(nf)])
     q = np.stack([cases.field(rng, "q", nx, ny) for _ in range(nf)])
@@ -121,7 +131,7 @@ def test_fused_alevel_chain_equals_four_reference_calls(gpu, mask, flag, unit):
     outs = [np.full((nf, ny, nx), cases.SENTINEL, np.float32) for _ in range(4)]
     fin = np.full(nf, flag, np.int32)
     fout = np.full((4, nf), -1, np.int32)
-    for device in (False, True):
+    for device in devices:
         args = [t, q, p] + outs
         if device:
             args = [_to_device(a) for a in args]

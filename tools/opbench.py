@@ -86,7 +86,8 @@ def main():
         def build(grid, nf):
             nx, ny = grid
             rng = {"t": (215, 305), "q": (1e-6, 2e-2), "p": (300, 1040), "w": (-30, 30), "any": (-50, 50), "tc": (-25, 5), "sst": (-1, 8), "sal": (30, 35),
-                   "aice": (0, 0.6), "wave": (0, 8), "rh01": (0.4, 1), "pmsl": (960, 1030), "pw": (3, 12), "depth": (20, 3000)}
+                   "aice": (0, 0.6), "wave": (0, 8), "rh01": (0.4, 1), "pmsl": (960, 1030), "pw": (3, 12), "depth": (20, 3000), "rh": (1, 100), "z": (100, 5900),
+                   "precip": (0, 5), "snow": (0, 0.6)}
             fields = [rnd(batch(grid, nf), *rng[k]) for k in kinds]
             return list(lead) + [nx, ny, nf] + fields + list(scalars_before_out) + [torch.empty(batch(grid, nf), device=dev), np.full(nf, flag_in, np.int32), UNDEF]
         return build
@@ -153,6 +154,18 @@ def main():
         "vesselIcingMertins": ("vesselIcingMertins_batched", MEPS, 40, 28, b_ew(icing6)),
         "vesselIcingModStall": ("vesselIcingModStall_batched", MEPS, 4, 48, b_ew(icing11, (5.0, 2.6, 4.0, 4.0))),
         "vesselIcingMincog": ("vesselIcingMincog_batched", MEPS, 4, 48, b_ew(icing11, (5.0, 2.6, 4.0, 4.0, 1))),
+        # fixed-level indices and level-independent conversions (the rest of the Python subset); showalterIndex reads its
+        # output too (points with an undefined input stay untouched)
+        "kIndex": ("kIndex_batched", MEPS, 48, 24, b_ew(["t", "t", "rh", "t", "rh"], (500.0, 700.0, 850.0, 1))),
+        "ductingIndex": ("ductingIndex_batched", MEPS, 96, 12, b_ew(["t", "rh"], (850.0, 1))),
+        "showalterIndex": ("showalterIndex_batched", MEPS, 64, 20, b_ew(["t", "t", "rh"], (500.0, 850.0, 1))),
+        "boydenIndex": ("boydenIndex_batched", MEPS, 64, 16, b_ew(["t", "z", "z"], (700.0, 1000.0, 1))),
+        "sweatIndex": ("sweatIndex_batched", MEPS, 32, 36, b_ew(["t", "t", "t", "t", "w", "w", "w", "w"])),
+        "seaSoundSpeed": ("seaSoundSpeed_batched", MEPS, 96, 12, b_ew(["sst", "sal"], (50.0, 1))),
+        "cvtemp_c1": ("cvtemp_batched", MEPS, 128, 8, b_ew(["t"], (1,))),
+        "cvhum_c1": ("cvhum_batched", MEPS, 96, 12, b_ew(["t", "rh"], ("kelvin", 1))),
+        "abshum": ("abshum_batched", MEPS, 96, 12, b_ew(["t", "rh"])),
+        "underCooledRain": ("underCooledRain_batched", MEPS, 64, 16, b_ew(["precip", "snow", "t"], (0.5, 0.1, 0.0))),
         # ensemble, 30 members: bytes per OUTPUT point = 4*(M+1)
         "meanValue": ("meanValue_batched", MEPS, 8, 124, b_ens("meanValue")),
         "stddevValue": ("stddevValue_batched", MEPS, 8, 124, b_ens("stddevValue")),
