@@ -158,6 +158,36 @@ bool abshum(int nx, int ny, const float* t, const float* rhum, float* abshumout,
 bool underCooledRain(int nx, int ny, const float* precip, const float* snow, const float* tk, float precipMin, float snowRateMax,
                      float tcMax, float* undercooled, ValuesDefined& fDefined, float undef); /* ref:222 */
 
+/* ---- pressure-level siblings, element functions, field arithmetic (the rest of SURVEY.md 8f rank 1) ---- */
+bool plevelthe(int nx, int ny, const float* t, const float* rh, float p, int compute, float* the, ValuesDefined& fDefined, float undef); /* ref:115 */
+bool pleveldz2tmean(int nx, int ny, const float* z1, const float* z2, float p1, float p2, int compute, float* tmean, ValuesDefined& fDefined,
+                    float undef); /* ref:120 */
+bool plevelducting(int nx, int ny, const float* t, const float* h, float p, int compute, float* duct, ValuesDefined& fDefined,
+                   float undef); /* ref:125 */
+bool vectorabs(int nx, int ny, const float* u, const float* v, float* ff, ValuesDefined& fDefined, float undef); /* ref:204 */
+bool pressure2FlightLevel(int nx, int ny, const float* pressure, float* flightlevel, ValuesDefined& fDefined, float undef); /* ref:227 */
+bool values2classes(int nx, int ny, const float* fvalue, float* fclass, const std::vector<float>& values, ValuesDefined& fDefined,
+                    float undef); /* ref:252 */
+void minvalueFields(int nx, int ny, const float* field1, const float* field2, float* fres, ValuesDefined& fDefined, float undef); /* ref:254 */
+void minvalueFieldConst(int nx, int ny, const float* field1, const float value, float* fres, ValuesDefined& fDefined, float undef); /* ref:256 */
+void maxvalueFields(int nx, int ny, const float* field1, const float* field2, float* fres, ValuesDefined& fDefined, float undef); /* ref:258 */
+void maxvalueFieldConst(int nx, int ny, const float* field1, const float value, float* fres, ValuesDefined& fDefined, float undef); /* ref:260 */
+void absvalueField(int nx, int ny, const float* field, float* fres, ValuesDefined& fDefined, float undef); /* ref:262 */
+void log10Field(int nx, int ny, const float* field, float* fres, ValuesDefined& fDefined, float undef); /* ref:264 */
+void pow10Field(int nx, int ny, const float* field, float* fres, ValuesDefined& fDefined, float undef); /* ref:266 */
+void logField(int nx, int ny, const float* field, float* fres, ValuesDefined& fDefined, float undef); /* ref:268 */
+void expField(int nx, int ny, const float* field, float* fres, ValuesDefined& fDefined, float undef); /* ref:270 */
+void powerField(int nx, int ny, const float* field, float value, float* fres, ValuesDefined& fDefined, float undef); /* ref:272 */
+void replaceUndefined(int nx, int ny, const float* field, float value, float* fres, ValuesDefined& fDefined, float undef); /* ref:274 */
+void replaceDefined(int nx, int ny, const float* field, float value, float* fres, ValuesDefined& fDefined, float undef); /* ref:276 */
+bool fieldOPERconstant(int compute, int nx, int ny, const float* field, float value, float* fres, ValuesDefined& fDefined,
+                       float undef); /* ref:280 */
+bool constantOPERfield(int compute, int nx, int ny, float value, const float* field, float* fres, ValuesDefined& fDefined,
+                       float undef); /* ref:282 */
+bool sumFields(int nx, int ny, const std::vector<float*>& fields, float* fres, ValuesDefined& fDefined, float undef); /* ref:284 */
+bool snow_in_cm(int nx, int ny, const float* snow_water, const float* tk2m, const float* td2m, float* snow_cm, ValuesDefined& fDefined,
+                float undef); /* ref:303 */
+
 /* ---- field arithmetic (compute first) ---- */
 bool fieldOPERfield(int compute, int nx, int ny, const float* field1, const float* field2, float* fres, ValuesDefined& fDefined,
                     float undef); /* ref:278 */

@@ -278,6 +278,98 @@ bool underCooledRain(int nx, int ny, const float* precip, const float* snow, con
   return done(fcb200_underCooledRain(nx, ny, precip, snow, tk, precipMin, snowRateMax, tcMax, undercooled, &f, undef), f, fDefined);
 }
 
+// ---- pressure-level siblings, element functions, field arithmetic
+bool plevelthe(int nx, int ny, const float* t, const float* rh, float p, int compute, float* the, ValuesDefined& fDefined, float undef)
+{
+  FCB_FLAG;
+  return done(fcb200_plevelthe(nx, ny, t, rh, p, compute, the, &f, undef), f, fDefined);
+}
+
+bool pleveldz2tmean(int nx, int ny, const float* z1, const float* z2, float p1, float p2, int compute, float* tmean, ValuesDefined& fDefined, float undef)
+{
+  FCB_FLAG;
+  return done(fcb200_pleveldz2tmean(nx, ny, z1, z2, p1, p2, compute, tmean, &f, undef), f, fDefined);
+}
+
+bool plevelducting(int nx, int ny, const float* t, const float* h, float p, int compute, float* duct, ValuesDefined& fDefined, float undef)
+{
+  FCB_FLAG;
+  return done(fcb200_plevelducting(nx, ny, t, h, p, compute, duct, &f, undef), f, fDefined);
+}
+
+bool vectorabs(int nx, int ny, const float* u, const float* v, float* ff, ValuesDefined& fDefined, float undef)
+{
+  FCB_FLAG;
+  return done(fcb200_vectorabs(nx, ny, u, v, ff, &f, undef), f, fDefined);
+}
+
+bool pressure2FlightLevel(int nx, int ny, const float* pressure, float* flightlevel, ValuesDefined& fDefined, float undef)
+{
+  FCB_FLAG;
+  return done(fcb200_pressure2FlightLevel(nx, ny, pressure, flightlevel, &f, undef), f, fDefined);
+}
+
+bool values2classes(int nx, int ny, const float* fvalue, float* fclass, const std::vector<float>& values, ValuesDefined& fDefined, float undef)
+{
+  FCB_FLAG;
+  return done(fcb200_values2classes(nx, ny, fvalue, fclass, values.data(), (int)values.size(), &f, undef), f, fDefined);
+}
+
+#define FCB_SHIM_VOID2(name)                                                                                                                         \
+  void name(int nx, int ny, const float* field1, const float* field2, float* fres, ValuesDefined& fDefined, float undef)                             \
+  {                                                                                                                                                  \
+    FCB_FLAG;                                                                                                                                        \
+    done(fcb200_##name(nx, ny, field1, field2, fres, &f, undef), f, fDefined);                                                                       \
+  }
+#define FCB_SHIM_VOID1C(name)                                                                                                                        \
+  void name(int nx, int ny, const float* field, const float value, float* fres, ValuesDefined& fDefined, float undef)                                \
+  {                                                                                                                                                  \
+    FCB_FLAG;                                                                                                                                        \
+    done(fcb200_##name(nx, ny, field, value, fres, &f, undef), f, fDefined);                                                                         \
+  }
+#define FCB_SHIM_VOID1(name)                                                                                                                         \
+  void name(int nx, int ny, const float* field, float* fres, ValuesDefined& fDefined, float undef)                                                   \
+  {                                                                                                                                                  \
+    FCB_FLAG;                                                                                                                                        \
+    done(fcb200_##name(nx, ny, field, fres, &f, undef), f, fDefined);                                                                                \
+  }
+FCB_SHIM_VOID2(minvalueFields)
+FCB_SHIM_VOID1C(minvalueFieldConst)
+FCB_SHIM_VOID2(maxvalueFields)
+FCB_SHIM_VOID1C(maxvalueFieldConst)
+FCB_SHIM_VOID1(absvalueField)
+FCB_SHIM_VOID1(log10Field)
+FCB_SHIM_VOID1(pow10Field)
+FCB_SHIM_VOID1(logField)
+FCB_SHIM_VOID1(expField)
+FCB_SHIM_VOID1C(powerField)
+FCB_SHIM_VOID1C(replaceUndefined)
+FCB_SHIM_VOID1C(replaceDefined)
+
+bool fieldOPERconstant(int compute, int nx, int ny, const float* field, float value, float* fres, ValuesDefined& fDefined, float undef)
+{
+  FCB_FLAG;
+  return done(fcb200_fieldOPERconstant(compute, nx, ny, field, value, fres, &f, undef), f, fDefined);
+}
+
+bool constantOPERfield(int compute, int nx, int ny, float value, const float* field, float* fres, ValuesDefined& fDefined, float undef)
+{
+  FCB_FLAG;
+  return done(fcb200_constantOPERfield(compute, nx, ny, value, field, fres, &f, undef), f, fDefined);
+}
+
+bool sumFields(int nx, int ny, const std::vector<float*>& fields, float* fres, ValuesDefined& fDefined, float undef)
+{
+  FCB_FLAG;
+  return done(fcb200_sumFields(nx, ny, fields.data(), (int)fields.size(), fres, &f, undef), f, fDefined);
+}
+
+bool snow_in_cm(int nx, int ny, const float* snow_water, const float* tk2m, const float* td2m, float* snow_cm, ValuesDefined& fDefined, float undef)
+{
+  FCB_FLAG;
+  return done(fcb200_snow_in_cm(nx, ny, snow_water, tk2m, td2m, snow_cm, &f, undef), f, fDefined);
+}
+
 bool windCooling(int nx, int ny, const float* t, const float* u, const float* v, int compute, float* dtcool, ValuesDefined& fDefined, float undef)
 {
   FCB_FLAG;

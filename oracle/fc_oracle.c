@@ -1833,3 +1833,418 @@ int fco_underCooledRain(int nx, int ny, const float* precip, const float* snow, 
   *fDefined = check_defined(nu, n);
   return 1;
 }
+
+/* ================================================================================================
+ * The rest of SURVEY.md 8f rank 1: field arithmetic, element functions, p-level siblings
+ * ================================================================================================ */
+static int fill_undef(int nx, int ny, float* fres, int* fDefined, float undef)
+{ /* FC.cc:76-82 */
+  const size_t n = (size_t)nx * ny;
+  *fDefined = NONE_DEFINED;
+  for (size_t i = 0; i < n; ++i)
+    fres[i] = undef;
+  return 1;
+}
+
+static inline float tk_rh_the(float tk, float rh, float thconv, float undef, size_t* nu)
+{ /* FC.cc:269-278 */
+  EWT_OR_UNDEF(e, tk - K_T0)
+  return tk * thconv + ewt_value(e) * rh;
+}
+
+int fco_plevelthe(int nx, int ny, const float* t, const float* rh, float p, int compute, float* the, int* fDefined, float undef)
+{ /* FC.cc:369-398 */
+  if (compute != 1 && compute != 2)
+    return 0;
+  if (p <= 0.0)
+    return 0;
+  const float pidcp = pidcp_from_p(p), pi = pidcp * K_CP;
+  const float cvrh = (float)(0.01 * (K_XLH / pi) * K_EPS / p);
+  const float tconv = (compute == 2) ? pidcp : 1.f;
+  const float thconv = 1 / pidcp;
+  const size_t n = (size_t)nx * ny;
+  const int all = *fDefined == ALL_DEFINED;
+  size_t nu = 0;
+  for (size_t i = 0; i < n; ++i) {
+    if (all || (is_def(t[i], undef) && is_def(rh[i], undef)))
+      the[i] = tk_rh_the(t[i] * tconv, rh[i] * cvrh, thconv, undef, &nu);
+    else {
+      the[i] = undef;
+      nu += 1;
+    }
+  }
+  *fDefined = check_defined(nu, n);
+  return 1;
+}
+
+int fco_pleveldz2tmean(int nx, int ny, const float* z1, const float* z2, float p1, float p2, int compute, float* tmean, int* fDefined, float undef)
+{ /* FC.cc:466-503; binaryFunctionFieldField: flag untouched */
+  if (p1 <= 0 || p2 <= 0 || p1 == p2)
+    return 0;
+  const float g = (float)9.8;
+  const float pi1 = pi_from_p(p1), pi2 = pi_from_p(p2);
+  float convert, tconvert;
+  switch (compute) {
+  case 1:
+    convert = (float)(g * 0.5 * (pi1 + pi2) / ((pi2 - pi1) * K_CP));
+    tconvert = -K_T0;
+    break;
+  case 2:
+    convert = (float)(g * 0.5 * (pi1 + pi2) / ((pi2 - pi1) * K_CP));
+    tconvert = 0.f;
+    break;
+  case 3:
+    convert = g / (pi2 - pi1);
+    tconvert = 0.f;
+    break;
+  default:
+    return 0;
+  }
+  const size_t n = (size_t)nx * ny;
+  const int all = *fDefined == ALL_DEFINED;
+  for (size_t i = 0; i < n; ++i) {
+    if (all || (is_def(z1[i], undef) && is_def(z2[i], undef)))
+      tmean[i] = (z1[i] - z2[i]) * convert + tconvert;
+    else
+      tmean[i] = undef;
+  }
+  return 1;
+}
+
+int fco_plevelducting(int nx, int ny, const float* t, const float* h, float p, int compute, float* duct, int* fDefined, float undef)
+{ /* FC.cc:597-636 */
+  if (p <= 0)
+    return 0;
+  const float tconv = (compute % 2 == 0) ? pidcp_from_p(p) : 1.f;
+  const size_t n = (size_t)nx * ny;
+  const int all = *fDefined == ALL_DEFINED;
+  if (compute == 1 || compute == 2) {
+    for (size_t i = 0; i < n; ++i) {
+      if (all || (is_def(t[i], undef) && is_def(h[i], undef)))
+        duct[i] = tk_q_duct(t[i] * tconv, h[i], p);
+      else
+        duct[i] = undef;
+    }
+    return 1;
+  }
+  if (compute == 3 || compute == 4) {
+    size_t nu = 0;
+    for (size_t i = 0; i < n; ++i) {
+      if (all || (is_def(t[i], undef) && is_def(h[i], undef)))
+        duct[i] = tk_rh_duct(t[i] * tconv, h[i], p, undef, &nu);
+      else {
+        duct[i] = undef;
+        nu += 1;
+      }
+    }
+    *fDefined = check_defined(nu, n);
+    return 1;
+  }
+  return 0;
+}
+
+int fco_vectorabs(int nx, int ny, const float* u, const float* v, float* ff, int* fDefined, float undef)
+{ /* FC.cc:1819-1841 */
+  const size_t n = (size_t)nx * ny;
+  const int all = *fDefined == ALL_DEFINED;
+  size_t nu = 0;
+  for (size_t i = 0; i < n; ++i) {
+    if (all || (is_def(u[i], undef) && is_def(v[i], undef)))
+      ff[i] = sqrtf(u[i] * u[i] + v[i] * v[i]);
+    else {
+      ff[i] = undef;
+      nu += 1;
+    }
+  }
+  *fDefined = check_defined(nu, n);
+  return 1;
+}
+
+int fco_pressure2FlightLevel(int nx, int ny, const float* pressure, float* flightlevel, int* fDefined, float undef)
+{ /* FC.cc:2311-2349, tables MC.h:87-89 */
+  static const float pT[16] = {1000, 925, 850, 800, 700, 500, 400, 300, 250, 200, 150, 100, 70, 50, 30, 10};
+  static const float fT[16] = {5, 25, 50, 65, 100, 185, 235, 300, 340, 385, 445, 530, 605, 675, 780, 1020};
+  const int nTab = 15;
+  const size_t n = (size_t)nx * ny;
+  const int all = *fDefined == ALL_DEFINED;
+  size_t nu = 0;
+  for (size_t i = 0; i < n; ++i) {
+    if (all || is_def(pressure[i], undef)) {
+      float p = pressure[i];
+      if (p > pT[0])
+        p = pT[0];
+      if (p < pT[nTab])
+        p = pT[nTab];
+      int k = 1;
+      while (k < nTab && pT[k] > p)
+        k++;
+      const float ratio = (p - pT[k - 1]) / (pT[k] - pT[k - 1]);
+      flightlevel[i] = fT[k - 1] + (fT[k] - fT[k - 1]) * ratio;
+    } else {
+      flightlevel[i] = undef;
+      nu += 1;
+    }
+  }
+  *fDefined = check_defined(nu, n);
+  return 1;
+}
+
+int fco_values2classes(int nx, int ny, const float* fvalue, float* fclass, const float* values, int nvalues_in, int* fDefined, float undef)
+{ /* FC.cc:2462-2499 */
+  if (nvalues_in < 2)
+    return 0;
+  const int nvalues = nvalues_in - 2;
+  const float fmin = values[0], fmax = values[nvalues + 1];
+  const size_t n = (size_t)nx * ny;
+  const int all = *fDefined == ALL_DEFINED;
+  size_t nu = 0;
+  for (size_t i = 0; i < n; ++i) {
+    if ((all || is_def(fvalue[i], undef)) && fvalue[i] >= fmin && fvalue[i] < fmax) {
+      int j = 1;
+      while (j < nvalues && values[j] < fvalue[i])
+        j++;
+      fclass[i] = (float)(j - 1);
+    } else {
+      fclass[i] = undef;
+      nu += 1;
+    }
+  }
+  *fDefined = check_defined(nu, n);
+  return 1;
+}
+
+/* unaryFunctionField / binaryFunctionFieldField, FC.cc:94-140: undefined -> undef, flag untouched */
+#define UNARY_LOOP(EXPR)                                                                                                                             \
+  do {                                                                                                                                               \
+    const size_t n = (size_t)nx * ny;                                                                                                                \
+    const int all = *fDefined == ALL_DEFINED;                                                                                                        \
+    for (size_t i = 0; i < n; ++i) {                                                                                                                 \
+      const float a = field[i];                                                                                                                      \
+      fres[i] = (all || is_def(a, undef)) ? (EXPR) : undef;                                                                                          \
+    }                                                                                                                                                \
+  } while (0)
+
+static inline float std_min(float a, float b)
+{ /* std::min(a, b) */
+  return (b < a) ? b : a;
+}
+static inline float std_max(float a, float b)
+{ /* std::max(a, b) */
+  return (a < b) ? b : a;
+}
+
+int fco_minvalueFields(int nx, int ny, const float* field1, const float* field2, float* fres, int* fDefined, float undef)
+{ /* FC.cc:2501-2505 */
+  const size_t n = (size_t)nx * ny;
+  const int all = *fDefined == ALL_DEFINED;
+  for (size_t i = 0; i < n; ++i)
+    fres[i] = (all || (is_def(field1[i], undef) && is_def(field2[i], undef))) ? std_min(field1[i], field2[i]) : undef;
+  return 1;
+}
+
+int fco_maxvalueFields(int nx, int ny, const float* field1, const float* field2, float* fres, int* fDefined, float undef)
+{ /* FC.cc:2516-2520 */
+  const size_t n = (size_t)nx * ny;
+  const int all = *fDefined == ALL_DEFINED;
+  for (size_t i = 0; i < n; ++i)
+    fres[i] = (all || (is_def(field1[i], undef) && is_def(field2[i], undef))) ? std_max(field1[i], field2[i]) : undef;
+  return 1;
+}
+
+int fco_minvalueFieldConst(int nx, int ny, const float* field, float value, float* fres, int* fDefined, float undef)
+{ /* FC.cc:2507-2514 */
+  if (value == undef)
+    return fill_undef(nx, ny, fres, fDefined, undef);
+  UNARY_LOOP(std_min(a, value));
+  return 1;
+}
+
+int fco_maxvalueFieldConst(int nx, int ny, const float* field, float value, float* fres, int* fDefined, float undef)
+{ /* FC.cc:2522-2529 */
+  if (value == undef)
+    return fill_undef(nx, ny, fres, fDefined, undef);
+  UNARY_LOOP(std_max(a, value));
+  return 1;
+}
+
+int fco_absvalueField(int nx, int ny, const float* field, float* fres, int* fDefined, float undef)
+{ /* FC.cc:2531-2534 */
+  UNARY_LOOP(fabsf(a));
+  return 1;
+}
+
+int fco_log10Field(int nx, int ny, const float* field, float* fres, int* fDefined, float undef)
+{ /* FC.cc:2536-2539 */
+  UNARY_LOOP(log10f(a));
+  return 1;
+}
+
+int fco_pow10Field(int nx, int ny, const float* field, float* fres, int* fDefined, float undef)
+{ /* FC.cc:2541-2544; math_util.h:121-125: std::pow(10, float) is the double pow */
+  UNARY_LOOP((float)pow(10.0, (double)a));
+  return 1;
+}
+
+int fco_logField(int nx, int ny, const float* field, float* fres, int* fDefined, float undef)
+{ /* FC.cc:2546-2549 */
+  UNARY_LOOP(logf(a));
+  return 1;
+}
+
+int fco_expField(int nx, int ny, const float* field, float* fres, int* fDefined, float undef)
+{ /* FC.cc:2551-2554 */
+  UNARY_LOOP(expf(a));
+  return 1;
+}
+
+int fco_powerField(int nx, int ny, const float* field, float value, float* fres, int* fDefined, float undef)
+{ /* FC.cc:2556-2563 */
+  if (value == undef)
+    return fill_undef(nx, ny, fres, fDefined, undef);
+  UNARY_LOOP(powf(a, value));
+  return 1;
+}
+
+int fco_replaceUndefined(int nx, int ny, const float* field, float value, float* fres, int* fDefined, float undef)
+{ /* FC.cc:2565-2587: tests `== undef` only (a NaN is kept) */
+  const size_t n = (size_t)nx * ny;
+  if (value == undef || *fDefined == ALL_DEFINED) {
+    if (fres != field)
+      memcpy(fres, field, sizeof(float) * n);
+    return 1;
+  }
+  if (*fDefined == NONE_DEFINED) {
+    for (size_t i = 0; i < n; ++i)
+      fres[i] = value;
+  } else {
+    for (size_t i = 0; i < n; ++i)
+      fres[i] = (field[i] == undef) ? value : field[i];
+  }
+  *fDefined = ALL_DEFINED;
+  return 1;
+}
+
+int fco_replaceDefined(int nx, int ny, const float* field, float value, float* fres, int* fDefined, float undef)
+{ /* FC.cc:2589-2609 */
+  const size_t n = (size_t)nx * ny;
+  if (value == undef || *fDefined == NONE_DEFINED) {
+    for (size_t i = 0; i < n; ++i)
+      fres[i] = undef;
+    *fDefined = NONE_DEFINED;
+    return 1;
+  }
+  if (*fDefined == ALL_DEFINED) {
+    for (size_t i = 0; i < n; ++i)
+      fres[i] = value;
+  } else {
+    for (size_t i = 0; i < n; ++i)
+      fres[i] = (field[i] != undef) ? value : field[i];
+  }
+  *fDefined = ALL_DEFINED;
+  return 1;
+}
+
+int fco_fieldOPERconstant(int compute, int nx, int ny, const float* field, float value, float* fres, int* fDefined, float undef)
+{ /* FC.cc:2627-2645 */
+  if ((value == undef) || (compute == 4 && value == 0))
+    return fill_undef(nx, ny, fres, fDefined, undef);
+  switch (compute) {
+  case 1:
+    UNARY_LOOP(a + value);
+    return 1;
+  case 2:
+    UNARY_LOOP(a - value);
+    return 1;
+  case 3:
+    UNARY_LOOP(a * value);
+    return 1;
+  case 4:
+    UNARY_LOOP(a / value);
+    return 1;
+  default:
+    return 0;
+  }
+}
+
+int fco_constantOPERfield(int compute, int nx, int ny, float value, const float* field, float* fres, int* fDefined, float undef)
+{ /* FC.cc:2647-2669 */
+  if (value == undef)
+    return fill_undef(nx, ny, fres, fDefined, undef);
+  switch (compute) {
+  case 1:
+    UNARY_LOOP(value + a);
+    return 1;
+  case 2:
+    UNARY_LOOP(value - a);
+    return 1;
+  case 3:
+    UNARY_LOOP(value * a);
+    return 1;
+  case 4: {
+    const size_t n = (size_t)nx * ny;
+    const int all = *fDefined == ALL_DEFINED;
+    size_t nu = 0;
+    for (size_t i = 0; i < n; ++i) {
+      if ((all || is_def(field[i], undef)) && field[i] != 0)
+        fres[i] = value / field[i];
+      else {
+        fres[i] = undef;
+        nu += 1;
+      }
+    }
+    *fDefined = check_defined(nu, n);
+    return 1;
+  }
+  default:
+    return 0;
+  }
+}
+
+int fco_sumFields(int nx, int ny, const float* const* fields, int nfields, float* fres, int* fDefined, float undef)
+{ /* FC.cc:2671-2694 */
+  const size_t n = (size_t)nx * ny;
+  const int all = *fDefined == ALL_DEFINED;
+  size_t nu = 0;
+  for (size_t i = 0; i < n; ++i) {
+    fres[i] = 0;
+    for (int j = 0; j < nfields; ++j) {
+      if (all || is_def(fields[j][i], undef))
+        fres[i] += fields[j][i];
+      else {
+        fres[i] = undef;
+        nu += 1;
+        break;
+      }
+    }
+  }
+  *fDefined = check_defined(nu, n);
+  return 1;
+}
+
+int fco_snow_in_cm(int nx, int ny, const float* snow_water, const float* tk2m, const float* td2m, float* snow_cm, int* fDefined, float undef)
+{ /* FC.cc:3063-3118: exp() on a double argument, every line a double expression rounded to float */
+  const size_t n = (size_t)nx * ny;
+  const int all = *fDefined == ALL_DEFINED;
+  size_t nu = 0;
+  for (size_t i = 0; i < n; ++i) {
+    if (all || (is_def(snow_water[i], undef) && is_def(tk2m[i], undef) && is_def(td2m[i], undef))) {
+      if (snow_water[i] <= 0.) {
+        snow_cm[i] = 0.f;
+        continue;
+      }
+      const float t = (float)((tk2m[i] + td2m[i]) / 2.);
+      const float logit_t = (float)((1 - exp((t - 274.3) * 3.5)) / (1 + exp((t - 274.3) * 3.5)));
+      const float mm2cm_t = (float)(0.13 / (0.02 + 0.1 * ((t - 252.0) / 20.0) * ((t - 252.0) / 20.0)));
+      const float fac = logit_t * mm2cm_t;
+      if (fac <= 1.)
+        snow_cm[i] = snow_water[i];
+      else
+        snow_cm[i] = snow_water[i] * fac;
+    } else {
+      snow_cm[i] = undef;
+      nu += 1;
+    }
+  }
+  *fDefined = check_defined(nu, n);
+  return 1;
+}

@@ -344,4 +344,89 @@ int fcref_underCooledRain(int nx, int ny, const float* precip, const float* snow
   return fc::underCooledRain(nx, ny, precip, snow, tk, precipMin, snowRateMax, tcMax, undercooled, f, undef);
 }
 
+// ---- the rest of SURVEY.md 8f rank 1
+int fcref_plevelthe(int nx, int ny, const float* t, const float* rh, float p, int compute, float* the, int* fDefined, float undef)
+{
+  Flag f(fDefined);
+  return fc::plevelthe(nx, ny, t, rh, p, compute, the, f, undef);
+}
+int fcref_pleveldz2tmean(int nx, int ny, const float* z1, const float* z2, float p1, float p2, int compute, float* tmean, int* fDefined, float undef)
+{
+  Flag f(fDefined);
+  return fc::pleveldz2tmean(nx, ny, z1, z2, p1, p2, compute, tmean, f, undef);
+}
+int fcref_plevelducting(int nx, int ny, const float* t, const float* h, float p, int compute, float* duct, int* fDefined, float undef)
+{
+  Flag f(fDefined);
+  return fc::plevelducting(nx, ny, t, h, p, compute, duct, f, undef);
+}
+int fcref_vectorabs(int nx, int ny, const float* u, const float* v, float* ff, int* fDefined, float undef)
+{
+  Flag f(fDefined);
+  return fc::vectorabs(nx, ny, u, v, ff, f, undef);
+}
+int fcref_pressure2FlightLevel(int nx, int ny, const float* pressure, float* flightlevel, int* fDefined, float undef)
+{
+  Flag f(fDefined);
+  return fc::pressure2FlightLevel(nx, ny, pressure, flightlevel, f, undef);
+}
+int fcref_values2classes(int nx, int ny, const float* fvalue, float* fclass, const float* values, int nvalues, int* fDefined, float undef)
+{
+  Flag f(fDefined);
+  return fc::values2classes(nx, ny, fvalue, fclass, std::vector<float>(values, values + (nvalues > 0 ? nvalues : 0)), f, undef);
+}
+#define FCREF_VOID2(name)                                                                                                                            \
+  int fcref_##name(int nx, int ny, const float* field1, const float* field2, float* fres, int* fDefined, float undef)                               \
+  {                                                                                                                                                  \
+    Flag f(fDefined);                                                                                                                                \
+    fc::name(nx, ny, field1, field2, fres, f, undef);                                                                                                \
+    return 1;                                                                                                                                        \
+  }
+#define FCREF_VOID1C(name)                                                                                                                           \
+  int fcref_##name(int nx, int ny, const float* field, float value, float* fres, int* fDefined, float undef)                                        \
+  {                                                                                                                                                  \
+    Flag f(fDefined);                                                                                                                                \
+    fc::name(nx, ny, field, value, fres, f, undef);                                                                                                  \
+    return 1;                                                                                                                                        \
+  }
+#define FCREF_VOID1(name)                                                                                                                            \
+  int fcref_##name(int nx, int ny, const float* field, float* fres, int* fDefined, float undef)                                                      \
+  {                                                                                                                                                  \
+    Flag f(fDefined);                                                                                                                                \
+    fc::name(nx, ny, field, fres, f, undef);                                                                                                         \
+    return 1;                                                                                                                                        \
+  }
+FCREF_VOID2(minvalueFields)
+FCREF_VOID2(maxvalueFields)
+FCREF_VOID1C(minvalueFieldConst)
+FCREF_VOID1C(maxvalueFieldConst)
+FCREF_VOID1(absvalueField)
+FCREF_VOID1(log10Field)
+FCREF_VOID1(pow10Field)
+FCREF_VOID1(logField)
+FCREF_VOID1(expField)
+FCREF_VOID1C(powerField)
+FCREF_VOID1C(replaceUndefined)
+FCREF_VOID1C(replaceDefined)
+int fcref_fieldOPERconstant(int compute, int nx, int ny, const float* field, float value, float* fres, int* fDefined, float undef)
+{
+  Flag f(fDefined);
+  return fc::fieldOPERconstant(compute, nx, ny, field, value, fres, f, undef);
+}
+int fcref_constantOPERfield(int compute, int nx, int ny, float value, const float* field, float* fres, int* fDefined, float undef)
+{
+  Flag f(fDefined);
+  return fc::constantOPERfield(compute, nx, ny, value, field, fres, f, undef);
+}
+int fcref_sumFields(int nx, int ny, const float* const* fields, int nfields, float* fres, int* fDefined, float undef)
+{
+  Flag f(fDefined);
+  return fc::sumFields(nx, ny, as_vector(fields, nfields), fres, f, undef);
+}
+int fcref_snow_in_cm(int nx, int ny, const float* snow_water, const float* tk2m, const float* td2m, float* snow_cm, int* fDefined, float undef)
+{
+  Flag f(fDefined);
+  return fc::snow_in_cm(nx, ny, snow_water, tk2m, td2m, snow_cm, f, undef);
+}
+
 } // extern "C"

@@ -61,6 +61,11 @@ FIELD_RANGES = {
     "precip": (0.0, 5.0),      # mm
     "snow": (0.0, 0.6),        # mm water
     "tc30": (-40.0, 35.0),     # temperature, deg C (cvtemp / cvhum Celsius modes)
+    "pfl": (5.0, 1050.0),      # pressure for the flight-level table, hPa (beyond both ends of the table)
+    "pos": (0.05, 900.0),      # strictly positive (log, pow)
+    "small": (-8.0, 8.0),      # exponent range (exp, 10^x)
+    "snoww": (-0.5, 20.0),     # snow water, kg/m2 (some non-positive)
+    "t2m": (255.0, 278.0),     # 2 m temperature / dew point around freezing, K
 }
 
 
@@ -179,6 +184,29 @@ SPECS = {
     "abshum": ["nx", "ny", ("in", "tk"), ("in", "rh"), "out", "flag", "undef"],
     "underCooledRain": ["nx", "ny", ("in", "precip"), ("in", "snow"), ("in", "tk"), ("f", "precipMin", 0.5), ("f", "snowRateMax", 0.1),
                         ("f", "tcMax", 0.0), "out", "flag", "undef"],
+    # the rest of SURVEY.md 8f rank 1
+    "plevelthe": ["nx", "ny", ("in", "tk"), ("in", "rh"), ("f", "p", 850.0), ("i", "compute", 1), "out", "flag", "undef"],
+    "pleveldz2tmean": ["nx", "ny", ("in", "z"), ("in", "z"), ("f", "p1", 1000.0), ("f", "p2", 500.0), ("i", "compute", 1), "out", "flag", "undef"],
+    "plevelducting": ["nx", "ny", ("in", "tk"), ("in", "q"), ("f", "p", 850.0), ("i", "compute", 1), "out", "flag", "undef"],
+    "vectorabs": ["nx", "ny", ("in", "wind"), ("in", "wind"), "out", "flag", "undef"],
+    "pressure2FlightLevel": ["nx", "ny", ("in", "pfl"), "out", "flag", "undef"],
+    "values2classes": ["nx", "ny", ("in", "tk"), "out", ("limits", (230.0, 250.0, 262.5, 270.0, 280.0, 300.0)), "flag", "undef"],
+    "minvalueFields": ["nx", "ny", ("in", "any"), ("in", "any"), "out", "flag", "undef"],
+    "minvalueFieldConst": ["nx", "ny", ("in", "any"), ("f", "value", 3.5), "out", "flag", "undef"],
+    "maxvalueFields": ["nx", "ny", ("in", "any"), ("in", "any"), "out", "flag", "undef"],
+    "maxvalueFieldConst": ["nx", "ny", ("in", "any"), ("f", "value", 3.5), "out", "flag", "undef"],
+    "absvalueField": ["nx", "ny", ("in", "any"), "out", "flag", "undef"],
+    "log10Field": ["nx", "ny", ("in", "pos"), "out", "flag", "undef"],
+    "pow10Field": ["nx", "ny", ("in", "small"), "out", "flag", "undef"],
+    "logField": ["nx", "ny", ("in", "pos"), "out", "flag", "undef"],
+    "expField": ["nx", "ny", ("in", "small"), "out", "flag", "undef"],
+    "powerField": ["nx", "ny", ("in", "pos"), ("f", "value", 1.7), "out", "flag", "undef"],
+    "replaceUndefined": ["nx", "ny", ("in", "any"), ("f", "value", -1.0), "out", "flag", "undef"],
+    "replaceDefined": ["nx", "ny", ("in", "any"), ("f", "value", -1.0), "out", "flag", "undef"],
+    "fieldOPERconstant": [("i", "compute", 1), "nx", "ny", ("in", "any"), ("f", "value", 2.5), "out", "flag", "undef"],
+    "constantOPERfield": [("i", "compute", 1), "nx", "ny", ("f", "value", 2.5), ("in", "any"), "out", "flag", "undef"],
+    "sumFields": ["nx", "ny", ("members", "tk"), "out", "flag", "undef"],
+    "snow_in_cm": ["nx", "ny", ("in", "snoww"), ("in", "t2m"), ("in", "t2m"), "out", "flag", "undef"],
 }
 
 # operators whose device result may differ from the CPU by transcendental ulps (powf/expf/exp/pow/tanh);
@@ -188,6 +216,8 @@ TRANSCENDENTAL = {
     "aleveltemp": 1e-5, "alevelthe": 1e-5, "alevelhum": 1e-5, "alevelducting": 1e-5,
     "windCooling": 1e-5, "vesselIcingModStall": 1e-5, "vesselIcingMincog": 1e-4,
     "abshum": 1e-6,  # double exp(): CUDA's is within 1 ulp of a double, the float result differs about once in 2^29
+    # device libm: logf 1 ulp, log10f / expf 2 ulp, powf 4 ulp, double pow / exp 1 ulp of a double
+    "log10Field": 1e-6, "logField": 1e-6, "expField": 1e-6, "powerField": 2e-6, "pow10Field": 1e-6, "snow_in_cm": 1e-6,
 }
 
 

@@ -53,6 +53,28 @@ VARIANTS = {
               dict(compute=6, unit="")],
     "abshum": [dict()],
     "underCooledRain": [dict(), dict(precipMin=0.0, snowRateMax=0.5, tcMax=20.0)],
+    "plevelthe": [dict(compute=1), dict(compute=2), dict(compute=3), dict(compute=1, p=0.0)],
+    "pleveldz2tmean": [dict(compute=1), dict(compute=2), dict(compute=3), dict(compute=4), dict(compute=1, p1=500.0, p2=1000.0), dict(compute=1, p1=500.0, p2=500.0)],
+    "plevelducting": [dict(compute=1), dict(compute=2), dict(compute=3, kinds={1: "rh"}), dict(compute=4, kinds={1: "rh"}), dict(compute=5), dict(compute=1, p=-3.0)],
+    "vectorabs": [dict()],
+    "pressure2FlightLevel": [dict()],
+    "values2classes": [dict(), dict(limits=(260.0, 280.0)), dict(limits=(260.0,)), dict(limits=(250.0, 255.0, 260.0, 265.0, 270.0, 275.0, 280.0, 285.0, 290.0, 295.0))],
+    "minvalueFields": [dict()],
+    "minvalueFieldConst": [dict(), dict(value=1.0e35)],
+    "maxvalueFields": [dict()],
+    "maxvalueFieldConst": [dict(), dict(value=1.0e35)],
+    "absvalueField": [dict()],
+    "log10Field": [dict(), dict(kinds={0: "any"})],
+    "pow10Field": [dict()],
+    "logField": [dict(), dict(kinds={0: "any"})],
+    "expField": [dict()],
+    "powerField": [dict(), dict(value=-0.5), dict(value=2.0), dict(value=1.0e35)],
+    "replaceUndefined": [dict(), dict(value=1.0e35)],
+    "replaceDefined": [dict(), dict(value=1.0e35)],
+    "fieldOPERconstant": [dict(compute=c) for c in (1, 2, 3, 4, 5)] + [dict(compute=4, value=0.0), dict(compute=2, value=1.0e35)],
+    "constantOPERfield": [dict(compute=c) for c in (1, 2, 3, 4, 5)] + [dict(compute=4, value=0.0), dict(compute=2, value=1.0e35)],
+    "sumFields": [dict()],
+    "snow_in_cm": [dict()],
 }
 
 STENCILS = {"ilevelgwind", "relvort", "absvort", "divergence", "advection", "gradient", "shapiro2_filter", "thermalFrontParameter", "jacobian"}
