@@ -188,6 +188,14 @@ bool sumFields(int nx, int ny, const std::vector<float*>& fields, float* fres, V
 bool snow_in_cm(int nx, int ny, const float* snow_water, const float* tk2m, const float* td2m, float* snow_cm, ValuesDefined& fDefined,
                 float undef); /* ref:303 */
 
+/* ---- geostrophic wind and vorticity in a pressure level ---- */
+bool plevelgwind_xcomp(int nx, int ny, const float* z, const float* xmapr, const float* ymapr, const float* fcoriolis, float* ug,
+                       ValuesDefined& fDefined, float undef); /* ref:127 */
+bool plevelgwind_ycomp(int nx, int ny, const float* z, const float* xmapr, const float* ymapr, const float* fcoriolis, float* vg,
+                       ValuesDefined& fDefined, float undef); /* ref:130 */
+bool plevelgvort(int nx, int ny, const float* z, const float* xmapr, const float* ymapr, const float* fcoriolis, float* gvort,
+                 ValuesDefined& fDefined, float undef); /* ref:133 */
+
 /* ---- field arithmetic (compute first) ---- */
 bool fieldOPERfield(int compute, int nx, int ny, const float* field1, const float* field2, float* fres, ValuesDefined& fDefined,
                     float undef); /* ref:278 */

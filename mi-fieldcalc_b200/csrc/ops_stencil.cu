@@ -588,6 +588,91 @@ struct GwindOp
   }
 };
 
+// plevelgwind_xcomp / plevelgwind_ycomp / plevelgvort (FC.cc:638-743): geostrophic wind components
+// and geostrophic vorticity from the height of a pressure surface.  Same tile shape as GwindOp (one staged array, three
+// grid-constant maps); MODE 0 = xcomp, 1 = ycomp, 2 = gvort (which also reads the centre point).
+template <int MODE>
+struct GeoOp
+{
+  static constexpr int NOUT = 1;
+  static constexpr bool TESTS_WHEN_ALL = false;
+  const float *z, *xm, *ym, *fc;
+  float* o;
+  template <bool ALL>
+  struct In
+  {
+    float zd, zl, zc, zr, zu, xm, ym, fc;
+  };
+  __device__ __forceinline__ bool all_defined(int, bool in_all) const { return in_all; }
+  __device__ __forceinline__ GeoOp at(int field, int n) const
+  {
+    GeoOp r = *this;
+    const long long off = (long long)field * n;
+    r.z += off;
+    r.o += off;
+    return r;
+  }
+  __host__ __device__ __forceinline__ float* out(int) const { return o; }
+  template <bool ALL>
+  __device__ __forceinline__ In<ALL> load(int i, int nx) const
+  {
+    In<ALL> r;
+    r.zd = z[i - nx];
+    r.zl = z[i - 1];
+    r.zc = z[i];
+    r.zr = z[i + 1];
+    r.zu = z[i + nx];
+    r.xm = xm[i];
+    r.ym = ym[i];
+    r.fc = fc[i];
+    return r;
+  }
+  static constexpr int HX = 1, EXTRA_FLOATS = 0;
+  static constexpr bool CUSTOM_TILE = false;
+  template <class V, class M>
+  __device__ unsigned tile_custom(const V&, const M&, float*, bool, bool, int, int, int, int, int, int, int, float) const { return 0; }
+  static constexpr int TY = 8, NARR = 1, NMAPS = 3;
+  __host__ __device__ __forceinline__ const float* arr(int) const { return z; }
+  __host__ __device__ static constexpr int halo(int) { return 1; }
+  __host__ __device__ __forceinline__ const float* map(int k) const { return k == 0 ? xm : k == 1 ? ym : fc; }
+  template <bool ALL, class View>
+  __device__ __forceinline__ In<ALL> fetch(const View& t, int r, const float* mp) const
+  {
+    In<ALL> in;
+    in.zd = t.template at<0>(r - 1, 0);
+    in.zl = t.template at<0>(r, -1);
+    in.zc = t.template at<0>(r, 0);
+    in.zr = t.template at<0>(r, 1);
+    in.zu = t.template at<0>(r + 1, 0);
+    in.xm = mp[0];
+    in.ym = mp[1];
+    in.fc = mp[2];
+    return in;
+  }
+  template <bool ALL, bool FAST = false>
+  __device__ __forceinline__ bool eval(const In<ALL>& r, float undef, float* val) const
+  {
+    bool ok = true;
+    if (!ALL)
+      ok = def4(r.zd, r.zl, r.zr, r.zu, undef) && (MODE != 2 || is_def(r.zc, undef));
+    if (!ok)
+      return false;
+    constexpr float g = (float)9.8; // MC.h:46
+    const double f = (double)r.fc;
+    if (MODE == 0)
+      val[0] = (float)(-0.5 * (double)r.ym * (double)(r.zu - r.zd) * (double)g / f); // :662
+    else if (MODE == 1)
+      val[0] = (float)(0.5 * (double)r.xm * (double)(r.zr - r.zl) * (double)g / f); // :694
+    else {
+      constexpr float g4 = (float)((double)g * 4.); // :717
+      const double zc2 = 2. * (double)r.zc;
+      const double d2x = (double)r.zl - zc2 + (double)r.zr, d2y = (double)r.zd - zc2 + (double)r.zu;
+      val[0] = (float)((0.25 * (double)r.xm * (double)r.xm * d2x + 0.25 * (double)r.ym * (double)r.ym * d2y) * (double)g4 / f); // :728-729
+    }
+    return true;
+  }
+};
+
 // thermalFrontParameter, FUSED (FC.cc:2266-2309).  The reference runs gradient(c=3) into a scratch field
 // `absdelt` (with its fillEdges, so absdelt(x, y) = G(clamp(x, 1, nx-2), clamp(y, 1, ny-2)), G = |grad T| at an
 // interior point) and then a second five-point pass over T and absdelt.  Here a tile of T with a halo of
@@ -1219,6 +1304,39 @@ int vortdiv(int nx, int ny, int nfields, const float* u, const float* v, const f
   return run_stencil(call, op, nx, ny, nfields, fDefined, undef, n - 2 * (size_t)nx);
 }
 
+template <int MODE>
+int geostrophic(int nx, int ny, int nfields, const float* z, const float* xmapr, const float* ymapr, const float* fcoriolis, float* out, int* fDefined,
+                float undef)
+{ // FC.cc:638-743.  plevelgwind_ycomp has no `nx < 3 || ny < 3` test in the reference and then reads and writes out of
+  // bounds in fillEdges (undefined behaviour); it is rejected here like its two siblings.
+  if (nx < 3 || ny < 3)
+    return 0;
+  if (!grid_ok(nx, ny, nfields))
+    return -1;
+  const size_t n = (size_t)nx * ny;
+  Call call;
+  GeoOp<MODE> op;
+  op.z = call.in(z, n * nfields);
+  op.xm = call.in(xmapr, n);
+  op.ym = call.in(ymapr, n);
+  op.fc = call.in(fcoriolis, n);
+  op.o = call.out(out, n * nfields);
+  if (MODE != 0)
+    return run_stencil(call, op, nx, ny, nfields, fDefined, undef, n - 2 * (size_t)nx);
+  // plevelgwind_xcomp increments n_undefined for EVERY point of the loop (:664 is outside the else): the flag is
+  // checkDefined(N - 2nx, N - 2nx) = NONE_DEFINED whatever the data
+  const FieldMeta* meta = flags_to_meta(call, fDefined, nfields);
+  unsigned long long* counters = call.counters(nfields);
+  if (!call.ok())
+    return -1;
+  if (!launch_stencil(call, op, nx, ny, nfields, undef, meta, counters, false))
+    return -1;
+  return call.finish([=](const unsigned long long*) {
+    for (int k = 0; k < nfields; ++k)
+      fDefined[k] = NONE_DEFINED;
+  });
+}
+
 } // namespace
 
 extern "C" {
@@ -1359,6 +1477,37 @@ int fcb200_ilevelgwind(int nx, int ny, const float* mpot, const float* xmapr, co
                        int* fDefined, float undef)
 {
   return fcb200_ilevelgwind_batched(nx, ny, 1, mpot, xmapr, ymapr, fcoriolis, ug, vg, fDefined, undef);
+}
+
+int fcb200_plevelgwind_xcomp_batched(int nx, int ny, int nfields, const float* z, const float* xmapr, const float* ymapr, const float* fcoriolis,
+                                     float* ug, int* fDefined, float undef)
+{
+  return geostrophic<0>(nx, ny, nfields, z, xmapr, ymapr, fcoriolis, ug, fDefined, undef);
+}
+int fcb200_plevelgwind_xcomp(int nx, int ny, const float* z, const float* xmapr, const float* ymapr, const float* fcoriolis, float* ug, int* fDefined,
+                             float undef)
+{
+  return geostrophic<0>(nx, ny, 1, z, xmapr, ymapr, fcoriolis, ug, fDefined, undef);
+}
+int fcb200_plevelgwind_ycomp_batched(int nx, int ny, int nfields, const float* z, const float* xmapr, const float* ymapr, const float* fcoriolis,
+                                     float* vg, int* fDefined, float undef)
+{
+  return geostrophic<1>(nx, ny, nfields, z, xmapr, ymapr, fcoriolis, vg, fDefined, undef);
+}
+int fcb200_plevelgwind_ycomp(int nx, int ny, const float* z, const float* xmapr, const float* ymapr, const float* fcoriolis, float* vg, int* fDefined,
+                             float undef)
+{
+  return geostrophic<1>(nx, ny, 1, z, xmapr, ymapr, fcoriolis, vg, fDefined, undef);
+}
+int fcb200_plevelgvort_batched(int nx, int ny, int nfields, const float* z, const float* xmapr, const float* ymapr, const float* fcoriolis,
+                               float* gvort, int* fDefined, float undef)
+{
+  return geostrophic<2>(nx, ny, nfields, z, xmapr, ymapr, fcoriolis, gvort, fDefined, undef);
+}
+int fcb200_plevelgvort(int nx, int ny, const float* z, const float* xmapr, const float* ymapr, const float* fcoriolis, float* gvort, int* fDefined,
+                       float undef)
+{
+  return geostrophic<2>(nx, ny, 1, z, xmapr, ymapr, fcoriolis, gvort, fDefined, undef);
 }
 
 int fcb200_thermalFrontParameter_batched(int nx, int ny, int nfields, const float* t, const float* xmapr, const float* ymapr, float* tfp,

@@ -370,6 +370,27 @@ bool snow_in_cm(int nx, int ny, const float* snow_water, const float* tk2m, cons
   return done(fcb200_snow_in_cm(nx, ny, snow_water, tk2m, td2m, snow_cm, &f, undef), f, fDefined);
 }
 
+bool plevelgwind_xcomp(int nx, int ny, const float* z, const float* xmapr, const float* ymapr, const float* fcoriolis, float* ug, ValuesDefined& fDefined,
+                       float undef)
+{
+  FCB_FLAG;
+  return done(fcb200_plevelgwind_xcomp(nx, ny, z, xmapr, ymapr, fcoriolis, ug, &f, undef), f, fDefined);
+}
+
+bool plevelgwind_ycomp(int nx, int ny, const float* z, const float* xmapr, const float* ymapr, const float* fcoriolis, float* vg, ValuesDefined& fDefined,
+                       float undef)
+{
+  FCB_FLAG;
+  return done(fcb200_plevelgwind_ycomp(nx, ny, z, xmapr, ymapr, fcoriolis, vg, &f, undef), f, fDefined);
+}
+
+bool plevelgvort(int nx, int ny, const float* z, const float* xmapr, const float* ymapr, const float* fcoriolis, float* gvort, ValuesDefined& fDefined,
+                 float undef)
+{
+  FCB_FLAG;
+  return done(fcb200_plevelgvort(nx, ny, z, xmapr, ymapr, fcoriolis, gvort, &f, undef), f, fDefined);
+}
+
 bool windCooling(int nx, int ny, const float* t, const float* u, const float* v, int compute, float* dtcool, ValuesDefined& fDefined, float undef)
 {
   FCB_FLAG;

@@ -2248,3 +2248,76 @@ int fco_snow_in_cm(int nx, int ny, const float* snow_water, const float* tk2m, c
   *fDefined = check_defined(nu, n);
   return 1;
 }
+
+/* ================================================================================================
+ * Geostrophic stencil siblings
+ * ================================================================================================ */
+int fco_plevelgwind_xcomp(int nx, int ny, const float* z, const float* xmapr, const float* ymapr, const float* fcoriolis, float* ug, int* fDefined,
+                          float undef)
+{ /* FC.cc:638-672: n_undefined += 1 for EVERY point (:664) -> the flag is always NONE_DEFINED */
+  (void)xmapr;
+  if (nx < 3 || ny < 3)
+    return 0;
+  const float g = (float)9.8;
+  const int n = nx * ny;
+  const int all = *fDefined == ALL_DEFINED;
+  size_t nundef = 0;
+  for (int i = nx; i < n - nx; ++i) {
+    if (DEF4(z[i - nx], z[i - 1], z[i + 1], z[i + nx]))
+      ug[i] = (float)(-0.5 * ymapr[i] * (z[i + nx] - z[i - nx]) * g / fcoriolis[i]);
+    else
+      ug[i] = undef;
+    nundef += 1;
+  }
+  *fDefined = check_defined(nundef, (size_t)(n - 2 * nx));
+  fill_edges(nx, ny, ug);
+  return 1;
+}
+
+int fco_plevelgwind_ycomp(int nx, int ny, const float* z, const float* xmapr, const float* ymapr, const float* fcoriolis, float* vg, int* fDefined,
+                          float undef)
+{ /* FC.cc:674-706.  The reference has no nx, ny >= 3 test here and then reads and writes out of bounds in
+   * fillEdges (undefined behaviour); this restatement and the product reject such grids like xcomp does. */
+  (void)ymapr;
+  if (nx < 3 || ny < 3)
+    return 0;
+  const float g = (float)9.8;
+  const int n = nx * ny;
+  const int all = *fDefined == ALL_DEFINED;
+  size_t nundef = 0;
+  for (int i = nx; i < n - nx; ++i) {
+    if (DEF4(z[i - nx], z[i - 1], z[i + 1], z[i + nx]))
+      vg[i] = (float)(0.5 * xmapr[i] * (z[i + 1] - z[i - 1]) * g / fcoriolis[i]);
+    else {
+      vg[i] = undef;
+      nundef += 1;
+    }
+  }
+  *fDefined = check_defined(nundef, (size_t)(n - 2 * nx));
+  fill_edges(nx, ny, vg);
+  return 1;
+}
+
+int fco_plevelgvort(int nx, int ny, const float* z, const float* xmapr, const float* ymapr, const float* fcoriolis, float* gvort, int* fDefined,
+                    float undef)
+{ /* FC.cc:708-743 */
+  const float g = (float)9.8;
+  const float g4 = (float)(g * 4.);
+  if (nx < 3 || ny < 3)
+    return 0;
+  const int n = nx * ny;
+  const int all = *fDefined == ALL_DEFINED;
+  size_t nundef = 0;
+  for (int i = nx; i < n - nx; ++i) {
+    if (all || (is_def(z[i - nx], undef) && is_def(z[i - 1], undef) && is_def(z[i], undef) && is_def(z[i + 1], undef) && is_def(z[i + nx], undef)))
+      gvort[i] = (float)((0.25 * xmapr[i] * xmapr[i] * (z[i - 1] - 2. * z[i] + z[i + 1]) + 0.25 * ymapr[i] * ymapr[i] * (z[i - nx] - 2. * z[i] + z[i + nx])) *
+                         g4 / fcoriolis[i]);
+    else {
+      gvort[i] = undef;
+      nundef += 1;
+    }
+  }
+  *fDefined = check_defined(nundef, (size_t)(n - 2 * nx));
+  fill_edges(nx, ny, gvort);
+  return 1;
+}

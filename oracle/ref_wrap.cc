@@ -429,4 +429,26 @@ int fcref_snow_in_cm(int nx, int ny, const float* snow_water, const float* tk2m,
   return fc::snow_in_cm(nx, ny, snow_water, tk2m, td2m, snow_cm, f, undef);
 }
 
+// ---- geostrophic stencil siblings
+int fcref_plevelgwind_xcomp(int nx, int ny, const float* z, const float* xmapr, const float* ymapr, const float* fcoriolis, float* ug, int* fDefined,
+                            float undef)
+{
+  Flag f(fDefined);
+  return fc::plevelgwind_xcomp(nx, ny, z, xmapr, ymapr, fcoriolis, ug, f, undef);
+}
+int fcref_plevelgwind_ycomp(int nx, int ny, const float* z, const float* xmapr, const float* ymapr, const float* fcoriolis, float* vg, int* fDefined,
+                            float undef)
+{
+  if (nx < 3 || ny < 3) // the reference has no such test and runs fillEdges out of bounds: never drive it there
+    return 0;
+  Flag f(fDefined);
+  return fc::plevelgwind_ycomp(nx, ny, z, xmapr, ymapr, fcoriolis, vg, f, undef);
+}
+int fcref_plevelgvort(int nx, int ny, const float* z, const float* xmapr, const float* ymapr, const float* fcoriolis, float* gvort, int* fDefined,
+                      float undef)
+{
+  Flag f(fDefined);
+  return fc::plevelgvort(nx, ny, z, xmapr, ymapr, fcoriolis, gvort, f, undef);
+}
+
 } // extern "C"

@@ -207,6 +207,10 @@ SPECS = {
     "constantOPERfield": [("i", "compute", 1), "nx", "ny", ("f", "value", 2.5), ("in", "any"), "out", "flag", "undef"],
     "sumFields": ["nx", "ny", ("members", "tk"), "out", "flag", "undef"],
     "snow_in_cm": ["nx", "ny", ("in", "snoww"), ("in", "t2m"), ("in", "t2m"), "out", "flag", "undef"],
+    # geostrophic stencil siblings
+    "plevelgwind_xcomp": ["nx", "ny", ("in", "z"), ("in!", "xm"), ("in!", "ym"), ("in!", "fc"), "out", "flag", "undef"],
+    "plevelgwind_ycomp": ["nx", "ny", ("in", "z"), ("in!", "xm"), ("in!", "ym"), ("in!", "fc"), "out", "flag", "undef"],
+    "plevelgvort": ["nx", "ny", ("in", "z"), ("in!", "xm"), ("in!", "ym"), ("in!", "fc"), "out", "flag", "undef"],
 }
 
 # operators whose device result may differ from the CPU by transcendental ulps (powf/expf/exp/pow/tanh);

@@ -75,9 +75,12 @@ VARIANTS = {
     "constantOPERfield": [dict(compute=c) for c in (1, 2, 3, 4, 5)] + [dict(compute=4, value=0.0), dict(compute=2, value=1.0e35)],
     "sumFields": [dict()],
     "snow_in_cm": [dict()],
+    "plevelgwind_xcomp": [dict()],
+    "plevelgwind_ycomp": [dict()],
+    "plevelgvort": [dict()],
 }
 
-STENCILS = {"ilevelgwind", "relvort", "absvort", "divergence", "advection", "gradient", "shapiro2_filter", "thermalFrontParameter", "jacobian"}
+STENCILS = {"plevelgwind_xcomp", "plevelgwind_ycomp", "plevelgvort", "ilevelgwind", "relvort", "absvort", "divergence", "advection", "gradient", "shapiro2_filter", "thermalFrontParameter", "jacobian"}
 ENSEMBLE = {"meanValue", "stddevValue", "extremeValue", "probability"}
 SLOW = {"vesselIcingModStall", "vesselIcingMincog"}
 
