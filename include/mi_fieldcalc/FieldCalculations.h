@@ -195,6 +195,8 @@ bool plevelgwind_ycomp(int nx, int ny, const float* z, const float* xmapr, const
                        ValuesDefined& fDefined, float undef); /* ref:130 */
 bool plevelgvort(int nx, int ny, const float* z, const float* xmapr, const float* ymapr, const float* fcoriolis, float* gvort,
                  ValuesDefined& fDefined, float undef); /* ref:133 */
+bool plevelqvector(int nx, int ny, const float* z, const float* t, const float* xmapr, const float* ymapr, const float* fcoriolis, float p,
+                   int compute, float* qcomp, ValuesDefined& fDefined, float undef); /* ref:122 */
 
 /* ---- field arithmetic (compute first) ---- */
 bool fieldOPERfield(int compute, int nx, int ny, const float* field1, const float* field2, float* fres, ValuesDefined& fDefined,

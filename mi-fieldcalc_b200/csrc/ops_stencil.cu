@@ -18,6 +18,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
+#include <vector>
 
 namespace fcb200 {
 namespace {
@@ -669,6 +670,86 @@ struct GeoOp
       const double d2x = (double)r.zl - zc2 + (double)r.zr, d2y = (double)r.zd - zc2 + (double)r.zu;
       val[0] = (float)((0.25 * (double)r.xm * (double)r.xm * d2x + 0.25 * (double)r.ym * (double)r.ym * d2y) * (double)g4 / f); // :728-729
     }
+    return true;
+  }
+};
+
+// plevelqvector, second pass (FC.cc:566-589): five-point differences of the geostrophic wind components (two scratch
+// fields produced by GeoOp<0> / GeoOp<1>, including their fillEdges) and of the temperature.  The tests are plain
+// `!= undef` comparisons (a NaN passes) and apply whatever the flag says.  COMP 0 = x component, 1 = y component.
+template <int COMP>
+struct QvecOp
+{
+  static constexpr int NOUT = 1;
+  static constexpr bool TESTS_WHEN_ALL = true;
+  const float *ug, *vg, *t, *xm, *ym;
+  float tscale, c;
+  float* o;
+  template <bool ALL>
+  struct In
+  {
+    float ud, ul, ur, uu, vd, vl, vr, vu, td, tl, tr, tu, xm, ym;
+  };
+  __device__ __forceinline__ bool all_defined(int, bool in_all) const { return in_all; }
+  __device__ __forceinline__ QvecOp at(int field, int n) const
+  {
+    QvecOp r = *this;
+    const long long off = (long long)field * n;
+    r.ug += off;
+    r.vg += off;
+    r.t += off;
+    r.o += off;
+    return r;
+  }
+  __host__ __device__ __forceinline__ float* out(int) const { return o; }
+  template <bool ALL>
+  __device__ __forceinline__ In<ALL> load(int i, int nx) const
+  {
+    In<ALL> r;
+    r.ud = ug[i - nx], r.ul = ug[i - 1], r.ur = ug[i + 1], r.uu = ug[i + nx];
+    r.vd = vg[i - nx], r.vl = vg[i - 1], r.vr = vg[i + 1], r.vu = vg[i + nx];
+    r.td = t[i - nx], r.tl = t[i - 1], r.tr = t[i + 1], r.tu = t[i + nx];
+    r.xm = xm[i];
+    r.ym = ym[i];
+    return r;
+  }
+  static constexpr int HX = 1, EXTRA_FLOATS = 0;
+  static constexpr bool CUSTOM_TILE = false;
+  template <class V, class M>
+  __device__ unsigned tile_custom(const V&, const M&, float*, bool, bool, int, int, int, int, int, int, int, float) const { return 0; }
+  static constexpr int TY = 8, NARR = 3, NMAPS = 2;
+  __host__ __device__ __forceinline__ const float* arr(int k) const { return k == 0 ? ug : k == 1 ? vg : t; }
+  __host__ __device__ static constexpr int halo(int) { return 1; }
+  __host__ __device__ __forceinline__ const float* map(int k) const { return k == 0 ? xm : ym; }
+  template <bool ALL, class View>
+  __device__ __forceinline__ In<ALL> fetch(const View& v, int r, const float* m) const
+  {
+    In<ALL> in;
+    in.ud = v.template at<0>(r - 1, 0), in.ul = v.template at<0>(r, -1), in.ur = v.template at<0>(r, 1), in.uu = v.template at<0>(r + 1, 0);
+    in.vd = v.template at<1>(r - 1, 0), in.vl = v.template at<1>(r, -1), in.vr = v.template at<1>(r, 1), in.vu = v.template at<1>(r + 1, 0);
+    in.td = v.template at<2>(r - 1, 0), in.tl = v.template at<2>(r, -1), in.tr = v.template at<2>(r, 1), in.tu = v.template at<2>(r + 1, 0);
+    in.xm = m[0];
+    in.ym = m[1];
+    return in;
+  }
+  template <bool ALL, bool FAST = false>
+  __device__ __forceinline__ bool eval(const In<ALL>& r, float undef, float* val) const
+  {
+    const bool ok = r.ud != undef && r.ul != undef && r.ur != undef && r.uu != undef && r.vd != undef && r.vl != undef && r.vr != undef &&
+                    r.vu != undef && r.td != undef && r.tl != undef && r.tr != undef && r.tu != undef;
+    if (!ok)
+      return false;
+    const float dtdx = (float)(0.5 * (double)r.xm * (double)tscale * (double)(r.tr - r.tl));
+    const float dtdy = (float)(0.5 * (double)r.ym * (double)tscale * (double)(r.tu - r.td));
+    float a, b;
+    if (COMP == 0) {
+      a = (float)(0.5 * (double)r.xm * (double)(r.ur - r.ul)); // dug/dx
+      b = (float)(0.5 * (double)r.xm * (double)(r.vr - r.vl)); // dvg/dx
+    } else {
+      a = (float)(0.5 * (double)r.ym * (double)(r.uu - r.ud)); // dug/dy
+      b = (float)(0.5 * (double)r.ym * (double)(r.vu - r.vd)); // dvg/dy
+    }
+    val[0] = c * (a * dtdx + b * dtdy);
     return true;
   }
 };
@@ -1337,6 +1418,41 @@ int geostrophic(int nx, int ny, int nfields, const float* z, const float* xmapr,
   });
 }
 
+template <int COMP>
+int qvector(int nx, int ny, int nfields, const float* z, const float* t, const float* xmapr, const float* ymapr, const float* fcoriolis, float tscale,
+            float c, float* qcomp, int* fDefined, float undef)
+{ // FC.cc:555-595: plevelgwind_xcomp and _ycomp into two scratch fields, then the second pass.  xcomp is given the caller's
+  // flag and leaves NONE_DEFINED behind (its quirk), so ycomp always runs with every test on.
+  const size_t n = (size_t)nx * ny;
+  Call call;
+  const float* d_z = call.in(z, n * nfields);
+  const float* d_t = call.in(t, n * nfields);
+  const float* d_xm = call.in(xmapr, n);
+  const float* d_ym = call.in(ymapr, n);
+  const float* d_fc = call.in(fcoriolis, n);
+  float* d_out = call.out(qcomp, n * nfields);
+  float* d_ug = static_cast<float*>(call.scratch(sizeof(float) * n * nfields));
+  float* d_vg = static_cast<float*>(call.scratch(sizeof(float) * n * nfields));
+  unsigned long long* counters = call.counters(3 * nfields);
+  if (!call.ok())
+    return -1;
+  const FieldMeta* meta_in = flags_to_meta(call, fDefined, nfields);
+  std::vector<int> none((size_t)nfields, (int)NONE_DEFINED);
+  const FieldMeta* meta_none = flags_to_meta(call, none.data(), nfields);
+  if (!call.ok())
+    return -1;
+  GeoOp<0> gx;
+  gx.z = d_z, gx.xm = d_xm, gx.ym = d_ym, gx.fc = d_fc, gx.o = d_ug;
+  GeoOp<1> gy;
+  gy.z = d_z, gy.xm = d_xm, gy.ym = d_ym, gy.fc = d_fc, gy.o = d_vg;
+  QvecOp<COMP> q;
+  q.ug = d_ug, q.vg = d_vg, q.t = d_t, q.xm = d_xm, q.ym = d_ym, q.tscale = tscale, q.c = c, q.o = d_out;
+  if (!launch_stencil(call, gx, nx, ny, nfields, undef, meta_in, counters) || !launch_stencil(call, gy, nx, ny, nfields, undef, meta_none, counters + nfields) ||
+      !launch_stencil(call, q, nx, ny, nfields, undef, meta_none, counters + 2 * nfields))
+    return -1;
+  return call.finish(flags_from_counters(fDefined, nfields, n - 2 * (size_t)nx, 2 * nfields));
+}
+
 } // namespace
 
 extern "C" {
@@ -1508,6 +1624,33 @@ int fcb200_plevelgvort(int nx, int ny, const float* z, const float* xmapr, const
                        float undef)
 {
   return geostrophic<2>(nx, ny, 1, z, xmapr, ymapr, fcoriolis, gvort, fDefined, undef);
+}
+
+int fcb200_plevelqvector_batched(int nx, int ny, int nfields, const float* z, const float* t, const float* xmapr, const float* ymapr,
+                                 const float* fcoriolis, float p, int compute, float* qcomp, int* fDefined, float undef)
+{ // FC.cc:505-595
+  if (p <= 0.0)
+    return 0;
+  if (nx < 3 || ny < 3)
+    return 0;
+  if (compute < 1 || compute > 4)
+    return 0;
+  if (!grid_ok(nx, ny, nfields))
+    return -1;
+  float tscale = 1.0f;
+  if (compute == 2 || compute == 4) {
+    const float pi = 1004.f * powf(p / 1000.f, 287.f / 1004.f); // :537 spells the Exner function out with p / p0
+    tscale = pi / 1004.f;
+  }
+  const float c = (float)((double)(-287.f) / ((double)p * 100.));
+  if (compute < 3)
+    return qvector<0>(nx, ny, nfields, z, t, xmapr, ymapr, fcoriolis, tscale, c, qcomp, fDefined, undef);
+  return qvector<1>(nx, ny, nfields, z, t, xmapr, ymapr, fcoriolis, tscale, c, qcomp, fDefined, undef);
+}
+int fcb200_plevelqvector(int nx, int ny, const float* z, const float* t, const float* xmapr, const float* ymapr, const float* fcoriolis, float p,
+                         int compute, float* qcomp, int* fDefined, float undef)
+{
+  return fcb200_plevelqvector_batched(nx, ny, 1, z, t, xmapr, ymapr, fcoriolis, p, compute, qcomp, fDefined, undef);
 }
 
 int fcb200_thermalFrontParameter_batched(int nx, int ny, int nfields, const float* t, const float* xmapr, const float* ymapr, float* tfp,

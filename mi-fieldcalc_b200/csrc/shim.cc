@@ -391,6 +391,13 @@ bool plevelgvort(int nx, int ny, const float* z, const float* xmapr, const float
   return done(fcb200_plevelgvort(nx, ny, z, xmapr, ymapr, fcoriolis, gvort, &f, undef), f, fDefined);
 }
 
+bool plevelqvector(int nx, int ny, const float* z, const float* t, const float* xmapr, const float* ymapr, const float* fcoriolis, float p, int compute,
+                   float* qcomp, ValuesDefined& fDefined, float undef)
+{
+  FCB_FLAG;
+  return done(fcb200_plevelqvector(nx, ny, z, t, xmapr, ymapr, fcoriolis, p, compute, qcomp, &f, undef), f, fDefined);
+}
+
 bool windCooling(int nx, int ny, const float* t, const float* u, const float* v, int compute, float* dtcool, ValuesDefined& fDefined, float undef)
 {
   FCB_FLAG;

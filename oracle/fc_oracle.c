@@ -2321,3 +2321,62 @@ int fco_plevelgvort(int nx, int ny, const float* z, const float* xmapr, const fl
   fill_edges(nx, ny, gvort);
   return 1;
 }
+
+int fco_plevelqvector(int nx, int ny, const float* z, const float* t, const float* xmapr, const float* ymapr, const float* fcoriolis, float p, int compute,
+                      float* qcomp, int* fDefined, float undef)
+{ /* FC.cc:505-595 */
+  if (p <= 0.0)
+    return 0;
+  if (nx < 3 || ny < 3)
+    return 0;
+  float tscale;
+  switch (compute) {
+  case 1:
+  case 3:
+    tscale = 1.0f;
+    break;
+  case 2:
+  case 4: {
+    const float pi = K_CP * powf(p / K_P0, K_R / K_CP);
+    tscale = pi / K_CP;
+    break;
+  }
+  default:
+    return 0;
+  }
+  const int n = nx * ny;
+  float* ug = (float*)malloc(sizeof(float) * (size_t)n);
+  float* vg = (float*)malloc(sizeof(float) * (size_t)n);
+  if (!fco_plevelgwind_xcomp(nx, ny, z, xmapr, ymapr, fcoriolis, ug, fDefined, undef) ||
+      !fco_plevelgwind_ycomp(nx, ny, z, xmapr, ymapr, fcoriolis, vg, fDefined, undef)) {
+    free(ug);
+    free(vg);
+    return 0;
+  }
+  const float c = (float)(-K_R / (p * 100.));
+  size_t nundef = 0;
+  for (int i = nx; i < n - nx; ++i) {
+    if (ug[i - nx] != undef && ug[i - 1] != undef && ug[i + 1] != undef && ug[i + nx] != undef && vg[i - nx] != undef && vg[i - 1] != undef &&
+        vg[i + 1] != undef && vg[i + nx] != undef && t[i - nx] != undef && t[i - 1] != undef && t[i + 1] != undef && t[i + nx] != undef) {
+      const float dtdx = (float)(0.5 * xmapr[i] * tscale * (t[i + 1] - t[i - 1]));
+      const float dtdy = (float)(0.5 * ymapr[i] * tscale * (t[i + nx] - t[i - nx]));
+      if (compute < 3) {
+        const float dugdx = (float)(0.5 * xmapr[i] * (ug[i + 1] - ug[i - 1]));
+        const float dvgdx = (float)(0.5 * xmapr[i] * (vg[i + 1] - vg[i - 1]));
+        qcomp[i] = c * (dugdx * dtdx + dvgdx * dtdy);
+      } else {
+        const float dugdy = (float)(0.5 * ymapr[i] * (ug[i + nx] - ug[i - nx]));
+        const float dvgdy = (float)(0.5 * ymapr[i] * (vg[i + nx] - vg[i - nx]));
+        qcomp[i] = c * (dugdy * dtdx + dvgdy * dtdy);
+      }
+    } else {
+      qcomp[i] = undef;
+      nundef += 1;
+    }
+  }
+  *fDefined = check_defined(nundef, (size_t)(n - 2 * nx));
+  fill_edges(nx, ny, qcomp);
+  free(ug);
+  free(vg);
+  return 1;
+}

@@ -451,4 +451,11 @@ int fcref_plevelgvort(int nx, int ny, const float* z, const float* xmapr, const 
   return fc::plevelgvort(nx, ny, z, xmapr, ymapr, fcoriolis, gvort, f, undef);
 }
 
+int fcref_plevelqvector(int nx, int ny, const float* z, const float* t, const float* xmapr, const float* ymapr, const float* fcoriolis, float p, int compute,
+                        float* qcomp, int* fDefined, float undef)
+{
+  Flag f(fDefined);
+  return fc::plevelqvector(nx, ny, z, t, xmapr, ymapr, fcoriolis, p, compute, qcomp, f, undef);
+}
+
 } // extern "C"

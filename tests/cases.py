@@ -211,6 +211,8 @@ SPECS = {
     "plevelgwind_xcomp": ["nx", "ny", ("in", "z"), ("in!", "xm"), ("in!", "ym"), ("in!", "fc"), "out", "flag", "undef"],
     "plevelgwind_ycomp": ["nx", "ny", ("in", "z"), ("in!", "xm"), ("in!", "ym"), ("in!", "fc"), "out", "flag", "undef"],
     "plevelgvort": ["nx", "ny", ("in", "z"), ("in!", "xm"), ("in!", "ym"), ("in!", "fc"), "out", "flag", "undef"],
+    "plevelqvector": ["nx", "ny", ("in", "z"), ("in", "tk"), ("in!", "xm"), ("in!", "ym"), ("in!", "fc"), ("f", "p", 700.0), ("i", "compute", 1), "out",
+                      "flag", "undef"],
 }
 
 # operators whose device result may differ from the CPU by transcendental ulps (powf/expf/exp/pow/tanh);

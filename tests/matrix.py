@@ -78,9 +78,10 @@ VARIANTS = {
     "plevelgwind_xcomp": [dict()],
     "plevelgwind_ycomp": [dict()],
     "plevelgvort": [dict()],
+    "plevelqvector": [dict(compute=c) for c in (1, 2, 3, 4, 5)] + [dict(compute=1, p=0.0)],
 }
 
-STENCILS = {"plevelgwind_xcomp", "plevelgwind_ycomp", "plevelgvort", "ilevelgwind", "relvort", "absvort", "divergence", "advection", "gradient", "shapiro2_filter", "thermalFrontParameter", "jacobian"}
+STENCILS = {"plevelqvector", "plevelgwind_xcomp", "plevelgwind_ycomp", "plevelgvort", "ilevelgwind", "relvort", "absvort", "divergence", "advection", "gradient", "shapiro2_filter", "thermalFrontParameter", "jacobian"}
 ENSEMBLE = {"meanValue", "stddevValue", "extremeValue", "probability"}
 SLOW = {"vesselIcingModStall", "vesselIcingMincog"}
 
