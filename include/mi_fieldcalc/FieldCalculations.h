@@ -211,6 +211,12 @@ bool extremeValue(int compute, int nx, int ny, const std::vector<float*>& fields
 bool probability(int compute, int nx, int ny, const std::vector<float*>& fields, const std::vector<ValuesDefined>& fDefinedIn,
                  const std::vector<float>& limits, float* fres, ValuesDefined& fDefinedOut, float undef); /* ref:294 */
 
+/* ---- neighbourhood statistics ---- */
+bool neighbourProbFunctions(int nx, int ny, const float* field, const std::vector<float>& constants, int compute, float* fres,
+                            ValuesDefined& fDefined, float undef); /* ref:297 */
+bool neighbourFunctions(int nx, int ny, const float* field, const std::vector<float>& constants, int compute, float* fres, ValuesDefined& fDefined,
+                        float undef); /* ref:300 */
+
 } // namespace fieldcalc
 } // namespace miutil
 

@@ -398,6 +398,20 @@ bool plevelqvector(int nx, int ny, const float* z, const float* t, const float* 
   return done(fcb200_plevelqvector(nx, ny, z, t, xmapr, ymapr, fcoriolis, p, compute, qcomp, &f, undef), f, fDefined);
 }
 
+bool neighbourProbFunctions(int nx, int ny, const float* field, const std::vector<float>& constants, int compute, float* fres, ValuesDefined& fDefined,
+                            float undef)
+{
+  FCB_FLAG;
+  return done(fcb200_neighbourProbFunctions(nx, ny, field, constants.data(), (int)constants.size(), compute, fres, &f, undef), f, fDefined);
+}
+
+bool neighbourFunctions(int nx, int ny, const float* field, const std::vector<float>& constants, int compute, float* fres, ValuesDefined& fDefined,
+                        float undef)
+{
+  FCB_FLAG;
+  return done(fcb200_neighbourFunctions(nx, ny, field, constants.data(), (int)constants.size(), compute, fres, &f, undef), f, fDefined);
+}
+
 bool windCooling(int nx, int ny, const float* t, const float* u, const float* v, int compute, float* dtcool, ValuesDefined& fDefined, float undef)
 {
   FCB_FLAG;

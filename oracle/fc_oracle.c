@@ -2380,3 +2380,148 @@ int fco_plevelqvector(int nx, int ny, const float* z, const float* t, const floa
   free(vg);
   return 1;
 }
+
+/* ================================================================================================
+ * Neighbourhood functions
+ * ================================================================================================ */
+static void neighbour_border_undef(int nx, int ny, int range, float* fres, float undef)
+{ /* FC.cc:2929-2949 / 2989-3008 */
+  for (int j = 0; j < range; j++)
+    for (int i = 0; i < nx; i++)
+      fres[i + j * nx] = undef;
+  for (int j = range; j < ny - range; j++) {
+    for (int i = 0; i < range; i++)
+      fres[i + j * nx] = undef;
+    for (int i = nx - range; i < nx; i++)
+      fres[i + j * nx] = undef;
+  }
+  for (int j = ny - range; j < ny; j++)
+    for (int i = 0; i < nx; i++)
+      fres[i + j * nx] = undef;
+}
+
+int fco_neighbourProbFunctions(int nx, int ny, const float* field, const float* constants, int nconstants, int compute, float* fres, int* fDefined,
+                               float undef)
+{ /* FC.cc:2862-2953.  Outside the reference's defined behaviour (it indexes out of bounds): range < 0 or
+   * range > min(nx, ny) -- rejected here and in the product. */
+  if (*fDefined != ALL_DEFINED)
+    return 0;
+  if (nconstants < 2)
+    return 0;
+  const int fsize = nx * ny;
+  const int limit = (int)constants[0];
+  const int range = (int)constants[1];
+  if (range < 0 || range > nx || range > ny)
+    return 0;
+  if (compute == 5) {
+    for (int i = 0; i < fsize; i++)
+      fres[i] = field[i] > limit ? 1 : 0;
+  } else if (compute == 6) {
+    for (int i = 0; i < fsize; i++)
+      fres[i] = field[i] < limit ? 1 : 0;
+  }
+  if (range == 0)
+    return 1;
+  float* tmp = (float*)malloc(sizeof(float) * (size_t)fsize);
+  for (int i = 0; i < nx; i++) {
+    tmp[i] = fres[i];
+    for (int j = 1; j < ny; j++)
+      tmp[i + j * nx] = fres[i + j * nx] + tmp[i + (j - 1) * nx];
+  }
+  for (int j = 0; j < ny; j++)
+    for (int i = 1; i < nx; i++)
+      tmp[i + j * nx] += tmp[(i - 1) + j * nx];
+  const int N = (2 * range + 1) * (2 * range + 1);
+  for (int i = range; i < nx - range; i++) {
+    const int imax = i + range;
+    for (int j = range; j < ny - range; j++) {
+      const int jmax = j + range;
+      fres[i + j * nx] = tmp[imax + jmax * nx];
+      if (i > range) {
+        fres[i + j * nx] -= tmp[i - range - 1 + jmax * nx];
+        if (j > range)
+          fres[i + j * nx] += tmp[i - range - 1 + (j - range - 1) * nx] - tmp[imax + (j - range - 1) * nx];
+      } else if (j > range) {
+        fres[i + j * nx] -= tmp[imax + (j - range - 1) * nx];
+      }
+      fres[i + j * nx] /= N;
+    }
+  }
+  free(tmp);
+  *fDefined = SOME_DEFINED;
+  neighbour_border_undef(nx, ny, range, fres, undef);
+  return 1;
+}
+
+static int cmp_float(const void* a, const void* b)
+{
+  const float x = *(const float*)a, y = *(const float*)b;
+  return (x > y) - (x < y);
+}
+
+int fco_neighbourFunctions(int nx, int ny, const float* field, const float* constants, int nconstants, int compute, float* fres, int* fDefined,
+                           float undef)
+{ /* FC.cc:2955-3061.  Outside the reference's defined behaviour: step / 2 > range (it paints outside the rows)
+   * and a percentile index beyond the window (it reads past its vector) -- rejected here and in the product. */
+  if (*fDefined != ALL_DEFINED)
+    return 0;
+  if (nconstants < 1 || (nconstants < 2 && compute > 3))
+    return 0;
+  int range = 3, step = 3, limit = 0;
+  if (compute < 4) {
+    range = (int)constants[0];
+    if (nconstants == 2)
+      step = (int)constants[1];
+  } else {
+    limit = (int)constants[0];
+    range = (int)constants[1];
+    if (nconstants == 3)
+      step = (int)constants[2];
+  }
+  if (range > nx || range > ny || range < 1)
+    return 0;
+  if (step < 1)
+    return 0;
+  const float ngridp = (float)((2 * range + 1) * (2 * range + 1));
+  const int ii = (int)(ngridp * limit / 100);
+  if (step / 2 > range)
+    return 0;
+  if (compute == 4 && (ii < 0 || ii >= (2 * range + 1) * (2 * range + 1)))
+    return 0;
+  *fDefined = SOME_DEFINED;
+  neighbour_border_undef(nx, ny, range, fres, undef);
+  const int nwin = (2 * range + 1) * (2 * range + 1);
+  float* values = (float*)malloc(sizeof(float) * (size_t)nwin);
+  for (int j = range; j < ny - range; j += step) {
+    for (int i = range; i < nx - range; i += step) {
+      int nv = 0;
+      float value = 0.0f;
+      if (compute == 2 || compute == 3)
+        value = field[(i - range) + (j - range) * nx];
+      for (int k = j - range; k < j + range + 1; k++) {
+        for (int jj = i - range; jj < i + range + 1; jj++) {
+          const float thisvalue = field[jj + k * nx];
+          if (compute == 1)
+            value += thisvalue;
+          if ((compute == 2 && thisvalue > value) || (compute == 3 && thisvalue < value))
+            value = thisvalue;
+          else if (compute == 4)
+            values[nv++] = thisvalue;
+          if ((compute == 5 && thisvalue > limit) || (compute == 6 && thisvalue < limit))
+            value++;
+        }
+      }
+      if (compute == 4) {
+        qsort(values, (size_t)nv, sizeof(float), cmp_float);
+        value = values[ii];
+      }
+      if (compute == 1 || compute > 4)
+        value /= ngridp;
+      for (int l = j - (step - 1) / 2; l < j + step / 2 + 1; l++)
+        for (int k = i - (step - 1) / 2; k < i + step / 2 + 1; k++)
+          fres[k + l * nx] = value;
+    }
+  }
+  free(values);
+  return 1;
+}

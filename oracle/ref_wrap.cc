@@ -458,4 +458,41 @@ int fcref_plevelqvector(int nx, int ny, const float* z, const float* t, const fl
   return fc::plevelqvector(nx, ny, z, t, xmapr, ymapr, fcoriolis, p, compute, qcomp, f, undef);
 }
 
+// ---- neighbourhood functions; parameter combinations for which the reference indexes out of
+// bounds are never driven into it (same rejections as the restatement)
+int fcref_neighbourProbFunctions(int nx, int ny, const float* field, const float* constants, int nconstants, int compute, float* fres, int* fDefined,
+                                 float undef)
+{
+  if (nconstants >= 2) {
+    const int range = (int)constants[1];
+    if (range < 0 || range > nx || range > ny)
+      return 0;
+  }
+  Flag f(fDefined);
+  return fc::neighbourProbFunctions(nx, ny, field, std::vector<float>(constants, constants + (nconstants > 0 ? nconstants : 0)), compute, fres, f, undef);
+}
+int fcref_neighbourFunctions(int nx, int ny, const float* field, const float* constants, int nconstants, int compute, float* fres, int* fDefined,
+                             float undef)
+{
+  if (!(nconstants < 1 || (nconstants < 2 && compute > 3))) {
+    int range = 3, step = 3, limit = 0;
+    if (compute < 4) {
+      range = (int)constants[0];
+      if (nconstants == 2)
+        step = (int)constants[1];
+    } else {
+      limit = (int)constants[0];
+      range = (int)constants[1];
+      if (nconstants == 3)
+        step = (int)constants[2];
+    }
+    const int nwin = (2 * range + 1) * (2 * range + 1);
+    const int ii = (int)((float)nwin * limit / 100);
+    if (range >= 1 && step >= 1 && (step / 2 > range || (compute == 4 && (ii < 0 || ii >= nwin))))
+      return 0;
+  }
+  Flag f(fDefined);
+  return fc::neighbourFunctions(nx, ny, field, std::vector<float>(constants, constants + (nconstants > 0 ? nconstants : 0)), compute, fres, f, undef);
+}
+
 } // extern "C"

@@ -211,6 +211,9 @@ SPECS = {
     "plevelgwind_xcomp": ["nx", "ny", ("in", "z"), ("in!", "xm"), ("in!", "ym"), ("in!", "fc"), "out", "flag", "undef"],
     "plevelgwind_ycomp": ["nx", "ny", ("in", "z"), ("in!", "xm"), ("in!", "ym"), ("in!", "fc"), "out", "flag", "undef"],
     "plevelgvort": ["nx", "ny", ("in", "z"), ("in!", "xm"), ("in!", "ym"), ("in!", "fc"), "out", "flag", "undef"],
+    # neighbourhood functions; the field is never masked (they require ALL_DEFINED and sort raw values)
+    "neighbourProbFunctions": ["nx", "ny", ("in!", "tk"), ("limits", (270.0, 2.0)), ("i", "compute", 5), "out", "flag", "undef"],
+    "neighbourFunctions": ["nx", "ny", ("in!", "tk"), ("limits", (2.0, 2.0)), ("i", "compute", 1), "out", "flag", "undef"],
     "plevelqvector": ["nx", "ny", ("in", "z"), ("in", "tk"), ("in!", "xm"), ("in!", "ym"), ("in!", "fc"), ("f", "p", 700.0), ("i", "compute", 1), "out",
                       "flag", "undef"],
 }

@@ -79,6 +79,14 @@ VARIANTS = {
     "plevelgwind_ycomp": [dict()],
     "plevelgvort": [dict()],
     "plevelqvector": [dict(compute=c) for c in (1, 2, 3, 4, 5)] + [dict(compute=1, p=0.0)],
+    "neighbourProbFunctions": [dict(compute=5), dict(compute=6), dict(compute=5, limits=(270.0, 0.0)), dict(compute=6, limits=(262.0, 1.0)),
+                               dict(compute=5, limits=(270.0, 3.0)), dict(compute=1, limits=(270.0, 1.0)), dict(compute=5, limits=(270.0,)),
+                               dict(compute=5, limits=(270.0, 50.0))],
+    "neighbourFunctions": [dict(compute=1), dict(compute=2), dict(compute=3), dict(compute=1, limits=(1.0,)), dict(compute=2, limits=(3.0, 1.0)),
+                           dict(compute=4, limits=(90.0, 2.0, 1.0)), dict(compute=4, limits=(50.0, 1.0)), dict(compute=4, limits=(0.0, 1.0, 2.0)),
+                           dict(compute=5, limits=(270.0, 2.0, 1.0)), dict(compute=6, limits=(270.0, 1.0, 3.0)), dict(compute=4, limits=(100.0, 1.0)),
+                           dict(compute=1, limits=(1.0, 4.0)), dict(compute=1, limits=(0.0,)), dict(compute=4, limits=(50.0,)), dict(compute=7, limits=(1.0, 1.0)),
+                           dict(compute=2, limits=(40.0, 1.0))],
 }
 
 STENCILS = {"plevelqvector", "plevelgwind_xcomp", "plevelgwind_ycomp", "plevelgvort", "ilevelgwind", "relvort", "absvort", "divergence", "advection", "gradient", "shapiro2_filter", "thermalFrontParameter", "jacobian"}

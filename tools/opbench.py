@@ -87,7 +87,7 @@ def main():
             nx, ny = grid
             rng = {"t": (215, 305), "q": (1e-6, 2e-2), "p": (300, 1040), "w": (-30, 30), "any": (-50, 50), "tc": (-25, 5), "sst": (-1, 8), "sal": (30, 35),
                    "aice": (0, 0.6), "wave": (0, 8), "rh01": (0.4, 1), "pmsl": (960, 1030), "pw": (3, 12), "depth": (20, 3000), "rh": (1, 100), "z": (100, 5900),
-                   "precip": (0, 5), "snow": (0, 0.6)}
+                   "precip": (0, 5), "snow": (0, 0.6), "pos": (0.05, 900), "snoww": (-0.5, 20), "t2m": (255, 278)}
             fields = [rnd(batch(grid, nf), *rng[k]) for k in kinds]
             return list(lead) + [nx, ny, nf] + fields + list(scalars_before_out) + [torch.empty(batch(grid, nf), device=dev), np.full(nf, flag_in, np.int32), UNDEF]
         return build
@@ -122,6 +122,23 @@ def main():
         nx, ny = grid
         return [nx, ny, nf, rnd(batch(grid, nf), 215, 305), rnd(batch(grid, nf), 1e-6, 2e-2), rnd(batch(grid, nf), 300, 1040), "celsius"] + \
                [torch.empty(batch(grid, nf), device=dev) for _ in range(4)] + [np.full(nf, flag_in, np.int32), np.zeros(4 * nf, np.int32), UNDEF]
+
+    def b_classes(grid, nf):
+        nx, ny = grid
+        lim = np.array([230.0, 250.0, 262.5, 270.0, 280.0, 300.0], np.float32)
+        return [nx, ny, nf, rnd(batch(grid, nf), 215, 305), torch.empty(batch(grid, nf), device=dev), lim, len(lim), np.full(nf, flag_in, np.int32), UNDEF]
+
+    def b_geo(grid, nf):
+        nx, ny = grid
+        z = rnd(batch(grid, nf), 4800, 5900)
+        xm, ym, fc = rnd((ny, nx), 1.9e-4, 2.1e-4, False), rnd((ny, nx), 1.9e-4, 2.1e-4, False), rnd((ny, nx), 1.1e-4, 1.4e-4, False)
+        return [nx, ny, nf, z, xm, ym, fc, torch.empty(batch(grid, nf), device=dev), np.full(nf, flag_in, np.int32), UNDEF]
+
+    def b_qvec(grid, nf):
+        nx, ny = grid
+        z, t = rnd(batch(grid, nf), 4800, 5900), rnd(batch(grid, nf), 215, 305)
+        xm, ym, fc = rnd((ny, nx), 1.9e-4, 2.1e-4, False), rnd((ny, nx), 1.9e-4, 2.1e-4, False), rnd((ny, nx), 1.1e-4, 1.4e-4, False)
+        return [nx, ny, nf, z, t, xm, ym, fc, 700.0, 1, torch.empty(batch(grid, nf), device=dev), np.full(nf, flag_in, np.int32), UNDEF]
 
     icing6 = ["tc", "sst", "w", "w", "sal", "aice"]
     icing11 = ["sal", "wave", "w", "w", "tc", "rh01", "sst", "pmsl", "pw", "aice", "depth"]
@@ -166,6 +183,18 @@ def main():
         "cvhum_c1": ("cvhum_batched", MEPS, 96, 12, b_ew(["t", "rh"], ("kelvin", 1))),
         "abshum": ("abshum_batched", MEPS, 96, 12, b_ew(["t", "rh"])),
         "underCooledRain": ("underCooledRain_batched", MEPS, 64, 16, b_ew(["precip", "snow", "t"], (0.5, 0.1, 0.0))),
+        # field arithmetic, element functions, p-level siblings (a sample of the 22 operators of ops_arith.cu)
+        "plevelthe_c1": ("plevelthe_batched", MEPS, 96, 12, b_ew(["t", "rh"], (850.0, 1))),
+        "vectorabs": ("vectorabs_batched", MEPS, 96, 12, b_ew(["w", "w"])),
+        "fieldOPERconstant_mul": ("fieldOPERconstant_batched", MEPS, 128, 8, b_ew(["any"], (2.5,), lead=(3,))),
+        "logField": ("logField_batched", MEPS, 128, 8, b_ew(["pos"])),
+        "pressure2FlightLevel": ("pressure2FlightLevel_batched", MEPS, 128, 8, b_ew(["p"])),
+        "values2classes": ("values2classes_batched", MEPS, 128, 8, b_classes),
+        "snow_in_cm": ("snow_in_cm_batched", MEPS, 64, 16, b_ew(["snoww", "t2m", "t2m"])),
+        # geostrophic stencil siblings (maps amortised over the batch)
+        "plevelgwind_ycomp": ("plevelgwind_ycomp_batched", MEPS, 64, 8, b_geo),
+        "plevelgvort": ("plevelgvort_batched", MEPS, 64, 8, b_geo),
+        "plevelqvector_c1": ("plevelqvector_batched", MEPS, 48, 12, b_qvec),
         # ensemble, 30 members: bytes per OUTPUT point = 4*(M+1)
         "meanValue": ("meanValue_batched", MEPS, 8, 124, b_ens("meanValue")),
         "stddevValue": ("stddevValue_batched", MEPS, 8, 124, b_ens("stddevValue")),
