@@ -140,6 +140,13 @@ def main():
         xm, ym, fc = rnd((ny, nx), 1.9e-4, 2.1e-4, False), rnd((ny, nx), 1.9e-4, 2.1e-4, False), rnd((ny, nx), 1.1e-4, 1.4e-4, False)
         return [nx, ny, nf, z, t, xm, ym, fc, 700.0, 1, torch.empty(batch(grid, nf), device=dev), np.full(nf, flag_in, np.int32), UNDEF]
 
+    def b_neigh(constants, compute):
+        def build(grid, nf):
+            nx, ny = grid
+            c = np.array(constants, np.float32)
+            return [nx, ny, nf, rnd(batch(grid, nf), 250, 300, False), c, len(c), compute, torch.zeros(batch(grid, nf), device=dev), np.zeros(nf, np.int32), UNDEF]
+        return build
+
     icing6 = ["tc", "sst", "w", "w", "sal", "aice"]
     icing11 = ["sal", "wave", "w", "w", "tc", "rh01", "sst", "pmsl", "pw", "aice", "depth"]
     OPS = {
@@ -195,6 +202,10 @@ def main():
         "plevelgwind_ycomp": ("plevelgwind_ycomp_batched", MEPS, 64, 8, b_geo),
         "plevelgvort": ("plevelgvort_batched", MEPS, 64, 8, b_geo),
         "plevelqvector_c1": ("plevelqvector_batched", MEPS, 48, 12, b_qvec),
+        # neighbourhood functions (field by field; they require ALL_DEFINED input: skipped in --mask runs)
+        "neighbourProb_r3": ("neighbourProbFunctions_batched", MEPS, 16, 8, b_neigh((275.0, 3.0), 5)),
+        "neighbourFunctions_mean_r3s3": ("neighbourFunctions_batched", MEPS, 16, 8, b_neigh((3.0, 3.0), 1)),
+        "neighbourFunctions_pct90_r3s3": ("neighbourFunctions_batched", MEPS, 16, 8, b_neigh((90.0, 3.0, 3.0), 4)),
         # ensemble, 30 members: bytes per OUTPUT point = 4*(M+1)
         "meanValue": ("meanValue_batched", MEPS, 8, 124, b_ens("meanValue")),
         "stddevValue": ("stddevValue_batched", MEPS, 8, 124, b_ens("stddevValue")),
@@ -205,13 +216,20 @@ def main():
     results = []
     print("%-24s %-10s %7s %9s %9s %8s %6s" % ("operator", "grid", "fields", "ms", "Gpt/s", "GB/s", "frac"))
     for name in wanted:
+        if args.mask > 0 and name.startswith("neighbour"):
+            continue
         call, grid, nf, bpp, build = OPS[name]
         sets = [build(grid, nf), build(grid, nf)]
         pts = grid[0] * grid[1] * nf
+        saved = [[a.copy() if isinstance(a, np.ndarray) and a.dtype == np.int32 else None for a in s] for s in sets]
         for s in sets:  # warm-up (also checks the call is accepted)
             r = gpu.call(call, *s)
             assert r == 1, (name, r)
         torch.cuda.synchronize()
+        for s, sv in zip(sets, saved):  # the timed (deferred) calls see the same input flags as the warm-up did
+            for a, b in zip(s, sv):
+                if b is not None:
+                    a[...] = b
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         gpu.begin_deferred()
         e0.record(stream)
