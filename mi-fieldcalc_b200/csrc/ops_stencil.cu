@@ -589,6 +589,79 @@ struct GwindOp
   }
 };
 
+// thermalFrontParameter, second pass of the UNFUSED form (FC.cc:2286-2303): |grad T| comes from a scratch field written by
+// GradientOp<3> (with its fillEdges).  all2 -- this pass's allDefined -- is pass 1's OUTPUT flag, i.e. "pass 1 counted
+// nothing": read from pass 1's device counter, no host round trip.
+struct TfpPass2Op
+{
+  static constexpr int NOUT = 1;
+  static constexpr bool TESTS_WHEN_ALL = true;
+  const float *tx, *ad, *xm, *ym;
+  const unsigned long long* pass1_undef; // per field
+  float* o;
+  template <bool ALL>
+  struct In
+  {
+    float td, tl, tr, tu, adn, al, ac, ar, au, xm, ym;
+  };
+  __device__ __forceinline__ bool all_defined(int field, bool) const { return pass1_undef[field] == 0; }
+  __device__ __forceinline__ TfpPass2Op at(int field, int n) const
+  {
+    TfpPass2Op r = *this;
+    const long long off = (long long)field * n;
+    r.tx += off;
+    r.ad += off;
+    r.o += off;
+    return r;
+  }
+  __host__ __device__ __forceinline__ float* out(int) const { return o; }
+  template <bool ALL>
+  __device__ __forceinline__ In<ALL> load(int i, int nx) const
+  {
+    In<ALL> r;
+    r.td = tx[i - nx], r.tl = tx[i - 1], r.tr = tx[i + 1], r.tu = tx[i + nx];
+    r.adn = ad[i - nx], r.al = ad[i - 1], r.ac = ad[i], r.ar = ad[i + 1], r.au = ad[i + nx];
+    r.xm = xm[i];
+    r.ym = ym[i];
+    return r;
+  }
+  static constexpr int HX = 1, EXTRA_FLOATS = 0;
+  static constexpr bool CUSTOM_TILE = false;
+  template <class V, class M>
+  __device__ unsigned tile_custom(const V&, const M&, float*, bool, bool, int, int, int, int, int, int, int, float) const { return 0; }
+  static constexpr int TY = 8, NARR = 2, NMAPS = 2;
+  __host__ __device__ __forceinline__ const float* arr(int k) const { return k == 0 ? tx : ad; }
+  __host__ __device__ static constexpr int halo(int) { return 1; }
+  __host__ __device__ __forceinline__ const float* map(int k) const { return k == 0 ? xm : ym; }
+  template <bool ALL, class View>
+  __device__ __forceinline__ In<ALL> fetch(const View& v, int r, const float* m) const
+  {
+    In<ALL> in;
+    in.td = v.template at<0>(r - 1, 0), in.tl = v.template at<0>(r, -1), in.tr = v.template at<0>(r, 1), in.tu = v.template at<0>(r + 1, 0);
+    in.adn = v.template at<1>(r - 1, 0), in.al = v.template at<1>(r, -1), in.ac = v.template at<1>(r, 0), in.ar = v.template at<1>(r, 1),
+    in.au = v.template at<1>(r + 1, 0);
+    in.xm = m[0];
+    in.ym = m[1];
+    return in;
+  }
+  template <bool ALL, bool FAST = false>
+  __device__ __forceinline__ bool eval(const In<ALL>& r, float undef, float* val) const
+  {
+    bool ok = true;
+    if (!ALL)
+      ok = def4(r.td, r.tl, r.tr, r.tu, undef) && def4(r.adn, r.al, r.ar, r.au, undef) && is_def(r.ac, undef);
+    ok = ok && (r.ac != 0); // tested even when allDefined (FC.cc:2292)
+    if (!ok)
+      return false;
+    const float dadx = half_map_diff_f<FAST>(r.xm, r.ar, r.al);
+    const float dady = half_map_diff_f<FAST>(r.ym, r.au, r.adn);
+    const float dtdxa = (float)(half_map_diff(r.xm, r.tr, r.tl) / (double)r.ac);
+    const float dtdya = (float)(half_map_diff(r.ym, r.tu, r.td) / (double)r.ac);
+    val[0] = -(dadx * dtdxa + dady * dtdya);
+    return true;
+  }
+};
+
 // plevelgwind_xcomp / plevelgwind_ycomp / plevelgvort (FC.cc:638-743): geostrophic wind components
 // and geostrophic vorticity from the height of a pressure surface.  Same tile shape as GwindOp (one staged array, three
 // grid-constant maps); MODE 0 = xcomp, 1 = ycomp, 2 = gvort (which also reads the centre point).
@@ -1655,7 +1728,7 @@ int fcb200_plevelqvector(int nx, int ny, const float* z, const float* t, const f
 
 int fcb200_thermalFrontParameter_batched(int nx, int ny, int nfields, const float* t, const float* xmapr, const float* ymapr, float* tfp,
                                          int* fDefined, float undef)
-{ // FC.cc:2266-2309, both passes in one kernel (TfpFusedOp)
+{ // FC.cc:2266-2309
   if (nx < 3 || ny < 3)
     return 0;
   if (!grid_ok(nx, ny, nfields))
@@ -1670,6 +1743,23 @@ int fcb200_thermalFrontParameter_batched(int nx, int ny, int nfields, const floa
   unsigned long long* counters = call.counters(2 * nfields); // [0, nfields): undefined elements of T, [nfields, 2 nfields): pass 2
   if (!call.ok())
     return -1;
+  // Default: the reference's own two passes through a scratch field -- gradient(c=3) on the tile engine, then TfpPass2Op --
+  // 20 B/point instead of the fused kernel's 8, but 1.7x faster (134 vs 79 Gpt/s on 16 ECMWF levels, 82 vs 53 with 30 % of
+  // T undefined; profiles/r01_tfp_unfused_vs_fused.txt): the fused kernel is bound by its ~210 instructions per point and
+  // four block barriers per field at 28 % occupancy, not by memory.  FCB200_TFP_FUSED=1 selects the fused kernel.
+  static const bool fused = getenv("FCB200_TFP_FUSED") != nullptr;
+  if (!fused) {
+    float* d_ad = static_cast<float*>(call.scratch(sizeof(float) * n * nfields));
+    if (!call.ok())
+      return -1;
+    if (!launch_stencil(call, GradientOp<3>{d_t, d_xm, d_ym, d_ad}, nx, ny, nfields, undef, meta, counters))
+      return -1;
+    TfpPass2Op p2;
+    p2.tx = d_t, p2.ad = d_ad, p2.xm = d_xm, p2.ym = d_ym, p2.pass1_undef = counters, p2.o = d_out;
+    if (!launch_stencil(call, p2, nx, ny, nfields, undef, meta, counters + nfields))
+      return -1;
+    return call.finish(flags_from_counters(fDefined, nfields, n - 2 * (size_t)nx, nfields));
+  }
   bool any_masked = false;
   for (int k = 0; k < nfields; ++k)
     any_masked = any_masked || fDefined[k] != ALL_DEFINED;
