@@ -102,6 +102,30 @@ __global__ void __launch_bounds__(256) sat_window_kernel(const float* __restrict
   }
 }
 
+// compute 5 / 6 with a small window: the summed-area table of a 0 / 1 indicator holds exact integers (< 2^24), so the
+// reference's four-entry difference IS the number of points of the window beyond the limit -- counted here directly
+// (the window's rows come from L1), one thread per output point.  Same quotient count / N, same bits.
+__global__ void __launch_bounds__(256) box_probability_kernel(const float* __restrict__ f, float* __restrict__ fres, int nx, int ny, int range, float limit,
+                                                              int above, float undef)
+{
+  const long long n = (long long)nx * ny;
+  const int N = (2 * range + 1) * (2 * range + 1);
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < n; idx += (long long)gridDim.x * blockDim.x) {
+    const int j = (int)(idx / nx), i = (int)(idx - (long long)j * nx);
+    if (i < range || i >= nx - range || j < range || j >= ny - range) {
+      fres[idx] = undef;
+      continue;
+    }
+    int count = 0;
+    for (int y = j - range; y <= j + range; ++y) {
+      const float* row = f + (size_t)y * nx;
+      for (int x = i - range; x <= i + range; ++x)
+        count += (above ? row[x] > limit : row[x] < limit) ? 1 : 0;
+    }
+    fres[idx] = (float)count / (float)N;
+  }
+}
+
 __global__ void __launch_bounds__(256) border_undef_kernel(float* __restrict__ fres, int nx, int ny, int range, float undef)
 {
   const long long n = (long long)nx * ny;
@@ -232,6 +256,11 @@ int fcb200_neighbourProbFunctions(int nx, int ny, const float* field, const floa
   if (!call.ok())
     return -1;
   cudaStream_t s = call.stream();
+  if (indicator && range >= 1 && range <= 8 && n < (1LL << 24) && static_cast<const void*>(d_f) != static_cast<const void*>(d_o)) {
+    box_probability_kernel<<<grid_for(n, 256), 256, 0, s>>>(d_f, d_o, nx, ny, range, (float)limit, compute == 5 ? 1 : 0, undef);
+    count_launch();
+    return call.finish([=](const unsigned long long*) { *fDefined = SOME_DEFINED; });
+  }
   if (indicator) {
     indicator_kernel<<<grid_for(n, 256), 256, 0, s>>>(d_f, d_o, n, (float)limit, compute == 5 ? 1 : 0);
     count_launch();

@@ -81,7 +81,7 @@ VARIANTS = {
     "plevelqvector": [dict(compute=c) for c in (1, 2, 3, 4, 5)] + [dict(compute=1, p=0.0)],
     "neighbourProbFunctions": [dict(compute=5), dict(compute=6), dict(compute=5, limits=(270.0, 0.0)), dict(compute=6, limits=(262.0, 1.0)),
                                dict(compute=5, limits=(270.0, 3.0)), dict(compute=1, limits=(270.0, 1.0)), dict(compute=5, limits=(270.0,)),
-                               dict(compute=5, limits=(270.0, 50.0))],
+                               dict(compute=5, limits=(270.0, 50.0)), dict(compute=6, limits=(270.0, 9.0))],
     "neighbourFunctions": [dict(compute=1), dict(compute=2), dict(compute=3), dict(compute=1, limits=(1.0,)), dict(compute=2, limits=(3.0, 1.0)),
                            dict(compute=4, limits=(90.0, 2.0, 1.0)), dict(compute=4, limits=(50.0, 1.0)), dict(compute=4, limits=(0.0, 1.0, 2.0)),
                            dict(compute=5, limits=(270.0, 2.0, 1.0)), dict(compute=6, limits=(270.0, 1.0, 3.0)), dict(compute=4, limits=(100.0, 1.0)),
