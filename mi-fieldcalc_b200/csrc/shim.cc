@@ -10,7 +10,11 @@
 // FCB200_ON_ERROR=return in the environment it prints the message and returns false instead.
 #include "mi_fieldcalc/FieldCalculations.h"
 
+#include "mi_fieldcalc/MetConstants.h"
+
 #include "fcb200.h"
+
+#include <cmath>
 
 #include <cstdio>
 #include <cstdlib>
@@ -53,7 +57,62 @@ ValuesDefined combineDefined(ValuesDefined a, ValuesDefined b)
   return (b != ALL_DEFINED) ? b : SOME_DEFINED;
 }
 
+// openmp_tools.h:58 of the reference: the thread count of its OpenMP loops.  There are no host loops here: the serial
+// build's answer (openmp_tools.cc:78).
+int compute_num_threads(long) { return 1; }
+
+// ---- MetConstants.cc:51-131 of the reference: ICAO standard atmosphere, seven layers of constant lapse rate up to
+// 84.852 km.  Layer k starts at height H[k] (km) with temperature T[k] (K) and pressure P[k] (hPa) and has the
+// temperature gradient L[k] (K/km).  Inside a layer: p/P = (1 + dh L/T)^(-g/(L R)) for L != 0, exp(-dh g/(R T)) for L = 0.
+namespace constants {
+namespace {
+const double kG = 9.80665, kR = 287.05287;
+const int kLayers = 8;
+const double kL[kLayers - 1] = {-6.5, 0, +1.0, +2.8, 0, -2.8, -2.0};
+const double kH[kLayers] = {0, 11, 20, 32, 47, 51, 71, 84.852};
+const double kT[kLayers] = {288.15, 216.65, 216.65, 228.65, 270.65, 270.65, 214.65, 186.946};
+const double kP[kLayers] = {1013.15,           226.29806486313493, 54.743370958898005,  8.679301101236328,
+                            1.1089482781849516, 0.6693192180209551, 0.0395600169484907, 0.0037334345211142398};
+} // namespace
+
+double ICAO_geo_altitude_from_pressure(double pressure)
+{
+  int k = 1;
+  while (k < kLayers && pressure < kP[k])
+    ++k;
+  if (k >= kLayers)
+    return 1000 * (kH[kLayers - 1] + 1); // above the standard atmosphere
+  --k;
+  const double lapse = kL[k] / 1000, base = kH[k] * 1000, ratio = pressure / kP[k];
+  if (lapse != 0)
+    return (kT[k] / lapse) * (std::pow(ratio, -(lapse * kR) / kG) - 1) + base;
+  return base - std::log(ratio) * (kR * kT[k]) / kG;
+}
+
+double ICAO_pressure_from_geo_altitude(double altitude)
+{
+  const double km = altitude / 1000;
+  int k = 1;
+  while (k < kLayers && km > kH[k])
+    ++k;
+  if (k >= kLayers)
+    return kP[kLayers - 1] - 1; // above the standard atmosphere
+  --k;
+  const double lapse = kL[k] / 1000, dh = altitude - kH[k] * 1000;
+  const double factor = (lapse != 0) ? std::pow(1 + dh * lapse / kT[k], -kG / (lapse * kR)) : std::exp(-dh * kG / (kR * kT[k]));
+  return kP[k] * factor;
+}
+
+int FL_from_geo_altitude(double a) { return 5 * (int)round(a * ft_per_m / 500); }
+
+double geo_altitude_from_FL(double fl) { return fl * 100 / ft_per_m; }
+
+} // namespace constants
+
 namespace fieldcalc {
+
+// FC.cc:298-301 (an exported helper of the reference, although not declared in its header)
+float bad_hlevel(float a, float b) { return (a < 0.0) || (b < 0.0) || (a == 0.0 && b == 0.0) || (b > 1.0); }
 
 namespace {
 

@@ -1,14 +1,16 @@
 // test_fieldcalc_api.cc -- the reference's own known-answer tests for the hot path, restated
 // against the drop-in C++ API (include/mi_fieldcalc/FieldCalculations.h).
 //
-// Source of the vectors: /root/reference/test/FieldCalculationsTest.cc -- XLevelHum :70-143,
-// ALevelTempPerformance :145-170, XOperX :172-223 (fieldOPERfield part), Probability :225-283,
-// Probability12 :285-305.  gtest is not installed, so a twenty-line checker stands in for it.
+// Source of the vectors: /root/reference/test/FieldCalculationsTest.cc -- absHum :56-68, XLevelHum :70-143,
+// ALevelTempPerformance :145-170, XOperX :172-223, Probability :225-283, Probability12 :285-305, Neighbour :307-451,
+// ReplaceDefined :453-482, ReplaceUndefined :484-513 -- and test/MetConstantsTest.cc :37-113 (ICAO standard atmosphere).
+// gtest is not installed, so a twenty-line checker stands in for it.
 //
 // The same source links against EITHER implementation of the API:
 //   - libmi-fieldcalc.so.0 from this repository (CUDA; pytest -m gpu), or
 //   - oracle/_ref/libfcref.so, the unmodified reference (CPU; validates this test itself).
 #include "mi_fieldcalc/FieldCalculations.h"
+#include "mi_fieldcalc/MetConstants.h"
 
 #include <cmath>
 #include <cstdio>
@@ -152,7 +154,163 @@ static void test_field_oper_field()
     CHECK(fc::fieldOPERfield(r.c, 1, 1, &r.a, &r.b, &out, f, UNDEF), "fieldOPERfield c=%d", r.c);
     CHECK((r.expect == UNDEF) == (f == NONE_DEFINED), "fieldOPERfield c=%d a=%g b=%g flag %d", r.c, r.a, r.b, (int)f);
     CHECK(near(r.expect, out, 1e-6f), "fieldOPERfield c=%d a=%g b=%g got %g want %g", r.c, r.a, r.b, out, r.expect);
+
+    out = 2 * UNDEF;
+    f = r.in;
+    CHECK(fc::fieldOPERconstant(r.c, 1, 1, &r.a, r.b, &out, f, UNDEF), "fieldOPERconstant c=%d", r.c);
+    CHECK((r.expect == UNDEF) == (f == NONE_DEFINED), "fieldOPERconstant c=%d a=%g b=%g flag %d", r.c, r.a, r.b, (int)f);
+    CHECK(near(r.expect, out, 1e-6f), "fieldOPERconstant c=%d a=%g b=%g got %g want %g", r.c, r.a, r.b, out, r.expect);
+
+    out = 2 * UNDEF;
+    f = r.in;
+    CHECK(fc::constantOPERfield(r.c, 1, 1, r.a, &r.b, &out, f, UNDEF), "constantOPERfield c=%d", r.c);
+    CHECK((r.expect == UNDEF) == (f == NONE_DEFINED), "constantOPERfield c=%d a=%g b=%g flag %d", r.c, r.a, r.b, (int)f);
+    CHECK(near(r.expect, out, 1e-6f), "constantOPERfield c=%d a=%g b=%g got %g want %g", r.c, r.a, r.b, out, r.expect);
   }
+}
+
+// ---- absHum ---------------------------------------------------------------------------------------------
+static void test_abshum()
+{
+  const float UNDEF = 12356789;
+  float out = 2 * UNDEF, t = 293.16f, rh = 0.8f;
+  ValuesDefined f = ALL_DEFINED;
+  CHECK(fc::abshum(1, 1, &t, &rh, &out, f, UNDEF), "abshum");
+  CHECK(near(13.82f, out, 0.1f), "abshum got %g", out);
+  CHECK(f == ALL_DEFINED, "abshum flag %d", (int)f);
+}
+
+// ---- Neighbour ------------------------------------------------------------------------------------------
+static void test_neighbour()
+{
+  const float UNDEF = 123456;
+  const int NX = 10, NY = 10;
+  float in[NX * NY], out[NX * NY], out2[NX * NY];
+  std::vector<float> c;
+  ValuesDefined f = ALL_DEFINED, f2 = ALL_DEFINED;
+  for (int i = 0; i < NX * NY; ++i)
+    in[i] = 0;
+
+  c = {float(NX + 1)};
+  CHECK(!fc::neighbourFunctions(NX, NY, in, c, 2, out, f, UNDEF), "range > nx must be rejected");
+  c = {float(NX), 0};
+  CHECK(!fc::neighbourFunctions(NX, NY, in, c, 2, out, f, UNDEF), "step < 1 must be rejected");
+
+  in[16] = 6;
+  for (int i = 0; i < NX * NY; ++i)
+    out[i] = UNDEF / 2;
+  c = {3, 3};
+  CHECK(fc::neighbourFunctions(NX, NY, in, c, 2, out, f, UNDEF), "max r3 s3");
+  CHECK(f == SOME_DEFINED, "flag %d", (int)f);
+  for (int i = 0; i < NX; i++)
+    for (int j = 0; j < NY; j++) {
+      const float e = (i < 2 || i >= NX - 2 || j < 2 || j >= NY - 2) ? UNDEF : (j < 5 ? 6.f : 0.f);
+      CHECK(e == out[i + j * NX], "max i=%d j=%d got %g want %g", i, j, out[i + j * NX], e);
+    }
+
+  auto four = [&]() {
+    for (int i = 0; i < NX * NY; ++i) {
+      in[i] = 0;
+      out[i] = out2[i] = UNDEF / 2;
+    }
+    in[25] = in[26] = in[35] = in[36] = 6;
+    f = f2 = ALL_DEFINED;
+  };
+  four();
+  c = {90, 2, 1};
+  CHECK(fc::neighbourFunctions(NX, NY, in, c, 4, out, f, UNDEF), "percentile");
+  CHECK(f == SOME_DEFINED, "flag %d", (int)f);
+  for (int i = 0; i < NX; i++)
+    for (int j = 0; j < NY; j++) {
+      const float e = (i < 2 || i >= NX - 2 || j < 2 || j >= NY - 2) ? UNDEF : ((i > 3 && i < 8 && j > 1 && j < 5) ? 6.f : 0.f);
+      CHECK(e == out[i + j * NX], "pct i=%d j=%d got %g want %g", i, j, out[i + j * NX], e);
+    }
+
+  four();
+  c = {5, 2, 1};
+  CHECK(fc::neighbourFunctions(NX, NY, in, c, 5, out, f, UNDEF), "prob above");
+  CHECK(fc::neighbourProbFunctions(NX, NY, in, c, 5, out2, f2, UNDEF), "prob above (SAT)");
+  CHECK(f == SOME_DEFINED && f2 == SOME_DEFINED, "flags %d %d", (int)f, (int)f2);
+  for (int i = 0; i < NX; i++)
+    for (int j = 0; j < NY; j++) {
+      CHECK(float_eq_4ulp(out[i + j * NX], out2[i + j * NX]), "above i=%d j=%d %g vs %g", i, j, out[i + j * NX], out2[i + j * NX]);
+      float e;
+      if (i < 2 || i >= NX - 2 || j < 2 || j >= NY - 2)
+        e = UNDEF;
+      else if (i > 3 && j < 5)
+        e = 0.16;
+      else if (i == 3 && j == 5)
+        e = 0.04;
+      else if (i > 2 && j < 6)
+        e = 0.08;
+      else
+        e = 0;
+      CHECK(e == out[i + j * NX], "above i=%d j=%d got %g want %g", i, j, out[i + j * NX], e);
+    }
+
+  four();
+  c = {5, 3, 1};
+  CHECK(fc::neighbourFunctions(NX, NY, in, c, 6, out, f, UNDEF), "prob below");
+  CHECK(fc::neighbourProbFunctions(NX, NY, in, c, 6, out2, f2, UNDEF), "prob below (SAT)");
+  CHECK(f == SOME_DEFINED && f2 == SOME_DEFINED, "flags %d %d", (int)f, (int)f2);
+  for (int i = 0; i < NX; i++)
+    for (int j = 0; j < NY; j++) {
+      CHECK(float_eq_4ulp(out[i + j * NX], out2[i + j * NX]), "below i=%d j=%d %g vs %g", i, j, out[i + j * NX], out2[i + j * NX]);
+      const float e = (i < 3 || i >= NX - 3 || j < 3 || j >= NY - 3) ? UNDEF : (j < 6 ? float(45. / 49.) : float(47. / 49.));
+      CHECK(float_eq_4ulp(e, out[i + j * NX]), "below i=%d j=%d got %g want %g", i, j, out[i + j * NX], e);
+    }
+}
+
+// ---- ReplaceDefined / ReplaceUndefined ----------------------------------------------------------------------
+static void test_replace()
+{
+  const int n = 2;
+  const float in1[n] = {0, 1};
+  float out1[n] = {-1, -1};
+  ValuesDefined d = SOME_DEFINED;
+  fc::replaceDefined(n, 1, in1, 5, out1, d, 0);
+  CHECK(out1[0] == 0 && out1[1] == 5 && d == ALL_DEFINED, "replaceDefined SOME: %g %g %d", out1[0], out1[1], (int)d);
+  d = ALL_DEFINED;
+  fc::replaceDefined(n, 1, in1, 7, out1, d, -1);
+  CHECK(out1[0] == 7 && out1[1] == 7 && d == ALL_DEFINED, "replaceDefined ALL: %g %g %d", out1[0], out1[1], (int)d);
+  d = NONE_DEFINED;
+  fc::replaceDefined(n, 1, in1, 7, out1, d, -1);
+  CHECK(out1[0] == -1 && out1[1] == -1 && d == NONE_DEFINED, "replaceDefined NONE: %g %g %d", out1[0], out1[1], (int)d);
+  d = SOME_DEFINED;
+  fc::replaceDefined(n, 1, in1, 1, out1, d, 1); // value == undef
+  CHECK(out1[0] == 1 && out1[1] == 1 && d == NONE_DEFINED, "replaceDefined value==undef: %g %g %d", out1[0], out1[1], (int)d);
+
+  out1[0] = out1[1] = -1;
+  d = SOME_DEFINED;
+  fc::replaceUndefined(n, 1, in1, 5, out1, d, 0);
+  CHECK(out1[0] == 5 && out1[1] == 1 && d == ALL_DEFINED, "replaceUndefined SOME: %g %g %d", out1[0], out1[1], (int)d);
+  d = ALL_DEFINED;
+  fc::replaceUndefined(n, 1, in1, 7, out1, d, -1);
+  CHECK(out1[0] == 0 && out1[1] == 1 && d == ALL_DEFINED, "replaceUndefined ALL: %g %g %d", out1[0], out1[1], (int)d);
+  d = NONE_DEFINED;
+  fc::replaceUndefined(n, 1, in1, 7, out1, d, -1);
+  CHECK(out1[0] == 7 && out1[1] == 7 && d == ALL_DEFINED, "replaceUndefined NONE: %g %g %d", out1[0], out1[1], (int)d);
+  d = SOME_DEFINED;
+  fc::replaceUndefined(n, 1, in1, 1, out1, d, 1); // value == undef
+  CHECK(out1[0] == 0 && out1[1] == 1 && d == SOME_DEFINED, "replaceUndefined value==undef: %g %g %d", out1[0], out1[1], (int)d);
+}
+
+// ---- MetConstantsTest: ICAO standard atmosphere (doc 7488) --------------------------------------------------
+static void test_icao()
+{
+  using namespace miutil::constants;
+  const double doc7488[][2] = {{8.7, 31985},  {10.0, 31055}, {11.1, 30360}, {19.4, 26680}, {97.3, 16353}, {139.5, 14069},
+                               {244.1, 10517}, {354.2, 8035}, {459.7, 6189}, {590.8, 4324}, {739.7, 2576}, {840.7, 1547},
+                               {936.8, 657},   {1010.0, 27},  {1020.0, -56}, {1050.0, -302}, {1130.0, -929}};
+  for (const auto& row : doc7488) {
+    CHECK(std::fabs(row[1] - ICAO_geo_altitude_from_pressure(row[0])) <= 1.55, "altitude of %g hPa", row[0]);
+    CHECK(std::fabs(row[0] - ICAO_pressure_from_geo_altitude(row[1])) <= 0.01 * row[0], "pressure at %g m", row[1]);
+  }
+  const int examples[][2] = {{600, 140}, {500, 185}, {400, 235}, {300, 300}, {250, 340}, {200, 385}, {150, 445}};
+  for (const auto& row : examples)
+    CHECK(row[1] == FL_from_geo_altitude(ICAO_geo_altitude_from_pressure(row[0])), "FL of %d hPa", row[0]);
+  for (int i = 0; i < nLevelTable; ++i)
+    CHECK((int)fLevelTable[i] == FL_from_geo_altitude(ICAO_geo_altitude_from_pressure(pLevelTable[i])), "FL of level %d", i);
 }
 
 // ---- Probability / Probability12 ------------------------------------------------------------------------
@@ -226,7 +384,11 @@ int main()
   test_xlevelhum();
   test_aleveltemp_large();
   test_field_oper_field();
+  test_abshum();
   test_probability();
+  test_neighbour();
+  test_replace();
+  test_icao();
   test_relvort_solid_body();
   std::printf("%d checks, %d failed\n", g_checks, g_failed);
   return g_failed ? 1 : 0;

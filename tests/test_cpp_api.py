@@ -44,6 +44,34 @@ def test_shim_exports_the_reference_symbols():
     assert len(ours) >= 35
     missing = sorted(ours - r)
     assert not missing, "symbols that the reference does not export under the same mangled name: %s" % missing
+    # and the other way round: the whole exported ABI of the reference (72 miutil::fieldcalc functions,
+    # fieldUndef / UNDEF, checkDefined x2, combineDefined, compute_num_threads, four ICAO conversions) except the
+    # saturation-table helper class, which is an implementation detail of the field functions
+    theirs = {x for x in r if ("6miutil" in x or x == "fieldUndef") and "ewt_calculator" not in x}
+    assert len(theirs) >= 80
+    absent = sorted(theirs - s)
+    assert not absent, "exported by the reference but not by the drop-in: %s" % absent
+
+
+def test_icao_host_utilities_match_the_reference():
+    """MetConstants.cc:81-131 restated in the shim (host scalars): bit-identical on a sweep of pressures / altitudes"""
+    import ctypes
+
+    import numpy as np
+    shim = os.path.join(LIB, "libmi-fieldcalc.so.0")
+    ref = os.path.join(REF, "libfcref.so")
+    if not (os.path.exists(shim) and os.path.exists(ref)):
+        pytest.skip("shim or oracle/_ref not built")
+    a, b = ctypes.CDLL(shim), ctypes.CDLL(ref)
+    xs = np.concatenate([np.linspace(-500, 90000, 2001), np.geomspace(1e-4, 1100, 2001)])
+    for name, restype in (("_ZN6miutil9constants31ICAO_geo_altitude_from_pressureEd", ctypes.c_double),
+                          ("_ZN6miutil9constants31ICAO_pressure_from_geo_altitudeEd", ctypes.c_double),
+                          ("_ZN6miutil9constants20FL_from_geo_altitudeEd", ctypes.c_int),
+                          ("_ZN6miutil9constants20geo_altitude_from_FLEd", ctypes.c_double)):
+        fa, fb = getattr(a, name), getattr(b, name)
+        fa.restype = fb.restype = restype
+        fa.argtypes = fb.argtypes = [ctypes.c_double]
+        assert all(fa(float(x)) == fb(float(x)) for x in xs), name
 
 
 @pytest.mark.gpu
