@@ -397,15 +397,25 @@ struct MomentumOp
 // Each output keeps its own definedness test and its own undefined counter, so values, masks and
 // the four flags are exactly those of the four separate calls.  The Exner function and the
 // saturation-table lookup are evaluated once per point instead of three / two times.
-template <int U_, int MB_, int J_ = 1>
+//
+// The same code serves the four operators on their own (aleveltemp c3, alevelhum c1, alevelhum c5/9, alevelthe c1):
+// OUTS selects which outputs exist, everything an absent output would need is compiled out.
+enum : unsigned { O_THETA = 1, O_RH = 2, O_TD = 4, O_THE = 8, O_ALL = 15 };
+
+template <int U_, int MB_, int J_ = 1, unsigned OUTS = O_ALL>
 struct AlevelChainOpT
 {
+  static constexpr bool HAS_Q = (OUTS & (O_RH | O_TD | O_THE)) != 0; // q is an input
+  static constexpr bool HAS_TAB = (OUTS & (O_RH | O_TD)) != 0;       // the saturation table is used
+  static constexpr bool HAS_POW = (OUTS & (O_THETA | O_THE)) != 0;   // the Exner function is used
   static constexpr int ITEM_ROUNDS = J_;
-  static constexpr int NIN = 3, NOUT = 4, UNROLL = U_;
-  static constexpr int NCOUNT = 4;
+  static constexpr int NIN = HAS_Q ? 3 : 2; // t, [q,] p
+  static constexpr int NOUT = ((OUTS & 1) ? 1 : 0) + ((OUTS & 2) ? 1 : 0) + ((OUTS & 4) ? 1 : 0) + ((OUTS & 8) ? 1 : 0);
+  static constexpr int UNROLL = U_;
+  static constexpr int NCOUNT = NOUT;
   static constexpr int MIN_BLOCKS = MB_;
   static constexpr bool HEAVY = false;
-  static constexpr bool USES_EWT = true, USES_POW = true;
+  static constexpr bool USES_EWT = HAS_TAB, USES_POW = HAS_POW;
   static constexpr bool QUAD = true;
   float tdconv;
 
@@ -420,16 +430,26 @@ struct AlevelChainOpT
   // the arithmetic, NaN, zero or negative pressure, ...).
   __device__ __noinline__ static void ieee_raw(float t, float q, float p, const dev::EwtTable& tab, const dev::PowTable& pw, float tdconv, Raw& r)
   {
-    const float pidcp = dev::pidcp_from_p(pw, p);
-    r.theta = t / pidcp;
-    r.the = (t * K_CP + q * K_XLH) / (K_CP * pidcp);
-    const dev::Ewt e(t - K_T0);
-    const float et = e.value(tab);
-    const float qsat = dev::K_EPS * et / p;
-    r.rh = (float)(100. * (double)q / (double)qsat);
-    const float rhc = dev::clamp_rh(q / qsat);
-    r.td = e.inverse(tab, rhc * et) + tdconv;
-    r.edef = e.defined;
+    if (HAS_POW) {
+      const float pidcp = dev::pidcp_from_p(pw, p);
+      if (OUTS & O_THETA)
+        r.theta = t / pidcp;
+      if (OUTS & O_THE)
+        r.the = (t * K_CP + q * K_XLH) / (K_CP * pidcp);
+    }
+    r.edef = true;
+    if (HAS_TAB) {
+      const dev::Ewt e(t - K_T0);
+      const float et = e.value(tab);
+      const float qsat = dev::K_EPS * et / p;
+      if (OUTS & O_RH)
+        r.rh = (float)(100. * (double)q / (double)qsat);
+      if (OUTS & O_TD) {
+        const float rhc = dev::clamp_rh(q / qsat);
+        r.td = e.inverse(tab, rhc * et) + tdconv;
+      }
+      r.edef = e.defined;
+    }
   }
   // `out` of the non-inlined call lives in local memory; copying it keeps the caller's own Raw in registers
   __device__ __forceinline__ static void ieee(float t, float q, float p, const dev::EwtTable& tab, const dev::PowTable& pw, float tdconv, Raw& r)
@@ -444,85 +464,114 @@ struct AlevelChainOpT
   }
 
   // Same expressions, same roundings, for PLAUSIBLE inputs: saturation-table position x in [0, 40)
-  // (-100 <= t - 273.15 < 100 degC), p in [2^-7, 2^11) hPa, q = +0 or 2^-90 <= |q| < 2^20.  Then every divisor,
-  // quotient and remainder below is a normal number far from the ends of the exponent range, the six divisions
-  // can use the guard-free sequences of device_common.cuh, the Exner function needs no classification of its
-  // argument and the table indices need no clamps -- straight-line code without a single branch, so the
-  // compiler interleaves the four points of a thread.  Returns false (after computing harmless garbage) when
-  // the inputs are not plausible; the caller then redoes the point with `ieee`.
+  // (-100 <= t - 273.15 < 100 degC; without the table: 2^-59 <= |t| < 2^59), p in [2^-7, 2^11) hPa, q = +0 or
+  // 2^-90 <= |q| < 2^20.  Then every divisor, quotient and remainder below is a normal number far from the ends of the
+  // exponent range, the divisions can use the guard-free sequences of device_common.cuh, the Exner function needs
+  // no classification of its argument and the table indices need no clamps -- straight-line code without a single
+  // branch, so the compiler interleaves the four points of a thread.  Returns false (after computing harmless
+  // garbage) when the inputs are not plausible; the caller then redoes the point with `ieee`.
   __device__ __forceinline__ bool fast(float t, float q, float p, const dev::EwtTable& tab, const dev::PowTable& pw, Raw& r) const
   {
-    const float x = (float)(((double)(t - K_T0) + 100.) * dev::c_dconst[0]); // Ewt::Ewt, MC.h:66
-    const unsigned uq = __float_as_uint(q) & 0x7fffffffu;
-    const bool plausible = (__float_as_uint(x) < 0x42200000u)                        // +0 <= x < 40
-                           && (__float_as_uint(p) - 0x3c000000u < 0x09000000u)       // 2^-7 <= p < 2^11
-                           && ((uq - 0x12800000u < 0x37000000u) || __float_as_uint(q) == 0u); // 2^-90 <= |q| < 2^20, or +0
-    const int l = plausible ? (int)x : 0;
+    bool plausible = __float_as_uint(p) - 0x3c000000u < 0x09000000u; // 2^-7 <= p < 2^11
+    if (HAS_Q) {
+      const unsigned uq = __float_as_uint(q) & 0x7fffffffu;
+      plausible = plausible && ((uq - 0x12800000u < 0x37000000u) || __float_as_uint(q) == 0u); // 2^-90 <= |q| < 2^20, or +0
+    }
+    if (!HAS_TAB)
+      plausible = plausible && ((__float_as_uint(t) & 0x7fffffffu) - 0x22000000u < 0x3b000000u); // 2^-59 <= |t| < 2^59
 
-    const float pidcp = pw.pow_normal<dev::POW_KAPPA>(p * dev::K_P0INV); // FC.cc:308-311
-    r.theta = dev::div_midrange(t, pidcp);
-    r.the = dev::div_midrange(t * K_CP + q * K_XLH, K_CP * pidcp);
-
-    const float2 e = tab.e[l];
-    const float et = e.x + e.y * (x - (float)l); // MC.h:78
-    const float qsat = dev::div_midrange(dev::K_EPS * et, p);
-    // (Evaluating this double quotient in float-float arithmetic with a midpoint test -- no conversions, no FP64 -- was
-    // measured 8 % SLOWER: the test's dependent chain costs more than the nine DFMA it replaces.)
-    r.rh = (float)dev::div_midrange(100. * (double)q, (double)qsat); // FC.cc:229
-    const float rq = dev::div_midrange(q, qsat);
-    const float rhc = rq < dev::K_RHMIN ? dev::K_RHMIN : (rq > dev::K_RHMAX ? dev::K_RHMAX : rq); // clamp_rh, FC.cc:186-194
-    const float etd = rhc * et;
-    // Ewt::inverse (MC.cc:37-45) with the bucket table; 0.02 * ewt[0] < 2^-15 lands below the first bucket -> index 0
-    int b = (int)(__float_as_uint(etd) >> 21) - dev::EWT_LUT0;
-    b = min(max(b, 0), dev::EWT_NLUT - 1);
-    int ll = min((int)tab.lut[b], l);
-    const int k = min(ll + 1, l); // the bucket index is the answer or one below it; k == ll when the walk may not go up
-    ll = (tab.e[k].x > etd) ? ll : k;
-    const float2 e2 = tab.e[ll];
-    const float y = (float)ll + dev::div_midrange(etd - e2.x, e2.y);
-    // (float)(-100. + (double)y * 5.): for |y| < 64 the double expression is exact (5y has at most 27
-    // significant bits and -100 + 5y at most 7 + 46) or, for |y| < 2^-23, rounds to -100 either way -> one fmaf
-    r.td = fmaf(5.f, y, -100.f) + tdconv;
+    if (HAS_POW) {
+      const float pidcp = pw.pow_normal<dev::POW_KAPPA>(p * dev::K_P0INV); // FC.cc:308-311
+      if (OUTS & O_THETA)
+        r.theta = dev::div_midrange(t, pidcp);
+      if (OUTS & O_THE)
+        r.the = dev::div_midrange(t * K_CP + q * K_XLH, K_CP * pidcp);
+    }
+    if (HAS_TAB) {
+      const float x = (float)(((double)(t - K_T0) + 100.) * dev::c_dconst[0]); // Ewt::Ewt, MC.h:66
+      plausible = plausible && (__float_as_uint(x) < 0x42200000u);              // +0 <= x < 40
+      const int l = plausible ? (int)x : 0;
+      const float2 e = tab.e[l];
+      const float et = e.x + e.y * (x - (float)l); // MC.h:78
+      const float qsat = dev::div_midrange(dev::K_EPS * et, p);
+      // (Evaluating this double quotient in float-float arithmetic with a midpoint test -- no conversions, no FP64 -- was
+      // measured 8 % SLOWER: the test's dependent chain costs more than the nine DFMA it replaces.)
+      if (OUTS & O_RH)
+        r.rh = (float)dev::div_midrange(100. * (double)q, (double)qsat); // FC.cc:229
+      if (OUTS & O_TD) {
+        const float rq = dev::div_midrange(q, qsat);
+        const float rhc = rq < dev::K_RHMIN ? dev::K_RHMIN : (rq > dev::K_RHMAX ? dev::K_RHMAX : rq); // clamp_rh, FC.cc:186-194
+        const float etd = rhc * et;
+        // Ewt::inverse (MC.cc:37-45) with the bucket table; 0.02 * ewt[0] < 2^-15 lands below the first bucket -> index 0
+        int b = (int)(__float_as_uint(etd) >> 21) - dev::EWT_LUT0;
+        b = min(max(b, 0), dev::EWT_NLUT - 1);
+        int ll = min((int)tab.lut[b], l);
+        const int k = min(ll + 1, l); // the bucket index is the answer or one below it; k == ll when the walk may not go up
+        ll = (tab.e[k].x > etd) ? ll : k;
+        const float2 e2 = tab.e[ll];
+        const float y = (float)ll + dev::div_midrange(etd - e2.x, e2.y);
+        // (float)(-100. + (double)y * 5.): for |y| < 64 the double expression is exact (5y has at most 27
+        // significant bits and -100 + 5y at most 7 + 46) or, for |y| < 2^-23, rounds to -100 either way -> one fmaf
+        r.td = fmaf(5.f, y, -100.f) + tdconv;
+      }
+    }
     r.edef = true;
     return plausible;
   }
 
-  // definedness tests of the four reference calls + their four counters
+  // definedness tests of the reference calls + one counter per output
   template <bool ALL>
   __device__ __forceinline__ void finish(float t, float q, float p, const Raw& r, float undef, float* out, unsigned* nundef) const
   {
-    const bool dt = ALL || is_def(t, undef), dq = ALL || is_def(q, undef), dp = ALL || is_def(p, undef);
+    const bool dt = ALL || is_def(t, undef), dq = ALL || !HAS_Q || is_def(q, undef), dp = ALL || is_def(p, undef);
     const bool ok_theta = dt && dp;          // aleveltemp tests t, p
     const bool ok_hum = dt && dq && r.edef;  // alevelhum c1/c5 test t, q only; an undefined p flows into the arithmetic
     const bool ok_the = dt && dq && dp;      // alevelthe tests t, q, p
-    out[0] = ok_theta ? r.theta : undef;
-    out[1] = ok_hum ? r.rh : undef;
-    out[2] = ok_hum ? r.td : undef;
-    out[3] = ok_the ? r.the : undef;
-    nundef[0] += ok_theta ? 0u : 1u;
-    nundef[1] += ok_hum ? 0u : 1u;
-    nundef[2] += ok_hum ? 0u : 1u;
-    nundef[3] += ok_the ? 0u : 1u;
+    int o = 0;
+    if (OUTS & O_THETA) {
+      out[o] = ok_theta ? r.theta : undef;
+      nundef[o++] += ok_theta ? 0u : 1u;
+    }
+    if (OUTS & O_RH) {
+      out[o] = ok_hum ? r.rh : undef;
+      nundef[o++] += ok_hum ? 0u : 1u;
+    }
+    if (OUTS & O_TD) {
+      out[o] = ok_hum ? r.td : undef;
+      nundef[o++] += ok_hum ? 0u : 1u;
+    }
+    if (OUTS & O_THE) {
+      out[o] = ok_the ? r.the : undef;
+      nundef[o++] += ok_the ? 0u : 1u;
+    }
   }
 
-  // For a field that is not ALL_DEFINED: an undefined q only reaches outputs that are undefined anyway, so
-  // it is replaced by +0 (plausible) for the arithmetic; a point with an undefined t has no defined output at
-  // all and never needs the IEEE redo.  An undefined p with defined t, q DOES flow into RH and Td (FC.cc:1429).
+  // For a field that is not ALL_DEFINED: an undefined q only reaches outputs that are undefined anyway, so it is
+  // replaced by +0 (plausible) for the arithmetic; the IEEE redo is only needed if some output of the point can still
+  // be defined -- never with an undefined t; with an undefined p only RH and Td, into which it flows (FC.cc:1429).
   template <bool ALL>
   __device__ __forceinline__ bool eval(float t, float q, float p, const PointCtx& c, Raw& r) const
   {
-    const float qe = (ALL || is_def(q, c.undef)) ? q : 0.f;
+    const bool dq = ALL || !HAS_Q || is_def(q, c.undef);
+    const float qe = dq ? q : 0.f;
     const bool plausible = fast(t, qe, p, c.tab, c.pw, r);
-    return plausible || !(ALL || is_def(t, c.undef));
+    if (ALL)
+      return plausible;
+    const bool dt = is_def(t, c.undef), dp = is_def(p, c.undef);
+    const bool live = dt && ((HAS_TAB && dq) || (HAS_POW && dp && ((OUTS & O_THETA) || dq)));
+    return plausible || !live;
   }
+
+  __device__ __forceinline__ static float Q(const float* in) { return HAS_Q ? in[1] : 0.f; }
+  __device__ __forceinline__ static float P(const float* in) { return in[NIN - 1]; }
 
   template <bool ALL>
   __device__ __forceinline__ void point(const float* in, float* out, const PointCtx& c, long long, unsigned* nundef) const
   {
     Raw r;
-    if (!eval<ALL>(in[0], in[1], in[2], c, r))
-      ieee(in[0], in[1], in[2], c.tab, c.pw, tdconv, r);
-    finish<ALL>(in[0], in[1], in[2], r, c.undef, out, nundef);
+    if (!eval<ALL>(in[0], Q(in), P(in), c, r))
+      ieee(in[0], Q(in), P(in), c.tab, c.pw, tdconv, r);
+    finish<ALL>(in[0], Q(in), P(in), r, c.undef, out, nundef);
   }
 
   // four consecutive points of one thread: all fast evaluations first (one basic block), the rare IEEE redo after
@@ -532,20 +581,22 @@ struct AlevelChainOpT
     Raw r[4];
     unsigned bad = 0;
 #pragma unroll
-    for (int w = 0; w < 4; ++w)
-      bad |= eval<ALL>(in[0][w], in[1][w], in[2][w], c, r[w]) ? 0u : (1u << w);
+    for (int w = 0; w < 4; ++w) {
+      const float q = HAS_Q ? in[1][w] : 0.f;
+      bad |= eval<ALL>(in[0][w], q, in[NIN - 1][w], c, r[w]) ? 0u : (1u << w);
+    }
     if (bad) {
 #pragma unroll
       for (int w = 0; w < 4; ++w)
         if (bad & (1u << w))
-          ieee(in[0][w], in[1][w], in[2][w], c.tab, c.pw, tdconv, r[w]);
+          ieee(in[0][w], HAS_Q ? in[1][w] : 0.f, in[NIN - 1][w], c.tab, c.pw, tdconv, r[w]);
     }
 #pragma unroll
     for (int w = 0; w < 4; ++w) {
-      float o[4];
-      finish<ALL>(in[0][w], in[1][w], in[2][w], r[w], c.undef, o, nundef);
+      float o[NOUT];
+      finish<ALL>(in[0][w], HAS_Q ? in[1][w] : 0.f, in[NIN - 1][w], r[w], c.undef, o, nundef);
 #pragma unroll
-      for (int k = 0; k < 4; ++k)
+      for (int k = 0; k < NOUT; ++k)
         out[k][w] = o[k];
     }
   }
@@ -621,6 +672,10 @@ int impl_xleveltemp(const Batch& b, const float* tinp, const float* pin, const f
     return run_elementwise(b, op, in, pf, tout, fDefined, undef, FLAG_FROM_COUNT, levels);
   }
   const float* in[2] = {tinp, pin};
+  // T -> theta: the fused chain's branch-free code with one output.  Shapes measured on B200 (MEPS x 96, fraction of the HBM
+  // roofline): 3 CTAs/SM 0.65, 4 CTAs/SM 0.63, 2 CTAs/SM 0.56; the generic TempOp 0.55.
+  if (KIND == ALEVEL && compute == 3)
+    return run_elementwise(b, AlevelChainOpT<2, 3, 2, O_THETA>{0.f}, in, pf, tout, fDefined, undef, FLAG_FROM_COUNT, levels);
   TempOp<KIND> op{compute};
   return run_elementwise(b, op, in, pf, tout, fDefined, undef, FLAG_FROM_COUNT, levels);
 }
@@ -642,6 +697,8 @@ int impl_xlevelthe(const Batch& b, const float* t, const float* q, const float* 
     return run_elementwise(b, op, in, pf, the, fDefined, undef, FLAG_FROM_COUNT, levels);
   }
   const float* in[3] = {t, q, pin};
+  // (the one-output form of the fused chain, AlevelChainOpT<.., O_THE>, was measured at 0.65 - 0.69 of the roofline for 2 - 4
+  // CTAs/SM against 0.72 for this generic operator: not used)
   TheOp<KIND> op{compute};
   return run_elementwise(b, op, in, pf, the, fDefined, undef, FLAG_FROM_COUNT, levels);
 }
@@ -655,6 +712,14 @@ int impl_xlevelhum(const Batch& b, const float* t, const float* huminp, const fl
   HumOp<KIND> op{compute, (KIND == HLEVEL) ? !no_p : no_p, (compute >= 9) ? H_T0 : 0.f};
   const float* in[3] = {t, huminp, pin};
   const int pf[3] = {1, 1, KIND == ALEVEL ? 1 : 0};
+  // T, q -> RH and T, q -> Td: one-output forms of the fused chain (0.77 / 0.69 of the roofline at 3 CTAs/SM against 0.62 / 0.47 for
+  // the generic HumOp; 2 CTAs/SM 0.65 / 0.62, 4 CTAs/SM 0.73 / 0.66).  Price: a field whose p is undefined where t and q are
+  // defined sends those points through the IEEE redo (p flows into the arithmetic, FC.cc:1429): 0.31 / 0.24 instead of 0.50 / 0.40
+  // with 30 % of t, q, p independently undefined.
+  if (KIND == ALEVEL && compute == 1)
+    return run_elementwise(b, AlevelChainOpT<2, 3, 2, O_RH>{0.f}, in, pf, humout, fDefined, undef, FLAG_FROM_COUNT, NoMeta());
+  if (KIND == ALEVEL && (compute == 5 || compute == 9))
+    return run_elementwise(b, AlevelChainOpT<2, 3, 2, O_TD>{(compute >= 9) ? H_T0 : 0.f}, in, pf, humout, fDefined, undef, FLAG_FROM_COUNT, NoMeta());
   return run_elementwise(b, op, in, pf, humout, fDefined, undef, FLAG_FROM_COUNT, [&](int k, FieldMeta& m) {
     if (KIND == HLEVEL) {
       m.a = alevel[k];
@@ -942,7 +1007,7 @@ int fcb200_alevel_chain_batched(int nx, int ny, int nfields, const float* t, con
   // Kernel shape (measured on B200, profiles/r01_chain_tuning.txt): 2 float4 groups per thread and round, 4 rounds per
   // item, 2 CTAs of 256 threads per SM (<= 128 registers: the straight-line code of 8 interleaved points needs
   // them; 64- and 80-register builds spill and lose 10-15 %).
-  return run(AlevelChainOpT<2, 2, 4>{tdconv});
+  return run(AlevelChainOpT<2, 2, 4, O_ALL>{tdconv});
 }
 
 } // extern "C"
