@@ -402,14 +402,18 @@ struct MomentumOp
 // OUTS selects which outputs exist, everything an absent output would need is compiled out.
 enum : unsigned { O_THETA = 1, O_RH = 2, O_TD = 4, O_THE = 8, O_ALL = 15 };
 
-template <int U_, int MB_, int J_ = 1, unsigned OUTS = O_ALL>
+// KIND = PLEVEL: the pressure is the field's scalar (FieldMeta::a) instead of a third input field -- plevelhum.
+// KIND = HLEVEL: the last input is the surface pressure, p = alevel + blevel * ps with the field's FieldMeta::a, ::b
+// (FC.cc:303-306) -- hleveltemp, hlevelhum, whose humidity modes test `ps != undef` (no NaN test, FC.cc:1187) where the
+// a-level ones test nothing.
+template <int U_, int MB_, int J_ = 1, unsigned OUTS = O_ALL, int KIND = ALEVEL>
 struct AlevelChainOpT
 {
   static constexpr bool HAS_Q = (OUTS & (O_RH | O_TD | O_THE)) != 0; // q is an input
   static constexpr bool HAS_TAB = (OUTS & (O_RH | O_TD)) != 0;       // the saturation table is used
   static constexpr bool HAS_POW = (OUTS & (O_THETA | O_THE)) != 0;   // the Exner function is used
   static constexpr int ITEM_ROUNDS = J_;
-  static constexpr int NIN = HAS_Q ? 3 : 2; // t, [q,] p
+  static constexpr int NIN = (HAS_Q ? 2 : 1) + (KIND != PLEVEL ? 1 : 0); // t, [q,] [p or ps]
   static constexpr int NOUT = ((OUTS & 1) ? 1 : 0) + ((OUTS & 2) ? 1 : 0) + ((OUTS & 4) ? 1 : 0) + ((OUTS & 8) ? 1 : 0);
   static constexpr int UNROLL = U_;
   static constexpr int NCOUNT = NOUT;
@@ -521,11 +525,16 @@ struct AlevelChainOpT
 
   // definedness tests of the reference calls + one counter per output
   template <bool ALL>
-  __device__ __forceinline__ void finish(float t, float q, float p, const Raw& r, float undef, float* out, unsigned* nundef) const
+  __device__ __forceinline__ void finish(float t, float q, float p, const Raw& r, const PointCtx& c, float* out, unsigned* nundef) const
   {
-    const bool dt = ALL || is_def(t, undef), dq = ALL || !HAS_Q || is_def(q, undef), dp = ALL || is_def(p, undef);
-    const bool ok_theta = dt && dp;          // aleveltemp tests t, p
-    const bool ok_hum = dt && dq && r.edef;  // alevelhum c1/c5 test t, q only; an undefined p flows into the arithmetic
+    const float undef = c.undef;
+    // PLEVEL: FieldMeta::all bit 0 = the flag is ALL_DEFINED, bit 1 = p == undef -> every point undefined (FC.cc:429-432)
+    const bool all = ALL || (KIND == PLEVEL && (c.m.all & 1) != 0);
+    const bool dt = (all || is_def(t, undef)) && !(KIND == PLEVEL && (c.m.all & 2) != 0);
+    const bool dq = all || !HAS_Q || is_def(q, undef), dp = all || KIND == PLEVEL || is_def(p, undef);
+    const bool ok_theta = dt && dp;          // a/hleveltemp test t, p (ps)
+    // alevelhum c1/c5 test t, q only -- an undefined p flows into the arithmetic; hlevelhum also tests ps != undef
+    const bool ok_hum = dt && dq && r.edef && (KIND != HLEVEL || all || p != undef);
     const bool ok_the = dt && dq && dp;      // alevelthe tests t, q, p
     int o = 0;
     if (OUTS & O_THETA) {
@@ -549,29 +558,36 @@ struct AlevelChainOpT
   // For a field that is not ALL_DEFINED: an undefined q only reaches outputs that are undefined anyway, so it is
   // replaced by +0 (plausible) for the arithmetic; the IEEE redo is only needed if some output of the point can still
   // be defined -- never with an undefined t; with an undefined p only RH and Td, into which it flows (FC.cc:1429).
+  // `praw` = the last input as stored (p, or ps for HLEVEL); the level pressure the arithmetic uses
+  __device__ __forceinline__ static float level_p(float praw, const PointCtx& c)
+  {
+    return KIND == PLEVEL ? c.m.a : (KIND == HLEVEL ? dev::p_hlevel(praw, c.m.a, c.m.b) : praw);
+  }
+
   template <bool ALL>
-  __device__ __forceinline__ bool eval(float t, float q, float p, const PointCtx& c, Raw& r) const
+  __device__ __forceinline__ bool eval(float t, float q, float praw, const PointCtx& c, Raw& r) const
   {
     const bool dq = ALL || !HAS_Q || is_def(q, c.undef);
     const float qe = dq ? q : 0.f;
-    const bool plausible = fast(t, qe, p, c.tab, c.pw, r);
+    const bool plausible = fast(t, qe, level_p(praw, c), c.tab, c.pw, r);
     if (ALL)
       return plausible;
-    const bool dt = is_def(t, c.undef), dp = is_def(p, c.undef);
-    const bool live = dt && ((HAS_TAB && dq) || (HAS_POW && dp && ((OUTS & O_THETA) || dq)));
+    const bool dt = is_def(t, c.undef), dp = KIND == PLEVEL || is_def(praw, c.undef);
+    const bool hum_live = HAS_TAB && dq && (KIND != HLEVEL || praw != c.undef);
+    const bool live = dt && (hum_live || (HAS_POW && dp && ((OUTS & O_THETA) || dq)));
     return plausible || !live;
   }
 
   __device__ __forceinline__ static float Q(const float* in) { return HAS_Q ? in[1] : 0.f; }
-  __device__ __forceinline__ static float P(const float* in) { return in[NIN - 1]; }
+  __device__ __forceinline__ static float P(const float* in) { return KIND == PLEVEL ? 0.f : in[NIN - 1]; }
 
   template <bool ALL>
   __device__ __forceinline__ void point(const float* in, float* out, const PointCtx& c, long long, unsigned* nundef) const
   {
     Raw r;
     if (!eval<ALL>(in[0], Q(in), P(in), c, r))
-      ieee(in[0], Q(in), P(in), c.tab, c.pw, tdconv, r);
-    finish<ALL>(in[0], Q(in), P(in), r, c.undef, out, nundef);
+      ieee(in[0], Q(in), level_p(P(in), c), c.tab, c.pw, tdconv, r);
+    finish<ALL>(in[0], Q(in), P(in), r, c, out, nundef);
   }
 
   // four consecutive points of one thread: all fast evaluations first (one basic block), the rare IEEE redo after
@@ -583,18 +599,18 @@ struct AlevelChainOpT
 #pragma unroll
     for (int w = 0; w < 4; ++w) {
       const float q = HAS_Q ? in[1][w] : 0.f;
-      bad |= eval<ALL>(in[0][w], q, in[NIN - 1][w], c, r[w]) ? 0u : (1u << w);
+      bad |= eval<ALL>(in[0][w], q, KIND == PLEVEL ? 0.f : in[NIN - 1][w], c, r[w]) ? 0u : (1u << w);
     }
     if (bad) {
 #pragma unroll
       for (int w = 0; w < 4; ++w)
         if (bad & (1u << w))
-          ieee(in[0][w], HAS_Q ? in[1][w] : 0.f, in[NIN - 1][w], c.tab, c.pw, tdconv, r[w]);
+          ieee(in[0][w], HAS_Q ? in[1][w] : 0.f, level_p(KIND == PLEVEL ? 0.f : in[NIN - 1][w], c), c.tab, c.pw, tdconv, r[w]);
     }
 #pragma unroll
     for (int w = 0; w < 4; ++w) {
       float o[NOUT];
-      finish<ALL>(in[0][w], HAS_Q ? in[1][w] : 0.f, in[NIN - 1][w], r[w], c.undef, o, nundef);
+      finish<ALL>(in[0][w], HAS_Q ? in[1][w] : 0.f, KIND == PLEVEL ? 0.f : in[NIN - 1][w], r[w], c, o, nundef);
 #pragma unroll
       for (int k = 0; k < NOUT; ++k)
         out[k][w] = o[k];
@@ -644,6 +660,17 @@ int impl_plevelhum(const Batch& b, const float* t, const float* huminp, const fl
   const bool even = (compute % 2 == 0);
   const float* in[2] = {t, huminp};
   const int pf[2] = {1, 1};
+  auto fill = [&](int k, FieldMeta& m) {
+    if (p[k] == undef && !rh_td)
+      m.all |= 2; // fillUndef -> every point undefined -> NONE_DEFINED (FC.cc:429-432)
+    m.a = p[k];
+    m.b = 1.f;
+  };
+  // T, q -> RH and T, q -> Td: the fused chain's branch-free code with one output and the field's scalar pressure
+  if (to_ah[compute] == 1)
+    return run_elementwise(b, AlevelChainOpT<2, 3, 2, O_RH, PLEVEL>{0.f}, in, pf, humout, fDefined, undef, FLAG_FROM_COUNT, fill);
+  if (to_ah[compute] == 5 || to_ah[compute] == 9)
+    return run_elementwise(b, AlevelChainOpT<2, 3, 2, O_TD, PLEVEL>{(compute >= 9) ? H_T0 : 0.f}, in, pf, humout, fDefined, undef, FLAG_FROM_COUNT, fill);
   return run_elementwise(b, op, in, pf, humout, fDefined, undef, FLAG_FROM_COUNT, [&](int k, FieldMeta& m) {
     if (p[k] == undef && !rh_td)
       m.all |= 2; // fillUndef -> every point undefined -> NONE_DEFINED (FC.cc:429-432)
@@ -674,8 +701,8 @@ int impl_xleveltemp(const Batch& b, const float* tinp, const float* pin, const f
   const float* in[2] = {tinp, pin};
   // T -> theta: the fused chain's branch-free code with one output.  Shapes measured on B200 (MEPS x 96, fraction of the HBM
   // roofline): 3 CTAs/SM 0.65, 4 CTAs/SM 0.63, 2 CTAs/SM 0.56; the generic TempOp 0.55.
-  if (KIND == ALEVEL && compute == 3)
-    return run_elementwise(b, AlevelChainOpT<2, 3, 2, O_THETA>{0.f}, in, pf, tout, fDefined, undef, FLAG_FROM_COUNT, levels);
+  if (compute == 3)
+    return run_elementwise(b, AlevelChainOpT<2, 3, 2, O_THETA, KIND>{0.f}, in, pf, tout, fDefined, undef, FLAG_FROM_COUNT, levels);
   TempOp<KIND> op{compute};
   return run_elementwise(b, op, in, pf, tout, fDefined, undef, FLAG_FROM_COUNT, levels);
 }
@@ -716,16 +743,17 @@ int impl_xlevelhum(const Batch& b, const float* t, const float* huminp, const fl
   // the generic HumOp; 2 CTAs/SM 0.65 / 0.62, 4 CTAs/SM 0.73 / 0.66).  Price: a field whose p is undefined where t and q are
   // defined sends those points through the IEEE redo (p flows into the arithmetic, FC.cc:1429): 0.31 / 0.24 instead of 0.50 / 0.40
   // with 30 % of t, q, p independently undefined.
-  if (KIND == ALEVEL && compute == 1)
-    return run_elementwise(b, AlevelChainOpT<2, 3, 2, O_RH>{0.f}, in, pf, humout, fDefined, undef, FLAG_FROM_COUNT, NoMeta());
-  if (KIND == ALEVEL && (compute == 5 || compute == 9))
-    return run_elementwise(b, AlevelChainOpT<2, 3, 2, O_TD>{(compute >= 9) ? H_T0 : 0.f}, in, pf, humout, fDefined, undef, FLAG_FROM_COUNT, NoMeta());
-  return run_elementwise(b, op, in, pf, humout, fDefined, undef, FLAG_FROM_COUNT, [&](int k, FieldMeta& m) {
+  auto levels = [&](int k, FieldMeta& m) {
     if (KIND == HLEVEL) {
       m.a = alevel[k];
       m.b = blevel[k];
     }
-  });
+  };
+  if (compute == 1)
+    return run_elementwise(b, AlevelChainOpT<2, 3, 2, O_RH, KIND>{0.f}, in, pf, humout, fDefined, undef, FLAG_FROM_COUNT, levels);
+  if (compute == 5 || compute == 9)
+    return run_elementwise(b, AlevelChainOpT<2, 3, 2, O_TD, KIND>{(compute >= 9) ? H_T0 : 0.f}, in, pf, humout, fDefined, undef, FLAG_FROM_COUNT, levels);
+  return run_elementwise(b, op, in, pf, humout, fDefined, undef, FLAG_FROM_COUNT, levels);
 }
 
 template <int KIND>
