@@ -118,6 +118,19 @@ def main():
             return a + [torch.empty(batch(grid, nt), device=dev), np.full(nt, flag_in, np.int32), UNDEF]
         return build
 
+    def b_hlevel(kinds, tail):
+        """hybrid levels: per-field arrays, one shared surface-pressure field, alevel / blevel per field (65 MEPS-like levels, repeated)"""
+        def build(grid, nf):
+            nx, ny = grid
+            rng = {"t": (215, 305), "q": (1e-6, 2e-2)}
+            fields = [rnd(batch(grid, nf), *rng[k]) for k in kinds]
+            ps = rnd((ny, nx), 950, 1040)
+            eta = (np.arange(nf) % 65 + 0.5) / 65.0
+            a = (200.0 * (1 - eta) * eta * 2.0 + 10.0 * (1 - eta)).astype(np.float32)
+            b = (eta ** 1.5).astype(np.float32)
+            return [nx, ny, nf] + fields + [ps, a, b] + list(tail) + [torch.empty(batch(grid, nf), device=dev), np.full(nf, flag_in, np.int32), UNDEF]
+        return build
+
     def b_chain(grid, nf):
         nx, ny = grid
         return [nx, ny, nf, rnd(batch(grid, nf), 215, 305), rnd(batch(grid, nf), 1e-6, 2e-2), rnd(batch(grid, nf), 300, 1040), "celsius"] + \
@@ -165,6 +178,9 @@ def main():
         "pleveltemp_c4": ("pleveltemp_batched", MEPS, 128, 8, b_pleveltemp(4)),
         "plevelhum_c1": ("plevelhum_batched", MEPS, 96, 12, b_plevelhum(1)),
         "plevelhum_c7": ("plevelhum_batched", MEPS, 96, 12, b_plevelhum(7)),
+        "hleveltemp_c3": ("hleveltemp_batched", MEPS, 96, 8, b_hlevel(["t"], ("kelvin", 3))),
+        "hlevelhum_c1": ("hlevelhum_batched", MEPS, 65, 12, b_hlevel(["t", "q"], ("celsius", 1))),
+        "hlevelhum_c5": ("hlevelhum_batched", MEPS, 65, 12, b_hlevel(["t", "q"], ("celsius", 5))),
         "aleveltemp_c3": ("aleveltemp_batched", MEPS, 96, 12, b_ew(["t", "p"], ("kelvin", 3))),
         "alevelhum_c1": ("alevelhum_batched", MEPS, 65, 16, b_ew(["t", "q", "p"], ("celsius", 1))),
         "alevelhum_c5": ("alevelhum_batched", MEPS, 65, 16, b_ew(["t", "q", "p"], ("celsius", 5))),
