@@ -41,7 +41,8 @@ struct EwArgs
   long long items;  // nfields * chunks
   int nfields;
   int chunks;       // items per field
-  int align0;       // (address of field 0, element 0) / 4 mod 4 -- identical for every array (W = 4 only)
+  int align0;       // (address of field 0, element 0) / 4 mod 4 -- identical for every per-field array (W = 4 only)
+  int scalar_mask;  // W = 4: inputs (bit k) shared by the batch whose alignment cannot follow the per-field arrays -> four 4-byte loads
   int nx;
   float undef;
   const FieldMeta* meta;
@@ -130,11 +131,18 @@ __device__ __forceinline__ void ew_load_group(const EwArgs<Op::NIN, Op::NOUT>& a
     for (int k = 0; k < Op::NIN; ++k) {
       const float* in = a.in[k] + ((unsigned long long)field * (unsigned)a.in_stride[k] + e);
       if constexpr (W == 4) {
-        const float4 q = *reinterpret_cast<const float4*>(in);
-        v[k][0] = q.x;
-        v[k][1] = q.y;
-        v[k][2] = q.z;
-        v[k][3] = q.w;
+        if ((a.scalar_mask >> k) & 1) { // warp-uniform: a grid-constant array (hybrid-level ps) next to odd-sized fields
+          v[k][0] = in[0];
+          v[k][1] = in[1];
+          v[k][2] = in[2];
+          v[k][3] = in[3];
+        } else {
+          const float4 q = *reinterpret_cast<const float4*>(in);
+          v[k][0] = q.x;
+          v[k][1] = q.y;
+          v[k][2] = q.z;
+          v[k][3] = q.w;
+        }
       } else {
         v[k][0] = in[0];
       }
@@ -398,14 +406,25 @@ bool launch_elementwise(Call& call, const Op& op, const float* const* in, const 
   constexpr int NIN = Op::NIN, NOUT = Op::NOUT;
   EwArgs<NIN, NOUT> a;
   bool vec = n >= 16;
-  const uintptr_t a0 = reinterpret_cast<uintptr_t>(in[0]) & 15;
+  // the vector path groups points by the alignment of the PER-FIELD arrays (taken from the first of them); an array shared
+  // by the batch cannot follow the per-field misalignment of odd-sized fields and is then read with 4-byte loads
+  uintptr_t a0 = reinterpret_cast<uintptr_t>(in[0]) & 15;
+  for (int k = NIN - 1; k >= 0; --k)
+    if (in_stride[k] == n)
+      a0 = reinterpret_cast<uintptr_t>(in[k]) & 15;
+  a.scalar_mask = 0;
   for (int k = 0; k < NIN; ++k) {
     a.in[k] = in[k];
     a.in_stride[k] = in_stride[k];
-    if ((reinterpret_cast<uintptr_t>(in[k]) & 15) != a0 || (a0 & 3))
+    const uintptr_t ak = reinterpret_cast<uintptr_t>(in[k]) & 15;
+    if ((ak & 3) || (a0 & 3))
       vec = false;
-    if (in_stride[k] != n && !(nfields == 1 || (n & 3) == 0))
-      vec = false; // a shared array cannot follow the per-field misalignment of the strided ones
+    if (in_stride[k] != n) {
+      if (ak != a0 || !(nfields == 1 || (n & 3) == 0))
+        a.scalar_mask |= 1 << k;
+    } else if (ak != a0) {
+      vec = false;
+    }
   }
   for (int k = 0; k < NOUT; ++k) {
     a.out[k] = out[k];
