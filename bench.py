@@ -43,7 +43,7 @@ BYTES_UNFUSED = {"aleveltemp": 12, "alevelhum_rh": 16, "alevelhum_td": 16, "alev
 BYTES_FUSED = 28
 # dram__bytes_read.sum + dram__bytes_write.sum of one fused-chain launch (65 levels), from the ncu --set full
 # capture committed under profiles/ (None until captured)
-TRAFFIC_NCU = 1798.8e6  # profiles/r01_ncu_full_chain_final_summary.csv: 791.7 MB read + 1007.1 MB written (algorithmic: 1846 MB)
+TRAFFIC_NCU = 1800.5e6  # profiles/r01_ncu_full_chain_final_summary.csv: 792.6 MB read + 1007.9 MB written (algorithmic: 1846 MB)
 
 
 def peaks():
@@ -342,7 +342,7 @@ def run_product(args):
     achieved = BYTES_FUSED * points_per_step / (kern_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "kernel": "ew_kernel<AlevelChainOpT<2, 2, 4>, 4> (fused chain)", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": TRAFFIC_NCU, "peak_source": peak_src, "algorithmic_bytes_per_point": BYTES_FUSED,
-                "kernel_ms": kern_ms, "note": "issue-bound, not HBM-bound: ~166 instructions per point (246 at the start of the round), 72 % issue-slot utilisation, DRAM 50 % busy (ncu, profiles/r01_ncu_full_chain_final_summary.csv; steps in profiles/r01_chain_tuning.txt)"}
+                "kernel_ms": kern_ms, "note": "issue-bound, not HBM-bound: ~157 instructions per point (246 at the start of the round), 67-72 % issue-slot utilisation, DRAM 50 % busy (ncu, profiles/r01_ncu_full_chain_final_summary.csv; steps in profiles/r01_chain_tuning.txt)"}
 
     # for the record: the same step as the UNFUSED reference call sequence (four batched launches, 60 B/point)
     gpu.begin_deferred()

@@ -93,6 +93,18 @@ struct op_item_rounds<Op, std::void_t<decltype(Op::ITEM_ROUNDS)>> : std::integra
 {
 };
 
+// Optional: `static constexpr bool SHARED_INPUT = true` -- some input may be ONE field shared by the whole batch (hybrid-level
+// ps).  Only such operators carry the per-input choice between a float4 load and four 4-byte loads (EwArgs::scalar_mask):
+// predicated-off loads still cost issue slots, so everybody else compiles the plain float4 load.
+template <class Op, class = void>
+struct op_shared_input : std::false_type
+{
+};
+template <class Op>
+struct op_shared_input<Op, std::void_t<decltype(Op::SHARED_INPUT)>> : std::integral_constant<bool, Op::SHARED_INPUT>
+{
+};
+
 template <class Op, int W>
 struct EwShape
 {
@@ -131,7 +143,7 @@ __device__ __forceinline__ void ew_load_group(const EwArgs<Op::NIN, Op::NOUT>& a
     for (int k = 0; k < Op::NIN; ++k) {
       const float* in = a.in[k] + ((unsigned long long)field * (unsigned)a.in_stride[k] + e);
       if constexpr (W == 4) {
-        if ((a.scalar_mask >> k) & 1) { // warp-uniform: a grid-constant array (hybrid-level ps) next to odd-sized fields
+        if (op_shared_input<Op>::value && ((a.scalar_mask >> k) & 1)) { // warp-uniform: a grid-constant array next to odd-sized fields
           v[k][0] = in[0];
           v[k][1] = in[1];
           v[k][2] = in[2];
@@ -420,8 +432,11 @@ bool launch_elementwise(Call& call, const Op& op, const float* const* in, const 
     if ((ak & 3) || (a0 & 3))
       vec = false;
     if (in_stride[k] != n) {
-      if (ak != a0 || !(nfields == 1 || (n & 3) == 0))
+      if (ak != a0 || !(nfields == 1 || (n & 3) == 0)) {
         a.scalar_mask |= 1 << k;
+        if (!op_shared_input<Op>::value)
+          vec = false;
+      }
     } else if (ak != a0) {
       vec = false;
     }

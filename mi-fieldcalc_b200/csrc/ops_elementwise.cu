@@ -75,6 +75,7 @@ struct PTempStreamOp
 template <int KIND>
 struct TempOp
 {
+  static constexpr bool SHARED_INPUT = (KIND == HLEVEL); // ps is one field for the whole batch
   static constexpr int NIN = (KIND == PLEVEL) ? 1 : 2, NOUT = 1, UNROLL = 2;
   static constexpr int NCOUNT = 1;
   static constexpr int MIN_BLOCKS = 4;
@@ -122,6 +123,7 @@ struct TempOp
 template <int KIND>
 struct TheOp
 {
+  static constexpr bool SHARED_INPUT = (KIND == HLEVEL); // ps is one field for the whole batch
   static constexpr int NIN = 3, NOUT = 1, UNROLL = 2;
   static constexpr int NCOUNT = 1;
   static constexpr int MIN_BLOCKS = 4;
@@ -149,6 +151,7 @@ struct TheOp
 template <int KIND>
 struct HumOp
 {
+  static constexpr bool SHARED_INPUT = (KIND == HLEVEL); // ps is one field for the whole batch
   static constexpr int NIN = (KIND == PLEVEL) ? 2 : 3, NOUT = 1, UNROLL = 2;
   static constexpr int NCOUNT = 1;
   static constexpr int MIN_BLOCKS = 4;
@@ -218,6 +221,7 @@ struct HumOp
 template <int KIND>
 struct DuctOp
 {
+  static constexpr bool SHARED_INPUT = (KIND == HLEVEL); // ps is one field for the whole batch
   static constexpr int NIN = 3, NOUT = 1, UNROLL = 2;
   static constexpr int NCOUNT = 1;
   static constexpr int MIN_BLOCKS = 4;
@@ -253,6 +257,7 @@ struct DuctOp
 template <int NCHK>
 struct KeepOrUndefOp
 {
+  static constexpr bool SHARED_INPUT = true;
   static constexpr int NIN = NCHK + 1, NOUT = 1, UNROLL = 2;
   static constexpr int NCOUNT = 1;
   static constexpr int MIN_BLOCKS = 5;
@@ -412,6 +417,7 @@ struct AlevelChainOpT
   static constexpr bool HAS_Q = (OUTS & (O_RH | O_TD | O_THE)) != 0; // q is an input
   static constexpr bool HAS_TAB = (OUTS & (O_RH | O_TD)) != 0;       // the saturation table is used
   static constexpr bool HAS_POW = (OUTS & (O_THETA | O_THE)) != 0;   // the Exner function is used
+  static constexpr bool SHARED_INPUT = (KIND == HLEVEL);
   static constexpr int ITEM_ROUNDS = J_;
   static constexpr int NIN = (HAS_Q ? 2 : 1) + (KIND != PLEVEL ? 1 : 0); // t, [q,] [p or ps]
   static constexpr int NOUT = ((OUTS & 1) ? 1 : 0) + ((OUTS & 2) ? 1 : 0) + ((OUTS & 4) ? 1 : 0) + ((OUTS & 8) ? 1 : 0);
