@@ -119,7 +119,53 @@ def test_fused_alevel_chain_full_size_batch(gpu, mask, flag):
     _chain_against_reference_calls(gpu, 949, 1069, 14, mask, flag, "celsius", (True,))
 
 
-def _chain_against_reference_calls(gpu, nx, ny, nf, mask, flag, unit, devices):
+@pytest.mark.parametrize("flag", [cases.ALL, cases.SOME])
+def test_fused_alevel_chain_values_at_the_edges_of_the_fast_path(gpu, flag):
+    """every combination of awkward t, q, p values -- the ends of the saturation table, the plausibility limits of the
+    branch-free path, zeros of both signs, subnormals, huge values, infinities, NaN, the undefined value -- must come out
+    exactly as from the reference's four calls (the fast path hands them to the IEEE redo)"""
+    _chain_against_reference_calls(gpu, 949, 23, 2, "none", flag, "celsius", (True,), edge_values=True)
+
+
+@pytest.mark.parametrize("flag", [cases.ALL, cases.SOME])
+def test_one_output_forms_at_the_edges_of_the_fast_path(gpu, flag):
+    """the single operators that run the fused chain's branch-free code (a / p / h-level temperature and humidity, T-input
+    modes) on the same awkward values, against the reference"""
+    arb = _arbiter()
+    combos = [(a, b, c) for a in EDGE_T for b in EDGE_Q for c in EDGE_P]
+    nx, ny = 119, 28
+    assert len(combos) == nx * ny
+    t, q, p = (np.array([c[k] for c in combos], np.float32).reshape(ny, nx) for k in range(3))
+    undef = float(cases.UNDEF)
+    calls = [("aleveltemp", (t, p, "kelvin", 3), 1e-5, 0.0), ("alevelhum", (t, q, p, "celsius", 1), 0.0, 0.0), ("alevelhum", (t, q, p, "celsius", 5), 0.0, 273.15),
+             ("alevelhum", (t, q, p, "kelvin", 9), 0.0, 273.15), ("hleveltemp", (t, p, 0.0, 1.0, "kelvin", 3), 1e-5, 0.0),
+             ("hleveltemp", (t, p, 50.0, 0.7, "kelvin", 3), 1e-5, 0.0), ("hlevelhum", (t, q, p, 0.0, 1.0, "celsius", 1), 0.0, 0.0),
+             ("hlevelhum", (t, q, p, 50.0, 0.7, "celsius", 5), 0.0, 273.15)]
+    for pv in (850.0, 2.0 ** -7, 0.0078, 2048.0, 1e-30, undef):
+        calls += [("plevelhum", (t, q, pv, "celsius", 1), 0.0, 0.0), ("plevelhum", (t, q, pv, "celsius", 7), 0.0, 273.15),
+                  ("plevelhum", (t, q, pv, "kelvin", 11), 0.0, 273.15)]
+    for name, args, rtol, floor in calls:
+        for device in (False, True):
+            res = []
+            for api, dev in ((gpu, device), (arb, False)):
+                o = np.full((ny, nx), cases.SENTINEL, np.float32)
+                f = np.array([flag], np.int32)
+                a = [(_to_device(x) if dev and isinstance(x, np.ndarray) else x) for x in args]
+                od = _to_device(o) if dev else o
+                ret = api.call(name, nx, ny, *a, od, f, undef)
+                res.append((ret, [od.cpu().numpy() if dev else od], int(f[0])))
+            case = cases.Case(name, [], [], None, cases.UNDEF, {})
+            case.floor = floor
+            problems = cases.compare(case, res[0], res[1], rtol=rtol)
+            assert not problems, "%s %s device=%s: %s" % (name, [x for x in args if not isinstance(x, np.ndarray)], device, problems)
+
+
+EDGE_T = [173.15, 173.1499, 173.2, 168.2, 373.14, 373.15, 373.2, 273.15, 0.0, -5.0, 1e-30, 3e38, np.inf, np.nan, float(cases.UNDEF), 127.9, 512.0]
+EDGE_Q = [0.0, -0.0, 1e-45, 1e-30, 7e-28, 1e-8, -1e-3, 0.5, 1e6, 1.1e6, 3e38, np.inf, np.nan, float(cases.UNDEF)]
+EDGE_P = [2.0 ** -7, 0.0078, 2047.9, 2048.0, 1e-30, 0.0, -0.0, -850.0, 1e-45, 3e38, np.inf, np.nan, float(cases.UNDEF), 1013.25]
+
+
+def _chain_against_reference_calls(gpu, nx, ny, nf, mask, flag, unit, devices, edge_values=False):
     arb = _arbiter()
     rng = np.random.default_rng(42)
     t = np.stack([cases.field(rng, "tk", nx, ny) for _ in range(nf)])
@@ -128,6 +174,18 @@ def _chain_against_reference_calls(gpu, nx, ny, nf, mask, flag, unit, devices):
     for a in (t, q, p):
         for k in range(nf):
             cases.apply_mask(rng, a[k], mask, cases.UNDEF)
+    if edge_values:
+        combos = [(a, b, c) for a in EDGE_T for b in EDGE_Q for c in EDGE_P]
+        assert len(combos) <= nx * ny
+        for k in range(nf):
+            for arr, col in ((t, 0), (q, 1), (p, 2)):
+                flat = arr[k].reshape(-1)
+                vals = np.array([c[col] for c in combos], np.float32)
+                if k == 1:  # second field: the same values scattered among ordinary ones (mixed warps)
+                    idx = rng.permutation(nx * ny)[:len(vals)] if col == 0 else idx
+                    flat[idx] = vals
+                else:
+                    flat[:len(vals)] = vals
     outs = [np.full((nf, ny, nx), cases.SENTINEL, np.float32) for _ in range(4)]
     fin = np.full(nf, flag, np.int32)
     fout = np.full((4, nf), -1, np.int32)
