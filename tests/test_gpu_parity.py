@@ -250,8 +250,12 @@ def _batched_case(name, nx, ny, nf, params, device):
 
 
 @pytest.mark.parametrize("device", [False, True])
-@pytest.mark.parametrize("name", sorted(matrix.STENCILS) + ["aleveltemp", "alevelhum", "fieldOPERfield", "windCooling", "vesselIcingOverland",
-                                                            "momentumXcoordinate"])
+@pytest.mark.parametrize("name", sorted(matrix.STENCILS) + ["aleveltemp", "alevelhum", "alevelthe", "alevelducting", "fieldOPERfield", "windCooling",
+                                                            "vesselIcingOverland", "momentumXcoordinate", "kIndex", "ductingIndex", "showalterIndex",
+                                                            "boydenIndex", "sweatIndex", "seaSoundSpeed", "cvtemp", "cvhum", "abshum", "underCooledRain",
+                                                            "plevelthe", "pleveldz2tmean", "plevelducting", "vectorabs", "pressure2FlightLevel",
+                                                            "minvalueFields", "maxvalueFieldConst", "absvalueField", "logField", "powerField",
+                                                            "replaceUndefined", "replaceDefined", "fieldOPERconstant", "constantOPERfield", "snow_in_cm"])
 def test_batched_equals_single_field_calls(gpu, name, device):
     """`<op>_batched` over nf stacked fields == nf reference calls, field by field (values, masks, flags);
     odd nx (fields of a batch are only 4-byte aligned) and nx % 4 == 0 (the float4 paths)"""
@@ -267,6 +271,69 @@ def test_batched_equals_single_field_calls(gpu, name, device):
                 outs = [(args[p][k].cpu().numpy() if device else args[p][k]) for p in out_pos]
                 problems = cases.compare(c, (1, outs, int(flags[k])), want, rtol=cases.TRANSCENDENTAL.get(name, 0.0))
                 assert not problems, "%s %s %dx%d field %d (%s): %s" % (name, params, nx, ny, k, c.params["mask"], "\n".join(problems))
+
+
+@pytest.mark.parametrize("device", [False, True])
+@pytest.mark.parametrize("name,params", [("hleveltemp", dict(unit="kelvin", compute=3)), ("hleveltemp", dict(unit="", compute=4)),
+                                         ("hlevelhum", dict(unit="celsius", compute=1)), ("hlevelhum", dict(unit="kelvin", compute=9)),
+                                         ("hlevelhum", dict(unit="celsius", compute=3)), ("hlevelthe", dict(compute=1)), ("hlevelducting", dict(compute=1)),
+                                         ("hlevelpressure", dict())])
+def test_hybrid_level_batches_share_the_surface_pressure(gpu, name, params, device):
+    """`hlevel*_batched`: per-field t / q, per-field alevel / blevel, ONE surface-pressure field for the whole batch.  With an
+    odd field size (949 x 9) the per-field arrays are only 4-byte aligned and the shared ps cannot follow their
+    misalignment: the float4 path reads it with 4-byte loads.  Field by field against single reference calls."""
+    arb = _arbiter()
+    spec = cases.SPECS[name]
+    nf = 7
+    levels = [(50.0, 0.7), (0.0, 1.0), (20.0, 0.1), (150.0, 0.0), (5.0, 0.95), (80.0, 0.5), (0.5, 0.999)]
+    variants = [("none", cases.ALL), ("bernoulli", cases.SOME), ("nan", cases.ALL), ("sparse", cases.SOME), ("none", cases.SOME), ("all", cases.SOME), ("nan", cases.SOME)]
+    for nx, ny in ((949, 9), (64, 19), (37, 23)):
+        singles = []
+        for k in range(nf):
+            mask, flag = variants[k]
+            singles.append(cases.build(name, nx, ny, seed=300 + k, flag_in=flag, mask=mask, alevel=levels[k][0], blevel=levels[k][1], **params))
+        # positions in the single-field argument list
+        pos, ps_pos, a_pos, b_pos = 0, None, None, None
+        for d in spec:
+            if isinstance(d, tuple) and d[0] == "in" and d[1] == "ps":
+                ps_pos = pos
+            if isinstance(d, tuple) and d[0] == "f" and d[1] == "alevel":
+                a_pos = pos
+            if isinstance(d, tuple) and d[0] == "f" and d[1] == "blevel":
+                b_pos = pos
+            pos += 1
+        for c in singles[1:]:  # one surface pressure for the batch (field 0's, with its mask pattern)
+            c.args[ps_pos] = singles[0].args[ps_pos]
+        args, out_pos, pos = [], [], 0
+        flags = np.array([c.args[c.flag_idx][0] for c in singles], np.int32)
+        for d in spec:
+            a0 = singles[0].args[pos]
+            if d == "ny":
+                args += [a0, nf]
+            elif d == "flag":
+                args.append(flags)
+            elif pos == ps_pos:
+                args.append(_to_device(a0) if device else a0)
+            elif pos == a_pos:
+                args.append(np.array([lv[0] for lv in levels], np.float32))
+            elif pos == b_pos:
+                args.append(np.array([lv[1] for lv in levels], np.float32))
+            elif d == "out" or (isinstance(d, tuple) and d[0] == "in"):
+                stacked = np.stack([c.args[pos] for c in singles])
+                stacked = _to_device(stacked) if device else stacked
+                if d == "out":
+                    out_pos.append(len(args))
+                args.append(stacked)
+            else:
+                args.append(a0)
+            pos += 1
+        r = gpu.call(name + "_batched", *args)
+        assert r == 1, (name, params, r, gpu.last_error())
+        for k, c in enumerate(singles):
+            want = cases.run(arb, c)
+            outs = [(args[p][k].cpu().numpy() if device else args[p][k]) for p in out_pos]
+            problems = cases.compare(c, (1, outs, int(flags[k])), want, rtol=cases.TRANSCENDENTAL.get(name, 0.0))
+            assert not problems, "%s %s %dx%d field %d (%s): %s" % (name, params, nx, ny, k, c.params["mask"], "\n".join(problems))
 
 
 @pytest.mark.parametrize("name", ["relvort", "divergence", "advection", "gradient", "jacobian", "ilevelgwind", "thermalFrontParameter", "shapiro2_filter",
