@@ -1044,4 +1044,37 @@ int fcb200_alevel_chain_batched(int nx, int ny, int nfields, const float* t, con
   return run(AlevelChainOpT<2, 2, 4, O_ALL>{tdconv});
 }
 
+int fcb200_hlevel_chain_batched(int nx, int ny, int nfields, const float* t, const float* q, const float* ps, const float* alevel, const float* blevel,
+                                const char* td_unit, float* theta, float* rh, float* td, float* thetae, const int* fDefinedIn, int* fDefinedOut,
+                                float undef)
+{ // = hleveltemp(c=3) + hlevelhum(c=1) + hlevelhum(c=5, unit) + hlevelthe(c=1) on the same inputs; p = alevel + blevel * ps with ONE surface
+  // pressure field for the batch (the MEPS layout: 65 hybrid levels above one ps): 24 bytes per point instead of the 28 of the a-level
+  // chain, which needs a pressure field per level
+  if (nfields > 0 && any_bad_hlevel(make_batch(nx, ny, nfields), alevel, blevel))
+    return 0; // FC.cc:1070, 1121, 1170
+  const int td_compute = hum_compute(5, td_unit);
+  EwJob<AlevelChainOpT<2, 2, 4, O_ALL, HLEVEL>> job;
+  job.nx = nx;
+  job.ny = ny;
+  job.nfields = nfields;
+  job.in[0] = t;
+  job.in[1] = q;
+  job.in[2] = ps;
+  job.per_field[0] = job.per_field[1] = true;
+  job.per_field[2] = false;
+  job.out[0] = theta;
+  job.out[1] = rh;
+  job.out[2] = td;
+  job.out[3] = thetae;
+  job.flags_in = fDefinedIn;
+  for (int o = 0; o < 4; ++o)
+    job.flags_out[o] = fDefinedOut + (size_t)o * (nfields > 0 ? nfields : 0);
+  job.undef = undef;
+  job.fill_meta = [&](int k, FieldMeta& m) {
+    m.a = alevel[k];
+    m.b = blevel[k];
+  };
+  return run_ew_job(AlevelChainOpT<2, 2, 4, O_ALL, HLEVEL>{(td_compute >= 9) ? H_T0 : 0.f}, job);
+}
+
 } // extern "C"

@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol():
 def test_every_single_field_entry_has_a_batched_twin():
     single = capi.parse_inc(os.path.join(capi.INCLUDE, "fcb200_api.inc"), "FC_FN")
     batched = capi.parse_inc(os.path.join(capi.INCLUDE, "fcb200_batched.inc"), "FCB_FN")
-    assert sorted(k + "_batched" for k in single) == sorted(k for k in batched if k != "alevel_chain_batched")
+    assert sorted(k + "_batched" for k in single) == sorted(k for k in batched if k not in ("alevel_chain_batched", "hlevel_chain_batched"))
 
 
 def test_oracle_and_reference_share_the_signature_list(oracle):

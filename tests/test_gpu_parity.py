@@ -127,6 +127,52 @@ def test_fused_alevel_chain_values_at_the_edges_of_the_fast_path(gpu, flag):
     _chain_against_reference_calls(gpu, 949, 23, 2, "none", flag, "celsius", (True,), edge_values=True)
 
 
+@pytest.mark.parametrize("mask,flag", [("none", cases.ALL), ("none", cases.SOME), ("bernoulli", cases.SOME), ("nan", cases.SOME), ("nan", cases.ALL)])
+@pytest.mark.parametrize("unit", ["celsius", "kelvin"])
+def test_fused_hlevel_chain_equals_four_reference_calls(gpu, mask, flag, unit):
+    """fcb200_hlevel_chain_batched == hleveltemp(c3) + hlevelhum(c1) + hlevelhum(c5/9) + hlevelthe(c1), level by level, with one
+    surface-pressure field for the batch (odd field size: the shared ps is read with 4-byte loads inside the float4 path)"""
+    arb = _arbiter()
+    nx, ny, nf = 949, 23, 6
+    rng = np.random.default_rng(7)
+    t = np.stack([cases.field(rng, "tk", nx, ny) for _ in range(nf)])
+    q = np.stack([cases.field(rng, "q", nx, ny) for _ in range(nf)])
+    ps = cases.field(rng, "ps", nx, ny)
+    for k in range(nf):
+        cases.apply_mask(rng, t[k], mask, cases.UNDEF)
+        cases.apply_mask(rng, q[k], mask, cases.UNDEF)
+    cases.apply_mask(rng, ps, mask, cases.UNDEF)
+    a = np.array([50.0, 0.0, 20.0, 150.0, 5.0, 0.5], np.float32)
+    b = np.array([0.7, 1.0, 0.1, 0.0, 0.95, 0.999], np.float32)
+    undef = float(cases.UNDEF)
+    for device in (False, True):
+        outs = [np.full((nf, ny, nx), cases.SENTINEL, np.float32) for _ in range(4)]
+        args = [t, q, ps] + outs
+        if device:
+            args = [_to_device(x) for x in args]
+        fin = np.full(nf, flag, np.int32)
+        fout = np.full((4, nf), -1, np.int32)
+        r = gpu.call("hlevel_chain_batched", nx, ny, nf, args[0], args[1], args[2], a, b, unit, args[3], args[4], args[5], args[6], fin, fout, undef)
+        assert r == 1, gpu.last_error()
+        got = [x.cpu().numpy() if device else x for x in args[3:]]
+        calls = [("hleveltemp", lambda k, o, f: (nx, ny, t[k], ps, float(a[k]), float(b[k]), "kelvin", 3, o, f, undef), 1e-5, 0.0),
+                 ("hlevelhum", lambda k, o, f: (nx, ny, t[k], q[k], ps, float(a[k]), float(b[k]), unit, 1, o, f, undef), 0.0, 0.0),
+                 ("hlevelhum", lambda k, o, f: (nx, ny, t[k], q[k], ps, float(a[k]), float(b[k]), unit, 5, o, f, undef), 0.0, 273.15),
+                 ("hlevelthe", lambda k, o, f: (nx, ny, t[k], q[k], ps, float(a[k]), float(b[k]), 1, o, f, undef), 1e-5, 0.0)]
+        for oi, (name, mk, rtol, floor) in enumerate(calls):
+            for k in range(nf):
+                o = np.full((ny, nx), cases.SENTINEL, np.float32)
+                f = np.array([flag], np.int32)
+                assert arb.call(name, *mk(k, o, f)) == 1
+                case = cases.Case(name, [], [], None, cases.UNDEF, {})
+                case.floor = floor
+                problems = cases.compare(case, (1, [got[oi][k]], int(fout[oi, k])), (1, [o], int(f[0])), rtol=rtol)
+                assert not problems, "output %d (%s) level %d device=%s: %s" % (oi, name, k, device, problems)
+    bad = b.copy()
+    bad[2] = 1.5  # one bad level rejects the batch (FC.cc:298-301)
+    assert gpu.call("hlevel_chain_batched", nx, ny, nf, t, q, ps, a, bad, unit, *outs, fin, fout, undef) == 0
+
+
 @pytest.mark.parametrize("flag", [cases.ALL, cases.SOME])
 def test_one_output_forms_at_the_edges_of_the_fast_path(gpu, flag):
     """the single operators that run the fused chain's branch-free code (a / p / h-level temperature and humidity, T-input

@@ -160,6 +160,14 @@ def main():
             return [nx, ny, nf, rnd(batch(grid, nf), 250, 300, False), c, len(c), compute, torch.zeros(batch(grid, nf), device=dev), np.zeros(nf, np.int32), UNDEF]
         return build
 
+    def b_hchain(grid, nf):
+        nx, ny = grid
+        eta = (np.arange(nf) % 65 + 0.5) / 65.0
+        a = (200.0 * (1 - eta) * eta * 2.0 + 10.0 * (1 - eta)).astype(np.float32)
+        b = (eta ** 1.5).astype(np.float32)
+        return [nx, ny, nf, rnd(batch(grid, nf), 215, 305), rnd(batch(grid, nf), 1e-6, 2e-2), rnd((ny, nx), 950, 1040), a, b, "celsius"] + \
+               [torch.empty(batch(grid, nf), device=dev) for _ in range(4)] + [np.full(nf, flag_in, np.int32), np.zeros(4 * nf, np.int32), UNDEF]
+
     icing6 = ["tc", "sst", "w", "w", "sal", "aice"]
     icing11 = ["sal", "wave", "w", "w", "tc", "rh01", "sst", "pmsl", "pw", "aice", "depth"]
     OPS = {
@@ -187,6 +195,7 @@ def main():
         "alevelthe_c1": ("alevelthe_batched", MEPS, 65, 16, b_ew(["t", "q", "p"], (1,))),
         "alevelducting_c1": ("alevelducting_batched", MEPS, 65, 16, b_ew(["t", "q", "p"], (1,))),
         "alevel_chain": ("alevel_chain_batched", MEPS, 65, 28, b_chain),
+        "hlevel_chain": ("hlevel_chain_batched", MEPS, 65, 24, b_hchain),
         "windCooling": ("windCooling_batched", MEPS, 65, 16, b_ew(["t", "w", "w"], (1,))),
         "fieldOPERfield_add": ("fieldOPERfield_batched", MEPS, 96, 12, b_ew(["any", "any"], (), lead=(1,))),
         "fieldOPERfield_div": ("fieldOPERfield_batched", MEPS, 96, 12, b_ew(["any", "any"], (), lead=(4,))),
