@@ -212,17 +212,16 @@ struct VectorAbsOp
   }
 };
 
-// pressure2FlightLevel, FC.cc:2311-2349; tables MC.h:87-89
-static __device__ __constant__ float c_plevel[16] = {1000, 925, 850, 800, 700, 500, 400, 300, 250, 200, 150, 100, 70, 50, 30, 10};
-static __device__ __constant__ float c_flevel[16] = {5, 25, 50, 65, 100, 185, 235, 300, 340, 385, 445, 530, 605, 675, 780, 1020};
-
+// pressure2FlightLevel, FC.cc:2311-2349; tables MC.h:87-89.  The level tables are read with a data-dependent index: from
+// constant memory that serialises per distinct index in a warp (0.22 of the roofline on white-noise pressures), so they are
+// staged in shared memory with the saturation table (USES_EWT = the engine's "stage the tables" switch).
 struct FlightLevelOp
 {
   static constexpr int NIN = 1, NOUT = 1, UNROLL = 2;
   static constexpr int NCOUNT = 1;
   static constexpr int MIN_BLOCKS = 4;
   static constexpr bool HEAVY = false;
-  static constexpr bool USES_EWT = false, USES_POW = false;
+  static constexpr bool USES_EWT = true, USES_POW = false;
   template <bool ALL>
   __device__ __forceinline__ void point(const float* in, float* out, const PointCtx& c, long long, unsigned* nundef) const
   {
@@ -233,12 +232,15 @@ struct FlightLevelOp
         p = 1000.f;
       if (p < 10.f)
         p = 10.f;
+      // k = 1 + the number of levels 1 .. 14 above p: the table decreases, so the reference's walk `while (k < nTab &&
+      // pLevelTable[k] > p) k++` stops exactly there (a NaN under ALL_DEFINED compares false everywhere: k = 1, as on the CPU)
       int k = 1;
-      while (k < nTab && c_plevel[k] > p) // (a NaN under ALL_DEFINED ends the walk at once, as on the CPU)
-        k++;
-      const float p0 = c_plevel[k - 1], p1 = c_plevel[k], f0 = c_flevel[k - 1], f1 = c_flevel[k];
-      const float ratio = (p - p0) / (p1 - p0);
-      out[0] = f0 + (f1 - f0) * ratio;
+#pragma unroll
+      for (int m = 1; m < nTab; ++m)
+        k += (c.tab.level[m].x > p) ? 1 : 0;
+      const float2 lo = c.tab.level[k - 1], hi = c.tab.level[k];
+      const float ratio = (p - lo.x) / (hi.x - lo.x);
+      out[0] = lo.y + (hi.y - lo.y) * ratio;
     } else {
       out[0] = c.undef;
       nundef[0] += 1;
