@@ -158,17 +158,34 @@ __global__ void __launch_bounds__(128) neighbour_windows_kernel(const float* __r
     if (compute == 2 || compute == 3)
       value = field[(i - range) + (size_t)(j - range) * nx];
     if (compute == 4) {
-      // ii-th smallest (0-based) by bitwise selection: at each bit, count the candidates (same prefix) with a 0 bit
+      // ii-th smallest (0-based) by bitwise selection: at each bit, count the candidates (same prefix) with a 0 bit.  Windows of
+      // up to 11 x 11 points are first copied (as keys) into a per-thread array: 32 passes over L1-resident local memory
+      // instead of 32 passes over the field.
+      constexpr int MAXW = 121;
+      unsigned keys[MAXW];
+      const int side = 2 * range + 1, count = side * side;
+      const bool local = count <= MAXW;
+      if (local) {
+        int n = 0;
+        for (int y = j - range; y <= j + range; ++y)
+          for (int x = i - range; x <= i + range; ++x)
+            keys[n++] = order_key(field[x + (size_t)y * nx]);
+      }
       unsigned prefix = 0, mask = 0;
       int k = ii;
       for (int bit = 31; bit >= 0; --bit) {
         const unsigned b = 1u << bit;
         int zeros = 0;
-        for (int y = j - range; y <= j + range; ++y)
-          for (int x = i - range; x <= i + range; ++x) {
-            const unsigned key = order_key(field[x + (size_t)y * nx]);
-            zeros += ((key & mask) == prefix && !(key & b)) ? 1 : 0;
-          }
+        if (local) {
+          for (int n = 0; n < count; ++n)
+            zeros += ((keys[n] & mask) == prefix && !(keys[n] & b)) ? 1 : 0;
+        } else {
+          for (int y = j - range; y <= j + range; ++y)
+            for (int x = i - range; x <= i + range; ++x) {
+              const unsigned key = order_key(field[x + (size_t)y * nx]);
+              zeros += ((key & mask) == prefix && !(key & b)) ? 1 : 0;
+            }
+        }
         if (k >= zeros) {
           k -= zeros;
           prefix |= b;
