@@ -299,28 +299,77 @@ struct HPressureOp
   }
 };
 
-// windCooling (FC.cc:2209-2221); the reference never updates the flag
+// windCooling (FC.cc:2209-2221); the reference never updates the flag.  Same construction as the fused alevel chain: a
+// branch-free path for plausible winds (2^-100 <= u*u + v*v < 2^100: the square root and the power need no range guards, the
+// double constants come from the constant bank), the four points of a float4 group in one basic block, and a non-inlined
+// redo with the ordinary operators for calm (u = v = 0), NaN, infinite or absurd winds.  The temperature needs no test: it only
+// enters double arithmetic that behaves identically for every bit pattern.
 struct WindCoolingOp
 {
   static constexpr int NIN = 3, NOUT = 1, UNROLL = 2;
   static constexpr int NCOUNT = 0;
-  static constexpr int MIN_BLOCKS = 4;
+  static constexpr int MIN_BLOCKS = 3;
   static constexpr bool HEAVY = false;
   static constexpr bool USES_EWT = false, USES_POW = true;
+  static constexpr bool QUAD = true;
   float tconv;
+
+  __device__ __forceinline__ static float chill(float tc, float ffpow)
+  { // FC.cc:2214-2216
+    const double* K = dev::c_dconst;
+    float d = (float)(K[2] + K[3] * (double)tc - K[4] * (double)ffpow + K[5] * (double)tc * (double)ffpow);
+    if (d > 0.f)
+      d = 0.f;
+    return d;
+  }
+
+  __device__ __noinline__ static float ieee(float tc, float u, float v, const dev::PowTable& pw)
+  {
+    const float ff = (float)((double)dev::absval(u, v) * 3.6);
+    return chill(tc, pw.pow<dev::POW_WINDCHILL>(ff));
+  }
+
+  __device__ __forceinline__ bool fast(float tc, float u, float v, const dev::PowTable& pw, float& d) const
+  {
+    const float s = u * u + v * v;
+    const bool plausible = __float_as_uint(s) - 0x0d800000u < 0x64000000u; // 2^-100 <= s < 2^100
+    const float ff = (float)((double)dev::sqrt_midrange(s) * dev::c_dconst[1]);
+    d = chill(tc, pw.pow_normal<dev::POW_WINDCHILL>(ff));
+    return plausible;
+  }
+
   template <bool ALL>
   __device__ __forceinline__ void point(const float* in, float* out, const PointCtx& c, long long, unsigned*) const
   {
-    if (ALL || (is_def(in[0], c.undef) && is_def(in[1], c.undef) && is_def(in[2], c.undef))) {
-      const float tc = in[0] - tconv;
-      const float ff = (float)((double)dev::absval(in[1], in[2]) * 3.6);
-      const float ffpow = c.pw.pow<dev::POW_WINDCHILL>(ff);
-      float d = (float)(13.12 + 0.6215 * (double)tc - 11.37 * (double)ffpow + 0.3965 * (double)tc * (double)ffpow);
-      if ((double)d > 0.)
-        d = 0.f;
-      out[0] = d;
-    } else
-      out[0] = c.undef;
+    const bool def = ALL || (is_def(in[0], c.undef) && is_def(in[1], c.undef) && is_def(in[2], c.undef));
+    const float tc = in[0] - tconv;
+    float d;
+    if (!fast(tc, in[1], in[2], c.pw, d) && def)
+      d = ieee(tc, in[1], in[2], c.pw);
+    out[0] = def ? d : c.undef;
+  }
+
+  template <bool ALL>
+  __device__ __forceinline__ void quad(const float (*in)[4], float (*out)[4], const PointCtx& c, unsigned*) const
+  {
+    float d[4];
+    unsigned bad = 0, defined = 0;
+#pragma unroll
+    for (int w = 0; w < 4; ++w) {
+      const bool def = ALL || (is_def(in[0][w], c.undef) && is_def(in[1][w], c.undef) && is_def(in[2][w], c.undef));
+      defined |= def ? (1u << w) : 0u;
+      if (!fast(in[0][w] - tconv, in[1][w], in[2][w], c.pw, d[w]) && def)
+        bad |= 1u << w;
+    }
+    if (bad) {
+#pragma unroll
+      for (int w = 0; w < 4; ++w)
+        if (bad & (1u << w))
+          d[w] = ieee(in[0][w] - tconv, in[1][w], in[2][w], c.pw);
+    }
+#pragma unroll
+    for (int w = 0; w < 4; ++w)
+      out[0][w] = (defined & (1u << w)) ? d[w] : c.undef;
   }
 };
 

@@ -206,6 +206,33 @@ def test_one_output_forms_at_the_edges_of_the_fast_path(gpu, flag):
             assert not problems, "%s %s device=%s: %s" % (name, [x for x in args if not isinstance(x, np.ndarray)], device, problems)
 
 
+@pytest.mark.parametrize("flag", [cases.ALL, cases.SOME])
+def test_wind_cooling_at_the_edges_of_the_fast_path(gpu, flag):
+    """calm, tiny, huge, infinite, NaN and undefined winds (the branch-free path hands them to the ordinary operators)"""
+    arb = _arbiter()
+    undef = float(cases.UNDEF)
+    w = [0.0, -0.0, 1e-45, 1e-30, 6.2e-16, 6.3e-16, 8.8e-16, 8.9e-16, 1e-8, 0.5, -7.25, 30.0, 7.9e14, 8.0e14, 1.1e15, 1.2e15, 3e38, np.inf, -np.inf, np.nan, undef]
+    tt = [253.15, 273.15, -40.0, 0.0, 1e30, np.inf, np.nan, undef]
+    combos = [(a, b, c) for a in tt for b in w for c in w]
+    nx, ny = 63, 56
+    assert len(combos) == nx * ny
+    t, u, v = (np.array([c[k] for c in combos], np.float32).reshape(ny, nx) for k in range(3))
+    for compute in (1, 2):
+        for device in (False, True):
+            res = []
+            for api, dev in ((gpu, device), (arb, False)):
+                o = np.full((ny, nx), cases.SENTINEL, np.float32)
+                f = np.array([flag], np.int32)
+                a = [(_to_device(x) if dev else x) for x in (t, u, v)]
+                od = _to_device(o) if dev else o
+                ret = api.call("windCooling", nx, ny, a[0], a[1], a[2], compute, od, f, undef)
+                res.append((ret, [od.cpu().numpy() if dev else od], int(f[0])))
+            case = cases.Case("windCooling", [], [], None, cases.UNDEF, {})
+            case.floor = 13.12
+            problems = cases.compare(case, res[0], res[1], rtol=1e-5)
+            assert not problems, "compute=%d device=%s: %s" % (compute, device, problems)
+
+
 EDGE_T = [173.15, 173.1499, 173.2, 168.2, 373.14, 373.15, 373.2, 273.15, 0.0, -5.0, 1e-30, 3e38, np.inf, np.nan, float(cases.UNDEF), 127.9, 512.0]
 EDGE_Q = [0.0, -0.0, 1e-45, 1e-30, 7e-28, 1e-8, -1e-3, 0.5, 1e6, 1.1e6, 3e38, np.inf, np.nan, float(cases.UNDEF)]
 EDGE_P = [2.0 ** -7, 0.0078, 2047.9, 2048.0, 1e-30, 0.0, -0.0, -850.0, 1e-45, 3e38, np.inf, np.nan, float(cases.UNDEF), 1013.25]
