@@ -454,7 +454,7 @@ struct MomentumOp
 //
 // The same code serves the four operators on their own (aleveltemp c3, alevelhum c1, alevelhum c5/9, alevelthe c1):
 // OUTS selects which outputs exist, everything an absent output would need is compiled out.
-enum : unsigned { O_THETA = 1, O_RH = 2, O_TD = 4, O_THE = 8, O_ALL = 15 };
+enum : unsigned { O_THETA = 1, O_RH = 2, O_TD = 4, O_THE = 8, O_ALL = 15, O_THESAT = 16 /* *leveltemp c4: T -> theta_e,sat (FC.cc:196-205) */ };
 
 // KIND = PLEVEL: the pressure is the field's scalar (FieldMeta::a) instead of a third input field -- plevelhum.
 // KIND = HLEVEL: the last input is the surface pressure, p = alevel + blevel * ps with the field's FieldMeta::a, ::b
@@ -464,12 +464,12 @@ template <int U_, int MB_, int J_ = 1, unsigned OUTS = O_ALL, int KIND = ALEVEL>
 struct AlevelChainOpT
 {
   static constexpr bool HAS_Q = (OUTS & (O_RH | O_TD | O_THE)) != 0; // q is an input
-  static constexpr bool HAS_TAB = (OUTS & (O_RH | O_TD)) != 0;       // the saturation table is used
-  static constexpr bool HAS_POW = (OUTS & (O_THETA | O_THE)) != 0;   // the Exner function is used
+  static constexpr bool HAS_TAB = (OUTS & (O_RH | O_TD | O_THESAT)) != 0; // the saturation table is used
+  static constexpr bool HAS_POW = (OUTS & (O_THETA | O_THE)) != 0 || ((OUTS & O_THESAT) != 0 && KIND != PLEVEL); // the Exner function is used
   static constexpr bool SHARED_INPUT = (KIND == HLEVEL);
   static constexpr int ITEM_ROUNDS = J_;
   static constexpr int NIN = (HAS_Q ? 2 : 1) + (KIND != PLEVEL ? 1 : 0); // t, [q,] [p or ps]
-  static constexpr int NOUT = ((OUTS & 1) ? 1 : 0) + ((OUTS & 2) ? 1 : 0) + ((OUTS & 4) ? 1 : 0) + ((OUTS & 8) ? 1 : 0);
+  static constexpr int NOUT = ((OUTS & 1) ? 1 : 0) + ((OUTS & 2) ? 1 : 0) + ((OUTS & 4) ? 1 : 0) + ((OUTS & 8) ? 1 : 0) + ((OUTS & 16) ? 1 : 0);
   static constexpr int UNROLL = U_;
   static constexpr int NCOUNT = NOUT;
   static constexpr int MIN_BLOCKS = MB_;
@@ -480,17 +480,21 @@ struct AlevelChainOpT
 
   struct Raw
   {
-    float theta, rh, td, the;
+    float theta, rh, td, the, thesat;
     bool edef; // the saturation-table lookup of t was in range
   };
 
   // The reference's expressions with ordinary IEEE operators: correct for ANY bit pattern.  Not inlined: it
   // only runs for points whose inputs fail the plausibility test of `fast` (undefined values that flow into
   // the arithmetic, NaN, zero or negative pressure, ...).
-  __device__ __noinline__ static void ieee_raw(float t, float q, float p, const dev::EwtTable& tab, const dev::PowTable& pw, float tdconv, Raw& r)
+  // `pi_field` = the field's pi = cp * (p/p0)^kappa evaluated on the host (KIND == PLEVEL, O_THESAT only)
+  __device__ __noinline__ static void ieee_raw(float t, float q, float p, const dev::EwtTable& tab, const dev::PowTable& pw, float tdconv, float pi_field,
+                                               Raw& r)
   {
+    float pi = pi_field;
     if (HAS_POW) {
       const float pidcp = dev::pidcp_from_p(pw, p);
+      pi = K_CP * pidcp;
       if (OUTS & O_THETA)
         r.theta = t / pidcp;
       if (OUTS & O_THE)
@@ -501,6 +505,8 @@ struct AlevelChainOpT
       const dev::Ewt e(t - K_T0);
       const float et = e.value(tab);
       const float qsat = dev::K_EPS * et / p;
+      if (OUTS & O_THESAT)
+        r.thesat = (K_CP * t + K_XLH * qsat) / pi;
       if (OUTS & O_RH)
         r.rh = (float)(100. * (double)q / (double)qsat);
       if (OUTS & O_TD) {
@@ -511,10 +517,12 @@ struct AlevelChainOpT
     }
   }
   // `out` of the non-inlined call lives in local memory; copying it keeps the caller's own Raw in registers
-  __device__ __forceinline__ static void ieee(float t, float q, float p, const dev::EwtTable& tab, const dev::PowTable& pw, float tdconv, Raw& r)
+  __device__ __forceinline__ static void ieee(float t, float q, float p, const dev::EwtTable& tab, const dev::PowTable& pw, float tdconv, float pi_field,
+                                              Raw& r)
   {
     Raw tmp;
-    ieee_raw(t, q, p, tab, pw, tdconv, tmp);
+    ieee_raw(t, q, p, tab, pw, tdconv, pi_field, tmp);
+    r.thesat = tmp.thesat;
     r.theta = tmp.theta;
     r.rh = tmp.rh;
     r.td = tmp.td;
@@ -529,8 +537,9 @@ struct AlevelChainOpT
   // no classification of its argument and the table indices need no clamps -- straight-line code without a single
   // branch, so the compiler interleaves the four points of a thread.  Returns false (after computing harmless
   // garbage) when the inputs are not plausible; the caller then redoes the point with `ieee`.
-  __device__ __forceinline__ bool fast(float t, float q, float p, const dev::EwtTable& tab, const dev::PowTable& pw, Raw& r) const
+  __device__ __forceinline__ bool fast(float t, float q, float p, float pi_field, const dev::EwtTable& tab, const dev::PowTable& pw, Raw& r) const
   {
+    float pi = pi_field;
     bool plausible = __float_as_uint(p) - 0x3c000000u < 0x09000000u; // 2^-7 <= p < 2^11
     if (HAS_Q) {
       const unsigned uq = __float_as_uint(q) & 0x7fffffffu;
@@ -541,6 +550,7 @@ struct AlevelChainOpT
 
     if (HAS_POW) {
       const float pidcp = pw.pow_normal<dev::POW_KAPPA>(p * dev::K_P0INV); // FC.cc:308-311
+      pi = K_CP * pidcp;                                                    // FC.cc:313-316
       if (OUTS & O_THETA)
         r.theta = dev::div_midrange(t, pidcp);
       if (OUTS & O_THE)
@@ -553,6 +563,8 @@ struct AlevelChainOpT
       const float2 e = tab.e[l];
       const float et = e.x + e.y * (x - (float)l); // MC.h:78
       const float qsat = dev::div_midrange(dev::K_EPS * et, p);
+      if (OUTS & O_THESAT)
+        r.thesat = dev::div_midrange(K_CP * t + K_XLH * qsat, pi); // t_thesat, FC.cc:196-205 (pi in [36, 1240] for plausible p)
       // (Evaluating this double quotient in float-float arithmetic with a midpoint test -- no conversions, no FP64 -- was
       // measured 8 % SLOWER: the test's dependent chain costs more than the nine DFMA it replaces.)
       if (OUTS & O_RH)
@@ -608,6 +620,11 @@ struct AlevelChainOpT
       out[o] = ok_the ? r.the : undef;
       nundef[o++] += ok_the ? 0u : 1u;
     }
+    if (OUTS & O_THESAT) { // *leveltemp c4 tests t and p (ps), then the table range
+      const bool ok = ok_theta && r.edef;
+      out[o] = ok ? r.thesat : undef;
+      nundef[o++] += ok ? 0u : 1u;
+    }
   }
 
   // For a field that is not ALL_DEFINED: an undefined q only reaches outputs that are undefined anyway, so it is
@@ -624,12 +641,12 @@ struct AlevelChainOpT
   {
     const bool dq = ALL || !HAS_Q || is_def(q, c.undef);
     const float qe = dq ? q : 0.f;
-    const bool plausible = fast(t, qe, level_p(praw, c), c.tab, c.pw, r);
+    const bool plausible = fast(t, qe, level_p(praw, c), c.m.b, c.tab, c.pw, r);
     if (ALL)
       return plausible;
     const bool dt = is_def(t, c.undef), dp = KIND == PLEVEL || is_def(praw, c.undef);
-    const bool hum_live = HAS_TAB && dq && (KIND != HLEVEL || praw != c.undef);
-    const bool live = dt && (hum_live || (HAS_POW && dp && ((OUTS & O_THETA) || dq)));
+    const bool hum_live = (OUTS & (O_RH | O_TD)) != 0 && dq && (KIND != HLEVEL || praw != c.undef);
+    const bool live = dt && (hum_live || ((OUTS & O_THESAT) && dp) || (HAS_POW && dp && ((OUTS & O_THETA) || dq)));
     return plausible || !live;
   }
 
@@ -641,7 +658,7 @@ struct AlevelChainOpT
   {
     Raw r;
     if (!eval<ALL>(in[0], Q(in), P(in), c, r))
-      ieee(in[0], Q(in), level_p(P(in), c), c.tab, c.pw, tdconv, r);
+      ieee(in[0], Q(in), level_p(P(in), c), c.tab, c.pw, tdconv, c.m.b, r);
     finish<ALL>(in[0], Q(in), P(in), r, c, out, nundef);
   }
 
@@ -660,7 +677,7 @@ struct AlevelChainOpT
 #pragma unroll
       for (int w = 0; w < 4; ++w)
         if (bad & (1u << w))
-          ieee(in[0][w], HAS_Q ? in[1][w] : 0.f, level_p(KIND == PLEVEL ? 0.f : in[NIN - 1][w], c), c.tab, c.pw, tdconv, r[w]);
+          ieee(in[0][w], HAS_Q ? in[1][w] : 0.f, level_p(KIND == PLEVEL ? 0.f : in[NIN - 1][w], c), c.tab, c.pw, tdconv, c.m.b, r[w]);
     }
 #pragma unroll
     for (int w = 0; w < 4; ++w) {
@@ -692,11 +709,14 @@ int impl_pleveltemp(const Batch& b, const float* tinp, const float* p, const cha
     PTempStreamOp op{compute};
     return run_elementwise(b, op, in, pf, tout, fDefined, undef, FLAG_UNCHANGED, [&](int k, FieldMeta& m) { m.a = host_pidcp(p[k]); });
   }
-  TempOp<PLEVEL> op{compute};
-  return run_elementwise(b, op, in, pf, tout, fDefined, undef, FLAG_FROM_COUNT, [&](int k, FieldMeta& m) {
+  auto fill = [&](int k, FieldMeta& m) {
     m.a = p[k];
     m.b = host_pidcp(p[k]) * H_CP;
-  });
+  };
+  if (compute == 4) // T -> theta_e,sat: one-output form of the fused chain's branch-free code
+    return run_elementwise(b, AlevelChainOpT<2, 3, 2, O_THESAT, PLEVEL>{0.f}, in, pf, tout, fDefined, undef, FLAG_FROM_COUNT, fill);
+  TempOp<PLEVEL> op{compute};
+  return run_elementwise(b, op, in, pf, tout, fDefined, undef, FLAG_FROM_COUNT, fill);
 }
 
 int impl_plevelhum(const Batch& b, const float* t, const float* huminp, const float* p, const char* unit, int compute, float* humout, int* fDefined,
@@ -758,6 +778,8 @@ int impl_xleveltemp(const Batch& b, const float* tinp, const float* pin, const f
   // roofline): 3 CTAs/SM 0.65, 4 CTAs/SM 0.63, 2 CTAs/SM 0.56; the generic TempOp 0.55.
   if (compute == 3)
     return run_elementwise(b, AlevelChainOpT<2, 3, 2, O_THETA, KIND>{0.f}, in, pf, tout, fDefined, undef, FLAG_FROM_COUNT, levels);
+  if (compute == 4)
+    return run_elementwise(b, AlevelChainOpT<2, 3, 2, O_THESAT, KIND>{0.f}, in, pf, tout, fDefined, undef, FLAG_FROM_COUNT, levels);
   TempOp<KIND> op{compute};
   return run_elementwise(b, op, in, pf, tout, fDefined, undef, FLAG_FROM_COUNT, levels);
 }
