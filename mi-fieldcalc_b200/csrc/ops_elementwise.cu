@@ -713,8 +713,8 @@ int impl_pleveltemp(const Batch& b, const float* tinp, const float* p, const cha
     m.a = p[k];
     m.b = host_pidcp(p[k]) * H_CP;
   };
-  if (compute == 4) // T -> theta_e,sat: one-output form of the fused chain's branch-free code
-    return run_elementwise(b, AlevelChainOpT<2, 3, 2, O_THESAT, PLEVEL>{0.f}, in, pf, tout, fDefined, undef, FLAG_FROM_COUNT, fill);
+  if (compute == 4) // T -> theta_e,sat: one-output form of the fused chain's branch-free code (0.49 -> 0.61; 4 CTAs/SM beats 3 and 5)
+    return run_elementwise(b, AlevelChainOpT<2, 4, 2, O_THESAT, PLEVEL>{0.f}, in, pf, tout, fDefined, undef, FLAG_FROM_COUNT, fill);
   TempOp<PLEVEL> op{compute};
   return run_elementwise(b, op, in, pf, tout, fDefined, undef, FLAG_FROM_COUNT, fill);
 }
