@@ -28,6 +28,13 @@ __device__ __forceinline__ float rh_fraction(float rh100)
   return dev::clamp_rh((float)(0.01 * (double)rh100));
 }
 
+// the same without a branch (selects): a NaN stays a NaN, exactly like clamp_rh
+__device__ __forceinline__ float rh_fraction_select(float rh100)
+{
+  const float rh = (float)(0.01 * (double)rh100);
+  return rh < dev::K_RHMIN ? dev::K_RHMIN : (rh > dev::K_RHMAX ? dev::K_RHMAX : rh);
+}
+
 __device__ __forceinline__ float ms2knots(float ff)
 { // MC.h:53, 132-135
   return (float)((double)ff * (3600.0 / 1852.0));
@@ -67,35 +74,86 @@ struct KIndexOp
   }
 };
 
-// ductingIndex, FC.cc:816-870
+// ductingIndex, FC.cc:816-870.  Same construction as CvHumOp: branch-free inside the saturation table, redo outside.
 struct DuctingIndexOp
 {
-  static constexpr int NIN = 2, NOUT = 1, UNROLL = 1;
+  static constexpr int NIN = 2, NOUT = 1, UNROLL = 2;
   static constexpr int NCOUNT = 1;
-  static constexpr int MIN_BLOCKS = 4;
+  static constexpr int MIN_BLOCKS = 3;
   static constexpr bool HEAVY = false;
   static constexpr bool USES_EWT = true, USES_POW = false;
+  static constexpr bool QUAD = true;
   float tconvert;
+
+  __device__ __noinline__ static bool exact(float t, float h, float tconvert, const dev::EwtTable& tab, float& r)
+  {
+    const float bduct = (float)3.8e+5;
+    const float rh = rh_fraction(h);
+    const float tk = t * tconvert;
+    const dev::Ewt e(tk - K_T0);
+    if (!e.defined)
+      return false;
+    const float et = e.value(tab);
+    const float etd = et * rh;
+    const float tdk = e.inverse(tab, etd) + K_T0;
+    r = bduct * (et / (tk * tk) - etd / (tdk * tdk));
+    return true;
+  }
+
+  __device__ __forceinline__ bool fast(float t, float h, const dev::EwtTable& tab, float& r) const
+  {
+    const float bduct = (float)3.8e+5;
+    const float rh = rh_fraction_select(h);
+    const float tk = t * tconvert;
+    const dev::EwtFast e(tab, tk - K_T0);
+    const float etd = e.et * rh;
+    const float tdk = e.dewpoint(tab, etd) + K_T0; // in [168, 373] for a plausible position: both squares are mid-range divisors
+    r = bduct * (dev::div_midrange(e.et, tk * tk) - dev::div_midrange(etd, tdk * tdk));
+    return e.plausible;
+  }
+
   template <bool ALL>
   __device__ __forceinline__ void point(const float* in, float* out, const PointCtx& c, long long, unsigned* nundef) const
   {
-    const float bduct = (float)3.8e+5;
-    bool ok = ALL || (is_def(in[0], c.undef) && is_def(in[1], c.undef));
-    float r = c.undef;
-    if (ok) {
-      const float rh = rh_fraction(in[1]);
-      const float tk = in[0] * tconvert;
-      const dev::Ewt e(tk - K_T0);
-      ok = e.defined;
-      if (ok) {
-        const float et = e.value(c.tab);
-        const float etd = et * rh;
-        const float tdk = e.inverse(c.tab, etd) + K_T0;
-        r = bduct * (et / (tk * tk) - etd / (tdk * tdk));
-      }
+    const bool def = ALL || (is_def(in[0], c.undef) && is_def(in[1], c.undef));
+    float r;
+    bool ok = fast(in[0], in[1], c.tab, r);
+    if (!ok && def)
+      ok = exact(in[0], in[1], tconvert, c.tab, r);
+    const bool good = def && ok;
+    out[0] = good ? r : c.undef;
+    nundef[0] += good ? 0u : 1u;
+  }
+
+  template <bool ALL>
+  __device__ __forceinline__ void quad(const float (*in)[4], float (*out)[4], const PointCtx& c, unsigned* nundef) const
+  {
+    float r[4];
+    unsigned okm = 0, defm = 0;
+#pragma unroll
+    for (int w = 0; w < 4; ++w) {
+      const bool def = ALL || (is_def(in[0][w], c.undef) && is_def(in[1][w], c.undef));
+      defm |= def ? (1u << w) : 0u;
+      okm |= fast(in[0][w], in[1][w], c.tab, r[w]) ? (1u << w) : 0u;
     }
-    out[0] = r;
-    nundef[0] += ok ? 0u : 1u;
+    const unsigned redo = defm & ~okm;
+    if (redo) {
+#pragma unroll
+      for (int w = 0; w < 4; ++w)
+        if (redo & (1u << w)) {
+          float v = 0.f;
+          if (exact(in[0][w], in[1][w], tconvert, c.tab, v)) {
+            okm |= 1u << w;
+            r[w] = v;
+          }
+        }
+    }
+#pragma unroll
+    for (int w = 0; w < 4; ++w) {
+      const bool good = ((defm & okm) >> w) & 1u;
+      out[0][w] = good ? r[w] : c.undef;
+      nundef[0] += good ? 0u : 1u;
+    }
   }
 };
 
@@ -266,39 +324,96 @@ struct CopyOp
   }
 };
 
-// cvhum, FC.cc:1738-1817
+// cvhum, FC.cc:1738-1817.  Branch-free path for temperatures inside the saturation table (dev::EwtFast), the four points of a
+// float4 group in one basic block; points outside the table (their result is undefined or, just below -100 degC, extrapolated)
+// are redone by `exact`, the reference's expressions with the ordinary operators.
 struct CvHumOp
 {
-  static constexpr int NIN = 2, NOUT = 1, UNROLL = 1;
+  static constexpr int NIN = 2, NOUT = 1, UNROLL = 2;
   static constexpr int NCOUNT = 1;
-  static constexpr int MIN_BLOCKS = 4;
+  static constexpr int MIN_BLOCKS = 3;
   static constexpr bool HEAVY = false;
   static constexpr bool USES_EWT = true, USES_POW = false;
+  static constexpr bool QUAD = true;
   int compute; // 1..5 after the unit remap
   float tconv, tdconv, unit_scale;
+
+  // returns "the table lookups were in range"; r = the value
+  __device__ __noinline__ static bool exact(float t, float h, int compute, float tconv, float tdconv, float unit_scale, const dev::EwtTable& tab, float& r)
+  {
+    const dev::Ewt e(t - tconv);
+    if (compute <= 3) {
+      if (!e.defined)
+        return false;
+      const float et = e.value(tab);
+      const float rh = rh_fraction(h);
+      r = e.inverse(tab, rh * et) + tdconv;
+      return true;
+    }
+    const dev::Ewt e2(h - tconv);
+    if (!(e.defined && e2.defined))
+      return false;
+    r = (e2.value(tab) / e.value(tab)) * unit_scale;
+    return true;
+  }
+
+  __device__ __forceinline__ bool fast(float t, float h, const dev::EwtTable& tab, float& r) const
+  {
+    const dev::EwtFast e(tab, t - tconv);
+    if (compute <= 3) {
+      r = e.dewpoint(tab, rh_fraction_select(h) * e.et) + tdconv;
+      return e.plausible;
+    }
+    const dev::EwtFast e2(tab, h - tconv);
+    r = dev::div_midrange(e2.et, e.et) * unit_scale; // both in [3.4e-5, 1013.25]
+    return e.plausible && e2.plausible;
+  }
+
+  template <bool ALL>
+  __device__ __forceinline__ void finish(bool def, bool ok, float r, float undef, float& out, unsigned* nundef) const
+  {
+    const bool good = def && ok;
+    out = good ? r : undef;
+    nundef[0] += good ? 0u : 1u;
+  }
+
   template <bool ALL>
   __device__ __forceinline__ void point(const float* in, float* out, const PointCtx& c, long long, unsigned* nundef) const
   {
-    bool ok = ALL || (is_def(in[0], c.undef) && is_def(in[1], c.undef));
-    float r = c.undef;
-    if (ok) {
-      const dev::Ewt e(in[0] - tconv);
-      if (compute <= 3) {
-        ok = e.defined;
-        if (ok) {
-          const float et = e.value(c.tab);
-          const float rh = rh_fraction(in[1]);
-          r = e.inverse(c.tab, rh * et) + tdconv;
-        }
-      } else {
-        const dev::Ewt e2(in[1] - tconv);
-        ok = e.defined && e2.defined;
-        if (ok)
-          r = (e2.value(c.tab) / e.value(c.tab)) * unit_scale;
-      }
+    const bool def = ALL || (is_def(in[0], c.undef) && is_def(in[1], c.undef));
+    float r;
+    bool ok = fast(in[0], in[1], c.tab, r);
+    if (!ok && def)
+      ok = exact(in[0], in[1], compute, tconv, tdconv, unit_scale, c.tab, r);
+    finish<ALL>(def, ok, r, c.undef, out[0], nundef);
+  }
+
+  template <bool ALL>
+  __device__ __forceinline__ void quad(const float (*in)[4], float (*out)[4], const PointCtx& c, unsigned* nundef) const
+  {
+    float r[4];
+    unsigned okm = 0, defm = 0;
+#pragma unroll
+    for (int w = 0; w < 4; ++w) {
+      const bool def = ALL || (is_def(in[0][w], c.undef) && is_def(in[1][w], c.undef));
+      defm |= def ? (1u << w) : 0u;
+      okm |= fast(in[0][w], in[1][w], c.tab, r[w]) ? (1u << w) : 0u;
     }
-    out[0] = r;
-    nundef[0] += ok ? 0u : 1u;
+    const unsigned redo = defm & ~okm;
+    if (redo) {
+#pragma unroll
+      for (int w = 0; w < 4; ++w)
+        if (redo & (1u << w)) {
+          float v = 0.f;
+          if (exact(in[0][w], in[1][w], compute, tconv, tdconv, unit_scale, c.tab, v)) {
+            okm |= 1u << w;
+            r[w] = v;
+          }
+        }
+    }
+#pragma unroll
+    for (int w = 0; w < 4; ++w)
+      finish<ALL>((defm >> w) & 1u, (okm >> w) & 1u, r[w], c.undef, out[0][w], nundef);
   }
 };
 

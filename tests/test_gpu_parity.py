@@ -234,6 +234,33 @@ def test_wind_cooling_at_the_edges_of_the_fast_path(gpu, flag):
             assert not problems, "compute=%d device=%s: %s" % (compute, device, problems)
 
 
+@pytest.mark.parametrize("flag", [cases.ALL, cases.SOME])
+def test_table_diagnostics_at_the_edges_of_the_fast_path(gpu, flag):
+    """cvhum and ductingIndex: temperatures at and beyond both ends of the saturation table, humidities of every kind"""
+    arb = _arbiter()
+    undef = float(cases.UNDEF)
+    hum = [0.0, -0.0, -5.0, 1e-30, 1.9, 2.0, 2.1, 55.0, 99.99, 100.0, 100.01, 1e6, 3e38, np.inf, -np.inf, np.nan, undef, 173.2, 273.15, 372.9, 25.0]
+    combos = [(a, b) for a in EDGE_T + [-100.0, -100.01, -105.0, -104.99, 99.99, 100.0, 20.0] for b in hum]
+    nx, ny = 21, 24
+    assert len(combos) == nx * ny
+    t, h = (np.array([c[k] for c in combos], np.float32).reshape(ny, nx) for k in range(2))
+    calls = [("cvhum", (t, h, "kelvin", 1)), ("cvhum", (t, h, "celsius", 1)), ("cvhum", (t, h, "", 3)), ("cvhum", (t, h, "", 4)), ("cvhum", (t, h, "1", 5)),
+             ("ductingIndex", (t, h, 850.0, 1)), ("ductingIndex", (t, h, 700.0, 2))]
+    for name, args in calls:
+        for device in (False, True):
+            res = []
+            for api, dev in ((gpu, device), (arb, False)):
+                o = np.full((ny, nx), cases.SENTINEL, np.float32)
+                f = np.array([flag], np.int32)
+                a = [(_to_device(x) if dev and isinstance(x, np.ndarray) else x) for x in args]
+                od = _to_device(o) if dev else o
+                ret = api.call(name, nx, ny, *a, od, f, undef)
+                res.append((ret, [od.cpu().numpy() if dev else od], int(f[0])))
+            case = cases.Case(name, [], [], None, cases.UNDEF, {})
+            problems = cases.compare(case, res[0], res[1], rtol=0.0)
+            assert not problems, "%s %s device=%s: %s" % (name, args[2:], device, problems)
+
+
 EDGE_T = [173.15, 173.1499, 173.2, 168.2, 373.14, 373.15, 373.2, 273.15, 0.0, -5.0, 1e-30, 3e38, np.inf, np.nan, float(cases.UNDEF), 127.9, 512.0]
 EDGE_Q = [0.0, -0.0, 1e-45, 1e-30, 7e-28, 1e-8, -1e-3, 0.5, 1e6, 1.1e6, 3e38, np.inf, np.nan, float(cases.UNDEF)]
 EDGE_P = [2.0 ** -7, 0.0078, 2047.9, 2048.0, 1e-30, 0.0, -0.0, -850.0, 1e-45, 3e38, np.inf, np.nan, float(cases.UNDEF), 1013.25]
