@@ -40,37 +40,93 @@ __device__ __forceinline__ float ms2knots(float ff)
   return (float)((double)ff * (3600.0 / 1852.0));
 }
 
-// kIndex, FC.cc:745-814
+// kIndex, FC.cc:745-814.  Same construction as CvHumOp: branch-free inside the saturation table (both levels), redo outside.
 struct KIndexOp
 {
-  static constexpr int NIN = 5, NOUT = 1, UNROLL = 1;
+  static constexpr int NIN = 5, NOUT = 1, UNROLL = 2;
   static constexpr int NCOUNT = 1;
-  static constexpr int MIN_BLOCKS = 3;
+  static constexpr int MIN_BLOCKS = 2;
   static constexpr bool HEAVY = false;
   static constexpr bool USES_EWT = true, USES_POW = false;
+  static constexpr bool QUAD = true;
   float cvt500, cvt700, cvt850;
+
+  __device__ __noinline__ static bool exact(float t500, float t700, float rh700, float t850, float rh850, float cvt500, float cvt700, float cvt850,
+                                            const dev::EwtTable& tab, float& r)
+  {
+    const float rh8 = rh_fraction(rh850);
+    const float tc850 = cvt850 * t850 - K_T0;
+    const float tc700 = cvt700 * t700 - K_T0;
+    const dev::Ewt e850(tc850), e700(tc700);
+    if (!(e850.defined && e700.defined))
+      return false;
+    const float tdc850 = e850.inverse(tab, e850.value(tab) * rh8);
+    const float rh7 = rh_fraction(rh700);
+    const float tdc700 = e700.inverse(tab, e700.value(tab) * rh7);
+    const float tc500 = cvt500 * t500 - K_T0;
+    r = (tc850 + tdc850) - (tc700 - tdc700) - tc500;
+    return true;
+  }
+
+  __device__ __forceinline__ bool fast(float t500, float t700, float rh700, float t850, float rh850, const dev::EwtTable& tab, float& r) const
+  {
+    const float tc850 = cvt850 * t850 - K_T0;
+    const float tc700 = cvt700 * t700 - K_T0;
+    const dev::EwtFast e850(tab, tc850), e700(tab, tc700);
+    const float tdc850 = e850.dewpoint(tab, e850.et * rh_fraction_select(rh850));
+    const float tdc700 = e700.dewpoint(tab, e700.et * rh_fraction_select(rh700));
+    const float tc500 = cvt500 * t500 - K_T0;
+    r = (tc850 + tdc850) - (tc700 - tdc700) - tc500;
+    return e850.plausible && e700.plausible;
+  }
+
+  template <bool ALL>
+  __device__ __forceinline__ bool defined(float a, float b, float c2, float d, float e, float undef) const
+  {
+    return ALL || (is_def(a, undef) && is_def(b, undef) && is_def(c2, undef) && is_def(d, undef) && is_def(e, undef));
+  }
+
   template <bool ALL>
   __device__ __forceinline__ void point(const float* in, float* out, const PointCtx& c, long long, unsigned* nundef) const
   {
-    const float t500 = in[0], t700 = in[1], rh700 = in[2], t850 = in[3], rh850 = in[4];
-    bool ok = ALL || (is_def(t500, c.undef) && is_def(t700, c.undef) && is_def(rh700, c.undef) && is_def(t850, c.undef) && is_def(rh850, c.undef));
-    float r = c.undef;
-    if (ok) {
-      const float rh8 = rh_fraction(rh850);
-      const float tc850 = cvt850 * t850 - K_T0;
-      const float tc700 = cvt700 * t700 - K_T0;
-      const dev::Ewt e850(tc850), e700(tc700);
-      ok = e850.defined && e700.defined;
-      if (ok) {
-        const float tdc850 = e850.inverse(c.tab, e850.value(c.tab) * rh8);
-        const float rh7 = rh_fraction(rh700);
-        const float tdc700 = e700.inverse(c.tab, e700.value(c.tab) * rh7);
-        const float tc500 = cvt500 * t500 - K_T0;
-        r = (tc850 + tdc850) - (tc700 - tdc700) - tc500;
-      }
+    const bool def = defined<ALL>(in[0], in[1], in[2], in[3], in[4], c.undef);
+    float r;
+    bool ok = fast(in[0], in[1], in[2], in[3], in[4], c.tab, r);
+    if (!ok && def)
+      ok = exact(in[0], in[1], in[2], in[3], in[4], cvt500, cvt700, cvt850, c.tab, r);
+    const bool good = def && ok;
+    out[0] = good ? r : c.undef;
+    nundef[0] += good ? 0u : 1u;
+  }
+
+  template <bool ALL>
+  __device__ __forceinline__ void quad(const float (*in)[4], float (*out)[4], const PointCtx& c, unsigned* nundef) const
+  {
+    float r[4];
+    unsigned okm = 0, defm = 0;
+#pragma unroll
+    for (int w = 0; w < 4; ++w) {
+      defm |= defined<ALL>(in[0][w], in[1][w], in[2][w], in[3][w], in[4][w], c.undef) ? (1u << w) : 0u;
+      okm |= fast(in[0][w], in[1][w], in[2][w], in[3][w], in[4][w], c.tab, r[w]) ? (1u << w) : 0u;
     }
-    out[0] = r;
-    nundef[0] += ok ? 0u : 1u;
+    const unsigned redo = defm & ~okm;
+    if (redo) {
+#pragma unroll
+      for (int w = 0; w < 4; ++w)
+        if (redo & (1u << w)) {
+          float v = 0.f;
+          if (exact(in[0][w], in[1][w], in[2][w], in[3][w], in[4][w], cvt500, cvt700, cvt850, c.tab, v)) {
+            okm |= 1u << w;
+            r[w] = v;
+          }
+        }
+    }
+#pragma unroll
+    for (int w = 0; w < 4; ++w) {
+      const bool good = ((defm & okm) >> w) & 1u;
+      out[0][w] = good ? r[w] : c.undef;
+      nundef[0] += good ? 0u : 1u;
+    }
   }
 };
 

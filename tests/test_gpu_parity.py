@@ -236,7 +236,7 @@ def test_wind_cooling_at_the_edges_of_the_fast_path(gpu, flag):
 
 @pytest.mark.parametrize("flag", [cases.ALL, cases.SOME])
 def test_table_diagnostics_at_the_edges_of_the_fast_path(gpu, flag):
-    """cvhum and ductingIndex: temperatures at and beyond both ends of the saturation table, humidities of every kind"""
+    """cvhum, ductingIndex and kIndex: temperatures at and beyond both ends of the saturation table, humidities of every kind"""
     arb = _arbiter()
     undef = float(cases.UNDEF)
     hum = [0.0, -0.0, -5.0, 1e-30, 1.9, 2.0, 2.1, 55.0, 99.99, 100.0, 100.01, 1e6, 3e38, np.inf, -np.inf, np.nan, undef, 173.2, 273.15, 372.9, 25.0]
@@ -245,7 +245,8 @@ def test_table_diagnostics_at_the_edges_of_the_fast_path(gpu, flag):
     assert len(combos) == nx * ny
     t, h = (np.array([c[k] for c in combos], np.float32).reshape(ny, nx) for k in range(2))
     calls = [("cvhum", (t, h, "kelvin", 1)), ("cvhum", (t, h, "celsius", 1)), ("cvhum", (t, h, "", 3)), ("cvhum", (t, h, "", 4)), ("cvhum", (t, h, "1", 5)),
-             ("ductingIndex", (t, h, 850.0, 1)), ("ductingIndex", (t, h, 700.0, 2))]
+             ("ductingIndex", (t, h, 850.0, 1)), ("ductingIndex", (t, h, 700.0, 2)),
+             ("kIndex", (t, t[::-1].copy(), h, t, h[:, ::-1].copy(), 500.0, 700.0, 850.0, 1)), ("kIndex", (t, t, h, t[::-1].copy(), h, 500.0, 700.0, 850.0, 2))]
     for name, args in calls:
         for device in (False, True):
             res = []
@@ -258,7 +259,7 @@ def test_table_diagnostics_at_the_edges_of_the_fast_path(gpu, flag):
                 res.append((ret, [od.cpu().numpy() if dev else od], int(f[0])))
             case = cases.Case(name, [], [], None, cases.UNDEF, {})
             problems = cases.compare(case, res[0], res[1], rtol=0.0)
-            assert not problems, "%s %s device=%s: %s" % (name, args[2:], device, problems)
+            assert not problems, "%s %s device=%s: %s" % (name, [x for x in args if not isinstance(x, np.ndarray)], device, problems)
 
 
 EDGE_T = [173.15, 173.1499, 173.2, 168.2, 373.14, 373.15, 373.2, 273.15, 0.0, -5.0, 1e-30, 3e38, np.inf, np.nan, float(cases.UNDEF), 127.9, 512.0]
