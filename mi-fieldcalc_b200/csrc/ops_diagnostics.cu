@@ -135,7 +135,7 @@ struct DuctingIndexOp
 {
   static constexpr int NIN = 2, NOUT = 1, UNROLL = 2;
   static constexpr int NCOUNT = 1;
-  static constexpr int MIN_BLOCKS = 3;
+  static constexpr int MIN_BLOCKS = 4;
   static constexpr bool HEAVY = false;
   static constexpr bool USES_EWT = true, USES_POW = false;
   static constexpr bool QUAD = true;
@@ -387,7 +387,7 @@ struct CvHumOp
 {
   static constexpr int NIN = 2, NOUT = 1, UNROLL = 2;
   static constexpr int NCOUNT = 1;
-  static constexpr int MIN_BLOCKS = 3;
+  static constexpr int MIN_BLOCKS = 4;
   static constexpr bool HEAVY = false;
   static constexpr bool USES_EWT = true, USES_POW = false;
   static constexpr bool QUAD = true;
