@@ -650,6 +650,26 @@ struct AlevelChainOpT
     return plausible || !live;
   }
 
+  // The IEEE redo of one point.  If the field is not ALL_DEFINED and p (ps) itself is undefined, theta and theta_e are undefined
+  // whatever the arithmetic says and only RH / Td -- into which the undefined p flows (FC.cc:1429) -- are needed: that redo is
+  // the humidity-only instantiation, without the Exner function.
+  template <bool ALL>
+  __device__ __forceinline__ void redo(float t, float q, float praw, const PointCtx& c, Raw& r) const
+  {
+    constexpr unsigned HUM = OUTS & (O_RH | O_TD);
+    if constexpr (!ALL && HUM != 0 && HUM != OUTS && KIND != PLEVEL) {
+      if (!is_def(praw, c.undef)) {
+        typename AlevelChainOpT<U_, MB_, J_, HUM, KIND>::Raw h;
+        AlevelChainOpT<U_, MB_, J_, HUM, KIND>::ieee_raw(t, q, level_p(praw, c), c.tab, c.pw, tdconv, c.m.b, h);
+        r.rh = h.rh;
+        r.td = h.td;
+        r.edef = h.edef;
+        return;
+      }
+    }
+    ieee(t, q, level_p(praw, c), c.tab, c.pw, tdconv, c.m.b, r);
+  }
+
   __device__ __forceinline__ static float Q(const float* in) { return HAS_Q ? in[1] : 0.f; }
   __device__ __forceinline__ static float P(const float* in) { return KIND == PLEVEL ? 0.f : in[NIN - 1]; }
 
@@ -658,7 +678,7 @@ struct AlevelChainOpT
   {
     Raw r;
     if (!eval<ALL>(in[0], Q(in), P(in), c, r))
-      ieee(in[0], Q(in), level_p(P(in), c), c.tab, c.pw, tdconv, c.m.b, r);
+      redo<ALL>(in[0], Q(in), P(in), c, r);
     finish<ALL>(in[0], Q(in), P(in), r, c, out, nundef);
   }
 
@@ -677,7 +697,7 @@ struct AlevelChainOpT
 #pragma unroll
       for (int w = 0; w < 4; ++w)
         if (bad & (1u << w))
-          ieee(in[0][w], HAS_Q ? in[1][w] : 0.f, level_p(KIND == PLEVEL ? 0.f : in[NIN - 1][w], c), c.tab, c.pw, tdconv, c.m.b, r[w]);
+          redo<ALL>(in[0][w], HAS_Q ? in[1][w] : 0.f, KIND == PLEVEL ? 0.f : in[NIN - 1][w], c, r[w]);
     }
 #pragma unroll
     for (int w = 0; w < 4; ++w) {
