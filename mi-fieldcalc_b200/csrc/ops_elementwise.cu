@@ -454,7 +454,11 @@ struct MomentumOp
 //
 // The same code serves the four operators on their own (aleveltemp c3, alevelhum c1, alevelhum c5/9, alevelthe c1):
 // OUTS selects which outputs exist, everything an absent output would need is compiled out.
-enum : unsigned { O_THETA = 1, O_RH = 2, O_TD = 4, O_THE = 8, O_ALL = 15, O_THESAT = 16 /* *leveltemp c4: T -> theta_e,sat (FC.cc:196-205) */ };
+enum : unsigned {
+  O_THETA = 1, O_RH = 2, O_TD = 4, O_THE = 8, O_ALL = 15,
+  O_THESAT = 16, // *leveltemp c4: T -> theta_e,sat (FC.cc:196-205)
+  O_TDRH = 32    // *levelhum T, RH(%) -> Td (a/h-level c7/11, p-level c5/9; tk_rh_td, FC.cc:254-267): the second input is RH, p is not used
+};
 
 // KIND = PLEVEL: the pressure is the field's scalar (FieldMeta::a) instead of a third input field -- plevelhum.
 // KIND = HLEVEL: the last input is the surface pressure, p = alevel + blevel * ps with the field's FieldMeta::a, ::b
@@ -463,13 +467,15 @@ enum : unsigned { O_THETA = 1, O_RH = 2, O_TD = 4, O_THE = 8, O_ALL = 15, O_THES
 template <int U_, int MB_, int J_ = 1, unsigned OUTS = O_ALL, int KIND = ALEVEL>
 struct AlevelChainOpT
 {
-  static constexpr bool HAS_Q = (OUTS & (O_RH | O_TD | O_THE)) != 0; // q is an input
-  static constexpr bool HAS_TAB = (OUTS & (O_RH | O_TD | O_THESAT)) != 0; // the saturation table is used
+  static constexpr bool HAS_Q = (OUTS & (O_RH | O_TD | O_THE | O_TDRH)) != 0; // q (or RH) is an input
+  static constexpr bool HAS_TAB = (OUTS & (O_RH | O_TD | O_THESAT | O_TDRH)) != 0; // the saturation table is used
+  static constexpr bool USES_P = (OUTS & ~O_TDRH) != 0;                          // the pressure enters the arithmetic
+  static constexpr bool Q_IS_RATIO = (OUTS & (O_RH | O_TD | O_THE)) != 0;          // q is divided / divides: its range matters
   static constexpr bool HAS_POW = (OUTS & (O_THETA | O_THE)) != 0 || ((OUTS & O_THESAT) != 0 && KIND != PLEVEL); // the Exner function is used
   static constexpr bool SHARED_INPUT = (KIND == HLEVEL);
   static constexpr int ITEM_ROUNDS = J_;
   static constexpr int NIN = (HAS_Q ? 2 : 1) + (KIND != PLEVEL ? 1 : 0); // t, [q,] [p or ps]
-  static constexpr int NOUT = ((OUTS & 1) ? 1 : 0) + ((OUTS & 2) ? 1 : 0) + ((OUTS & 4) ? 1 : 0) + ((OUTS & 8) ? 1 : 0) + ((OUTS & 16) ? 1 : 0);
+  static constexpr int NOUT = ((OUTS & 1) ? 1 : 0) + ((OUTS & 2) ? 1 : 0) + ((OUTS & 4) ? 1 : 0) + ((OUTS & 8) ? 1 : 0) + ((OUTS & 16) ? 1 : 0) + ((OUTS & 32) ? 1 : 0);
   static constexpr int UNROLL = U_;
   static constexpr int NCOUNT = NOUT;
   static constexpr int MIN_BLOCKS = MB_;
@@ -480,7 +486,7 @@ struct AlevelChainOpT
 
   struct Raw
   {
-    float theta, rh, td, the, thesat;
+    float theta, rh, td, the, thesat, tdrh;
     bool edef; // the saturation-table lookup of t was in range
   };
 
@@ -513,6 +519,10 @@ struct AlevelChainOpT
         const float rhc = dev::clamp_rh(q / qsat);
         r.td = e.inverse(tab, rhc * et) + tdconv;
       }
+      if (OUTS & O_TDRH) {
+        const float rhc = dev::clamp_rh((float)(0.01 * (double)q));
+        r.tdrh = e.inverse(tab, rhc * et) + tdconv;
+      }
       r.edef = e.defined;
     }
   }
@@ -523,6 +533,7 @@ struct AlevelChainOpT
     Raw tmp;
     ieee_raw(t, q, p, tab, pw, tdconv, pi_field, tmp);
     r.thesat = tmp.thesat;
+    r.tdrh = tmp.tdrh;
     r.theta = tmp.theta;
     r.rh = tmp.rh;
     r.td = tmp.td;
@@ -540,8 +551,8 @@ struct AlevelChainOpT
   __device__ __forceinline__ bool fast(float t, float q, float p, float pi_field, const dev::EwtTable& tab, const dev::PowTable& pw, Raw& r) const
   {
     float pi = pi_field;
-    bool plausible = __float_as_uint(p) - 0x3c000000u < 0x09000000u; // 2^-7 <= p < 2^11
-    if (HAS_Q) {
+    bool plausible = !USES_P || (__float_as_uint(p) - 0x3c000000u < 0x09000000u); // 2^-7 <= p < 2^11
+    if (Q_IS_RATIO) {
       const unsigned uq = __float_as_uint(q) & 0x7fffffffu;
       plausible = plausible && ((uq - 0x12800000u < 0x37000000u) || __float_as_uint(q) == 0u); // 2^-90 <= |q| < 2^20, or +0
     }
@@ -569,9 +580,9 @@ struct AlevelChainOpT
       // measured 8 % SLOWER: the test's dependent chain costs more than the nine DFMA it replaces.)
       if (OUTS & O_RH)
         r.rh = (float)dev::div_midrange(100. * (double)q, (double)qsat); // FC.cc:229
-      if (OUTS & O_TD) {
-        const float rq = dev::div_midrange(q, qsat);
-        const float rhc = rq < dev::K_RHMIN ? dev::K_RHMIN : (rq > dev::K_RHMAX ? dev::K_RHMAX : rq); // clamp_rh, FC.cc:186-194
+      // dew point from a relative humidity (a NaN stays a NaN through the selects, like clamp_rh, FC.cc:186-194)
+      auto dewpoint = [&](float rh) {
+        const float rhc = rh < dev::K_RHMIN ? dev::K_RHMIN : (rh > dev::K_RHMAX ? dev::K_RHMAX : rh);
         const float etd = rhc * et;
         // Ewt::inverse (MC.cc:37-45) with the bucket table; 0.02 * ewt[0] < 2^-15 lands below the first bucket -> index 0
         int b = (int)(__float_as_uint(etd) >> 21) - dev::EWT_LUT0;
@@ -583,8 +594,12 @@ struct AlevelChainOpT
         const float y = (float)ll + dev::div_midrange(etd - e2.x, e2.y);
         // (float)(-100. + (double)y * 5.): for |y| < 64 the double expression is exact (5y has at most 27
         // significant bits and -100 + 5y at most 7 + 46) or, for |y| < 2^-23, rounds to -100 either way -> one fmaf
-        r.td = fmaf(5.f, y, -100.f) + tdconv;
-      }
+        return fmaf(5.f, y, -100.f) + tdconv;
+      };
+      if (OUTS & O_TD)
+        r.td = dewpoint(dev::div_midrange(q, qsat));
+      if (OUTS & O_TDRH)
+        r.tdrh = dewpoint((float)(0.01 * (double)q));
     }
     r.edef = true;
     return plausible;
@@ -620,6 +635,11 @@ struct AlevelChainOpT
       out[o] = ok_the ? r.the : undef;
       nundef[o++] += ok_the ? 0u : 1u;
     }
+    if (OUTS & O_TDRH) { // alevelhum c7/11 test `p != undef` although p is not used (FC.cc:1429); hlevelhum and plevelhum do not
+      const bool ok = dt && dq && r.edef && (KIND != ALEVEL || all || p != undef);
+      out[o] = ok ? r.tdrh : undef;
+      nundef[o++] += ok ? 0u : 1u;
+    }
     if (OUTS & O_THESAT) { // *leveltemp c4 tests t and p (ps), then the table range
       const bool ok = ok_theta && r.edef;
       out[o] = ok ? r.thesat : undef;
@@ -646,7 +666,8 @@ struct AlevelChainOpT
       return plausible;
     const bool dt = is_def(t, c.undef), dp = KIND == PLEVEL || is_def(praw, c.undef);
     const bool hum_live = (OUTS & (O_RH | O_TD)) != 0 && dq && (KIND != HLEVEL || praw != c.undef);
-    const bool live = dt && (hum_live || ((OUTS & O_THESAT) && dp) || (HAS_POW && dp && ((OUTS & O_THETA) || dq)));
+    const bool live = dt && (hum_live || ((OUTS & O_TDRH) && dq && (KIND != ALEVEL || praw != c.undef)) || ((OUTS & O_THESAT) && dp) ||
+                             (HAS_POW && dp && ((OUTS & O_THETA) || dq)));
     return plausible || !live;
   }
 
@@ -766,6 +787,8 @@ int impl_plevelhum(const Batch& b, const float* t, const float* huminp, const fl
     return run_elementwise(b, AlevelChainOpT<2, 3, 2, O_RH, PLEVEL>{0.f}, in, pf, humout, fDefined, undef, FLAG_FROM_COUNT, fill);
   if (to_ah[compute] == 5 || to_ah[compute] == 9)
     return run_elementwise(b, AlevelChainOpT<2, 3, 2, O_TD, PLEVEL>{(compute >= 9) ? H_T0 : 0.f}, in, pf, humout, fDefined, undef, FLAG_FROM_COUNT, fill);
+  if (to_ah[compute] == 7 || to_ah[compute] == 11) // T, RH -> Td (p-level numbering 5 / 9): p is not used, not even when it is undefined
+    return run_elementwise(b, AlevelChainOpT<2, 3, 2, O_TDRH, PLEVEL>{(compute >= 9) ? H_T0 : 0.f}, in, pf, humout, fDefined, undef, FLAG_FROM_COUNT, fill);
   return run_elementwise(b, op, in, pf, humout, fDefined, undef, FLAG_FROM_COUNT, [&](int k, FieldMeta& m) {
     if (p[k] == undef && !rh_td)
       m.all |= 2; // fillUndef -> every point undefined -> NONE_DEFINED (FC.cc:429-432)
@@ -850,6 +873,8 @@ int impl_xlevelhum(const Batch& b, const float* t, const float* huminp, const fl
     return run_elementwise(b, AlevelChainOpT<2, 3, 2, O_RH, KIND>{0.f}, in, pf, humout, fDefined, undef, FLAG_FROM_COUNT, levels);
   if (compute == 5 || compute == 9)
     return run_elementwise(b, AlevelChainOpT<2, 3, 2, O_TD, KIND>{(compute >= 9) ? H_T0 : 0.f}, in, pf, humout, fDefined, undef, FLAG_FROM_COUNT, levels);
+  if (compute == 7 || compute == 11) // T, RH -> Td
+    return run_elementwise(b, AlevelChainOpT<2, 3, 2, O_TDRH, KIND>{(compute >= 9) ? H_T0 : 0.f}, in, pf, humout, fDefined, undef, FLAG_FROM_COUNT, levels);
   return run_elementwise(b, op, in, pf, humout, fDefined, undef, FLAG_FROM_COUNT, levels);
 }
 

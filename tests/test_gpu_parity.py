@@ -187,10 +187,13 @@ def test_one_output_forms_at_the_edges_of_the_fast_path(gpu, flag):
              ("alevelhum", (t, q, p, "kelvin", 9), 0.0, 273.15), ("hleveltemp", (t, p, 0.0, 1.0, "kelvin", 3), 1e-5, 0.0),
              ("hleveltemp", (t, p, 50.0, 0.7, "kelvin", 3), 1e-5, 0.0), ("hlevelhum", (t, q, p, 0.0, 1.0, "celsius", 1), 0.0, 0.0),
              ("hlevelhum", (t, q, p, 50.0, 0.7, "celsius", 5), 0.0, 273.15)]
+    calls += [("alevelhum", (t, q, p, "celsius", 7), 0.0, 273.15), ("alevelhum", (t, q, p, "kelvin", 11), 0.0, 273.15),
+              ("hlevelhum", (t, q, p, 50.0, 0.7, "celsius", 7), 0.0, 273.15), ("hlevelhum", (t, q, p, 0.0, 1.0, "kelvin", 11), 0.0, 273.15)]
     calls += [("aleveltemp", (t, p, "", 4), 1e-5, 0.0), ("hleveltemp", (t, p, 0.0, 1.0, "", 4), 1e-5, 0.0), ("hleveltemp", (t, p, 50.0, 0.7, "", 4), 1e-5, 0.0)]
     for pv in (850.0, 2.0 ** -7, 0.0078, 2048.0, 1e-30, undef):
         calls += [("plevelhum", (t, q, pv, "celsius", 1), 0.0, 0.0), ("plevelhum", (t, q, pv, "celsius", 7), 0.0, 273.15),
-                  ("plevelhum", (t, q, pv, "kelvin", 11), 0.0, 273.15), ("pleveltemp", (t, pv, "", 4), 0.0, 0.0)]
+                  ("plevelhum", (t, q, pv, "kelvin", 11), 0.0, 273.15), ("pleveltemp", (t, pv, "", 4), 0.0, 0.0),
+                  ("plevelhum", (t, q, pv, "celsius", 5), 0.0, 273.15), ("plevelhum", (t, q, pv, "kelvin", 9), 0.0, 273.15)]
     for name, args, rtol, floor in calls:
         for device in (False, True):
             res = []

@@ -192,6 +192,7 @@ def main():
         "aleveltemp_c3": ("aleveltemp_batched", MEPS, 96, 12, b_ew(["t", "p"], ("kelvin", 3))),
         "alevelhum_c1": ("alevelhum_batched", MEPS, 65, 16, b_ew(["t", "q", "p"], ("celsius", 1))),
         "alevelhum_c5": ("alevelhum_batched", MEPS, 65, 16, b_ew(["t", "q", "p"], ("celsius", 5))),
+        "alevelhum_c7": ("alevelhum_batched", MEPS, 65, 16, b_ew(["t", "rh", "p"], ("celsius", 7))),
         "alevelthe_c1": ("alevelthe_batched", MEPS, 65, 16, b_ew(["t", "q", "p"], (1,))),
         "alevelducting_c1": ("alevelducting_batched", MEPS, 65, 16, b_ew(["t", "q", "p"], (1,))),
         "alevel_chain": ("alevel_chain_batched", MEPS, 65, 28, b_chain),
