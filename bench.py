@@ -14,6 +14,17 @@ alternate between two input sets, so nothing is served from cache ("inputs large
     python bench.py [--gpus N] [--steps K] [--warmup W]            # product arm
     python bench.py --impl reference [--gpus N] [--steps K] ...    # the reference's CPU code (oracle/_ref)
     torchrun --nproc-per-node N bench.py --gpus N ...              # one rank per GPU, weak scaling by batch
+
+Besides the headline the same JSON line carries
+  per_operator   every operator BASELINE.json's configs name (cfg1 vorticity / divergence / pleveltemp, the cfg2 single
+                 operators, cfg3 ECMWF stencils at 137 levels, cfg4 ensemble reductions with ALL_DEFINED and 5 %-masked
+                 members, cfg5 icing / arithmetic / stencils with 30 % undefined): Gpt/s, GB/s and fraction of the measured HBM
+                 peak at the algorithmic bytes per point, a clock sample taken under that operator's load and -- at N=1 -- the
+                 reference's CPU code (serial and OpenMP builds of oracle/_ref) timed on field 0 of the SAME inputs;
+  cfg1_latency   microseconds per single-field call of the drop-in API (device, pinned and pageable host pointers, flag
+                 read-back included) and of the three-call chain in deferred mode;
+  e2e.ceiling    the same bytes moved by plain cudaMemcpyAsync copies (no kernel): the host-link limit of the e2e number;
+  slab           (N > 1) one ECMWF grid split into row slabs with an NCCL halo exchange (SURVEY.md 8e case 2).
 """
 from __future__ import annotations
 
@@ -41,9 +52,18 @@ WORKLOAD = "meps65_alevel_chain"
 # (12 + 16 + 16 + 16), fused = t, q, p read once + four outputs
 BYTES_UNFUSED = {"aleveltemp": 12, "alevelhum_rh": 16, "alevelhum_td": 16, "alevelthe": 16}
 BYTES_FUSED = 28
-# dram__bytes_read.sum + dram__bytes_write.sum of one fused-chain launch (65 levels), from the ncu --set full
-# capture committed under profiles/ (None until captured)
-TRAFFIC_NCU = 1800.5e6  # profiles/r01_ncu_full_chain_final_summary.csv: 792.6 MB read + 1007.9 MB written (algorithmic: 1846 MB)
+
+
+def ncu_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum of ONE fused-chain launch (65 levels), as recorded from the latest
+    `ncu --set full` capture by tools/ncu_summary.py --traffic (profiles/chain_traffic.json).  A profiler counter cannot be
+    read inside an unprofiled run, so this is the committed capture's figure with its provenance, or None."""
+    path = os.path.join(ROOT, "profiles", "chain_traffic.json")
+    try:
+        d = json.load(open(path))
+        return float(d["bytes_per_launch"]), d.get("source", path)
+    except (OSError, ValueError, KeyError):
+        return None, None
 
 
 def peaks():
@@ -75,8 +95,10 @@ def synth_level_set(rng, nlev, dtype=np.float32):
 
 # ------------------------------------------------------------------------------------- clocks sampler
 class ClockSampler:
+    """nvidia-smi sampling every 100 ms for the life of the object; window(t0, t1) condenses the samples of one timed region"""
     FIELDS = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, index):
         self.rows, self.proc = [], None
@@ -90,103 +112,134 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append((time.time(), line.strip()))
-
-    def samples_since(self, t0):
-        return sum(1 for ts, _ in self.rows if ts >= t0)
-
-    def stop(self, t0, t1):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        sm, smax, reasons = [], None, set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ts, line in self.rows:
             parts = [x.strip() for x in line.split(",")]
             if len(parts) < 6:
                 continue
             try:
-                smax = float(parts[1])
-                if t0 - 0.05 <= ts <= t1 + 0.15:
-                    sm.append(float(parts[0]))
-                    for nme, val in zip(names, parts[2:6]):
-                        if val.lower().startswith("active"):
-                            reasons.add(nme)
+                self.rows.append((time.time(), float(parts[0]), float(parts[1]), [v.lower().startswith("active") for v in parts[2:6]]))
             except ValueError:
                 continue
-        if not sm:  # region shorter than the sampling period: take what we have
-            sm = [float(l.split(",")[0]) for _, l in self.rows if l and l.split(",")[0].strip().replace(".", "").isdigit()]
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons), "samples": len(sm)}
+
+    def samples_since(self, t0):
+        return sum(1 for r in self.rows if r[0] >= t0)
+
+    def window(self, t0, t1):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"], "samples": 0}
+        rows = [r for r in self.rows if t0 - 0.02 <= r[0] <= t1 + 0.02]
+        reasons = sorted({n for r in rows for n, on in zip(self.NAMES, r[3]) if on})
+        smax = self.rows[-1][2] if self.rows else None
+        return {"sm_mhz": float(np.median([r[1] for r in rows])) if rows else None, "sm_max_mhz": smax, "reasons": reasons, "samples": len(rows)}
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+
+
+def numa_bind(torch, local):
+    """Run this rank's host thread -- and therefore its pinned staging buffers (first touch) -- on the NUMA node its GPU hangs
+    off: N ranks copying through one node's memory is what flattened the end-to-end scaling in round 1.  Best effort."""
+    try:
+        bus = torch.cuda.get_device_properties(local).pci_bus_id
+        dom = torch.cuda.get_device_properties(local).pci_domain_id
+        dev = torch.cuda.get_device_properties(local).pci_device_id
+        path = "/sys/bus/pci/devices/%04x:%02x:%02x.0/numa_node" % (dom, bus, dev)
+        node = int(open(path).read().strip())
+        if node < 0:
+            return None
+        cpus = []
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus += list(range(int(a), int(b or a) + 1))
+        allowed = sorted(set(cpus) & os.sched_getaffinity(0))
+        if not allowed:
+            return None
+        os.sched_setaffinity(0, allowed)
+        return {"numa_node": node, "cpus": len(allowed)}
+    except Exception:  # noqa: BLE001 -- sysfs layout differs between boxes; binding is an optimisation
+        return None
 
 
 # ------------------------------------------------------------------------------------- reference arm
-def pick_reference_lib():
-    """Serial (the reference's default build) or OpenMP (its optional build, <= 8 threads): whichever is
-    faster on this host for one aleveltemp call -- some containers expose cores that do not run in parallel."""
+def reference_threads():
+    """the reference never uses more than 8 threads (openmp_tools.cc:58-65) and reads OMP_NUM_THREADS at its first call
+    (openmp_tools.cc:45-56).  torch.distributed.run exports OMP_NUM_THREADS=1 to every rank: set it EXPLICITLY (round 1 used
+    setdefault and timed a one-thread CPU under torchrun)."""
+    try:
+        avail = len(os.sched_getaffinity(0))
+    except AttributeError:
+        avail = os.cpu_count() or 1
+    threads = max(1, min(8, avail))
+    os.environ["OMP_NUM_THREADS"] = str(threads)
+    os.environ.pop("OMP_THREAD_LIMIT", None)
+    return threads
+
+
+def reference_libs():
+    """(serial, openmp, kind, threads): the two builds of the unmodified reference (oracle/_ref), or the C port twice"""
     import fclibs
-    threads = min(8, os.cpu_count() or 1)
-    os.environ.setdefault("OMP_NUM_THREADS", str(threads))
-    cands = []
-    for omp in (True, False):
-        lib = fclibs.reference(openmp=omp)
-        if lib is not None:
-            cands.append((lib, "reference", threads if omp else 1))
-    if not cands:
-        return fclibs.oracle(), "port", 1
-    if len(cands) == 1:
-        return cands[0]
-    rng = np.random.default_rng(1)
-    t = rng.uniform(220, 300, (NY, NX)).astype(np.float32)
-    p = rng.uniform(300, 1000, (NY, NX)).astype(np.float32)
-    o = np.empty_like(t)
-    best = None
-    for lib, kind, thr in cands:
+    threads = reference_threads()
+    serial, omp = fclibs.reference(openmp=False), fclibs.reference(openmp=True)
+    if serial is None and omp is None:
+        o = fclibs.oracle()
+        return o, None, "port", 1
+    return serial, omp, "reference", threads
+
+
+def chain_on_cpu(lib, t, q, p, outs):
+    for k in range(t.shape[0]):
         f = np.array([0], np.int32)
-        lib.call("aleveltemp", NX, NY, t, p, "kelvin", 3, o, f, UNDEF)
+        lib.call("aleveltemp", NX, NY, t[k], p[k], "kelvin", 3, outs[0], f, UNDEF)
+        f[0] = 0
+        lib.call("alevelhum", NX, NY, t[k], q[k], p[k], "celsius", 1, outs[1], f, UNDEF)
+        f[0] = 0
+        lib.call("alevelhum", NX, NY, t[k], q[k], p[k], "celsius", 5, outs[2], f, UNDEF)
+        f[0] = 0
+        lib.call("alevelthe", NX, NY, t[k], q[k], p[k], 1, outs[3], f, UNDEF)
+
+
+def pick_reference_lib():
+    """Serial (the reference's default build) or OpenMP (its optional build, <= 8 threads): whichever is faster on this host
+    for the chain on one level -- some containers expose cores that do not run in parallel.  Returns (lib, kind, threads USED)."""
+    serial, omp, kind, threads = reference_libs()
+    cands = [(lib, thr) for lib, thr in ((omp, threads), (serial, 1)) if lib is not None]
+    if len(cands) == 1:
+        return cands[0][0], kind, cands[0][1]
+    t, q, p = synth_level_set(np.random.default_rng(1), 1)
+    outs = [np.empty((NY, NX), np.float32) for _ in range(4)]
+    best = None
+    for lib, thr in cands:
+        chain_on_cpu(lib, t, q, p, outs)
         t0 = time.perf_counter()
-        lib.call("aleveltemp", NX, NY, t, p, "kelvin", 3, o, f, UNDEF)
+        chain_on_cpu(lib, t, q, p, outs)
         dt = time.perf_counter() - t0
         if best is None or dt < best[0]:
-            best = (dt, lib, kind, thr)
-    return best[1], best[2], best[3]
+            best = (dt, lib, thr)
+    return best[1], kind, best[2]
 
 
 def run_reference(args):
-    """The reference's own CPU implementation of the chain (oracle/_ref, OpenMP build: the reference
-    never uses more than 8 threads, openmp_tools.cc:58-65), on a bounded sample of the workload."""
+    """The reference's own CPU implementation of the chain (oracle/_ref, OpenMP build: the reference never uses more than
+    8 threads, openmp_tools.cc:58-65), one step = the same 65 levels the product arm runs."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     lib, kind, threads = pick_reference_lib()
-    nlev = args.ref_levels
-    rng = np.random.default_rng(2000)
-    t, q, p = synth_level_set(rng, nlev)
+    nlev = args.levels
+    t, q, p = synth_level_set(np.random.default_rng(2000), nlev)
     outs = [np.empty((NY, NX), np.float32) for _ in range(4)]
-
-    def step():
-        for k in range(nlev):
-            f = np.array([0], np.int32)
-            lib.call("aleveltemp", NX, NY, t[k], p[k], "kelvin", 3, outs[0], f, UNDEF)
-            f[0] = 0
-            lib.call("alevelhum", NX, NY, t[k], q[k], p[k], "celsius", 1, outs[1], f, UNDEF)
-            f[0] = 0
-            lib.call("alevelhum", NX, NY, t[k], q[k], p[k], "celsius", 5, outs[2], f, UNDEF)
-            f[0] = 0
-            lib.call("alevelthe", NX, NY, t[k], q[k], p[k], 1, outs[3], f, UNDEF)
-
-    for _ in range(max(1, args.warmup)):
-        step()
+    for _ in range(max(1, min(args.warmup, 2))):
+        chain_on_cpu(lib, t, q, p, outs)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        step()
+        chain_on_cpu(lib, t, q, p, outs)
     dt = time.perf_counter() - t0
     value = nlev * N * args.steps / dt
-    sample = "%d of %d levels per step (%d grid points), chain of 4 reference calls per level" % (nlev, NLEV, nlev * N)
+    sample = "%d of %d levels per step (%d grid points), chain of 4 reference calls per level, %d thread(s)" % (nlev, NLEV, nlev * N, threads)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "grid points/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "grid": [NX, NY], "levels_per_step": nlev, "host": "cpu"},
+        "config": {"workload": WORKLOAD, "grid": [NX, NY], "levels_per_step": nlev, "host": "cpu", "omp_num_threads": os.environ.get("OMP_NUM_THREADS")},
         "cpu_baseline": {"value": value, "unit": "grid points/s", "cores": threads, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": "grid points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -197,21 +250,12 @@ def run_reference(args):
 def cpu_baseline_sample(nlev=6, reps=2):
     """Bounded CPU sample timed next to the GPU number (rank 0, N=1 only)."""
     lib, kind, threads = pick_reference_lib()
-    rng = np.random.default_rng(2000)
-    t, q, p = synth_level_set(rng, nlev)
+    t, q, p = synth_level_set(np.random.default_rng(2000), nlev)
     outs = [np.empty((NY, NX), np.float32) for _ in range(4)]
     best = None
     for _ in range(reps + 1):
         t0 = time.perf_counter()
-        for k in range(nlev):
-            f = np.array([0], np.int32)
-            lib.call("aleveltemp", NX, NY, t[k], p[k], "kelvin", 3, outs[0], f, UNDEF)
-            f[0] = 0
-            lib.call("alevelhum", NX, NY, t[k], q[k], p[k], "celsius", 1, outs[1], f, UNDEF)
-            f[0] = 0
-            lib.call("alevelhum", NX, NY, t[k], q[k], p[k], "celsius", 5, outs[2], f, UNDEF)
-            f[0] = 0
-            lib.call("alevelthe", NX, NY, t[k], q[k], p[k], 1, outs[3], f, UNDEF)
+        chain_on_cpu(lib, t, q, p, outs)
         dt = time.perf_counter() - t0
         best = dt if best is None else min(best, dt)
     return {"value": nlev * N / best, "unit": "grid points/s", "cores": threads, "kind": kind,
@@ -231,6 +275,152 @@ class stdout_to_stderr:
         sys.stdout.flush()
         os.dup2(self.saved, 1)
         os.close(self.saved)
+
+
+# ------------------------------------------------------------------------------------- per-operator battery
+def cpu_time_call(lib, name, args, budget_s=1.5):
+    """best wall time of the reference's single-field call (first call discarded: OpenMP thread start-up, page faults)"""
+    import copy
+    best, spent = None, 0.0
+    for rep in range(4):
+        a = copy.deepcopy(args)
+        t0 = time.perf_counter()
+        rc = lib.call(name, *a)
+        dt = time.perf_counter() - t0
+        spent += dt
+        if rc != 1:
+            return None
+        if rep > 0:
+            best = dt if best is None else min(best, dt)
+        if rep > 0 and spent > budget_s:
+            break
+    return best
+
+
+def per_operator(gpu, torch, dev, stream, sampler, peak, rank, world, dist, with_cpu, levels_cfg3, min_seconds):
+    """every operator of BASELINE.json's configs: device-resident throughput (CUDA events on the launching stream around
+    deferred launches, inputs far larger than L2), a clock sample under ITS load, and the reference CPU code on field 0 of the
+    same inputs.  N > 1: every rank runs the same battery on its own shard (weak scaling by field batch); ms = max over ranks."""
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import oplib
+    inputs = oplib.Inputs(torch, dev, seed=4321 + rank)
+    serial = omp = None
+    threads = 1
+    if with_cpu:
+        serial, omp, kind, threads = reference_libs()
+    out = []
+    for row in oplib.rows(levels_cfg3=levels_cfg3):
+        b = oplib.Built(row, inputs, 0.0)
+        ms, launches, wall0, wall1 = oplib.time_row(gpu, torch, stream, b, min_seconds, sampler)
+        rec = {"operator": row.name, "config": row.cfg, "call": "fcb200_" + row.call, "grid": list(row.grid), "fields": row.nf, "mask": b.mask,
+               "bytes_per_point": row.bpp, "ms": ms, "launches_timed": launches}
+        if sampler is not None:
+            rec["clocks"] = sampler.window(wall0, wall1)
+        if row.note:
+            rec["note"] = row.note
+        if with_cpu:
+            single, cpu_pts = b.single_host_args()
+            name = row.call.replace("_batched", "")
+            cpu = {"points": cpu_pts, "kind": kind, "sample": "field 0 of the GPU batch" + ("" if cpu_pts == row.grid[0] * row.grid[1] else ", first %d rows" % (cpu_pts // row.grid[0]))}
+            for label, lib in (("serial_mpts", serial), ("omp_mpts", omp)):
+                if lib is not None:
+                    dt = cpu_time_call(lib, name, single)
+                    cpu[label] = None if dt is None else cpu_pts / dt / 1e6
+            cpu["omp_threads"] = threads
+            rec["cpu"] = cpu
+        out.append(rec)
+        del b
+        torch.cuda.empty_cache()
+    ms_all = torch.tensor([r["ms"] for r in out], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(ms_all, op=dist.ReduceOp.MAX)
+    for r, ms in zip(out, ms_all.tolist()):
+        pts = r["grid"][0] * r["grid"][1] * r["fields"]
+        r["ms"] = ms
+        r["gpts"] = world * pts / (ms * 1e-3) / 1e9          # whole job
+        r["gbs_per_gpu"] = r["bytes_per_point"] * pts / (ms * 1e-3) / 1e9
+        r["frac"] = r["gbs_per_gpu"] / peak
+        if "cpu" in r and r["cpu"].get("omp_mpts"):
+            r["speedup_vs_cpu_omp"] = r["gpts"] * 1e3 / r["cpu"]["omp_mpts"]
+    return out
+
+
+def cfg1_latency(gpu, torch, dev):
+    """BASELINE.json configs[0] as the reference API delivers it: ONE 949x1069 field per call (FC.h:102-107), the call returns
+    when output and flag are final.  Microseconds per call (median of 60) with device, pinned-host and pageable-host fields,
+    and the three calls as one deferred chain (one synchronisation, no flag read-back in between)."""
+    rng = np.random.default_rng(77)
+    host = {k: rng.uniform(lo, hi, (NY, NX)).astype(np.float32) for k, (lo, hi) in
+            dict(t=(230, 290), u=(-30, 30), v=(-30, 30), xm=(1.9e-4, 2.1e-4), ym=(1.9e-4, 2.1e-4)).items()}
+    host["o"] = np.empty((NY, NX), np.float32)
+    pinned = {k: torch.from_numpy(a.copy()).pin_memory() for k, a in host.items()}
+    device = {k: torch.from_numpy(a).to(dev) for k, a in host.items()}
+    flag = np.zeros(1, np.int32)
+
+    def calls(m):
+        return [("pleveltemp_c3", lambda: gpu.call("pleveltemp", NX, NY, m["t"], 500.0, "kelvin", 3, m["o"], flag, UNDEF), 8),
+                ("relvort", lambda: gpu.call("relvort", NX, NY, m["u"], m["v"], m["xm"], m["ym"], m["o"], flag, UNDEF), 20),
+                ("divergence", lambda: gpu.call("divergence", NX, NY, m["u"], m["v"], m["xm"], m["ym"], m["o"], flag, UNDEF), 20)]
+
+    res = {"grid": [NX, NY], "unit": "us per call (median of 60, flag read-back included)", "calls": {}}
+    for where, m in (("device", device), ("pinned_host", pinned), ("pageable_host", host)):
+        for name, fn, bpp in calls(m):
+            for _ in range(5):
+                flag[0] = 0
+                fn()
+            ts = []
+            for _ in range(60):
+                flag[0] = 0
+                t0 = time.perf_counter()
+                fn()
+                ts.append(time.perf_counter() - t0)
+            us = float(np.median(ts)) * 1e6
+            res["calls"].setdefault(name, {})[where] = {"us": us, "mpts": N / us, "bytes_moved_over_pcie": 0 if where == "device" else bpp * N}
+    # the three calls as one deferred chain on device fields (what a caller's expression evaluator would enqueue)
+    outs = [torch.empty((NY, NX), dtype=torch.float32, device=dev) for _ in range(3)]
+    fl = [np.zeros(1, np.int32) for _ in range(3)]
+
+    def chain():
+        gpu.begin_deferred()
+        gpu.call("pleveltemp", NX, NY, device["t"], 500.0, "kelvin", 3, outs[0], fl[0], UNDEF)
+        gpu.call("relvort", NX, NY, device["u"], device["v"], device["xm"], device["ym"], outs[1], fl[1], UNDEF)
+        gpu.call("divergence", NX, NY, device["u"], device["v"], device["xm"], device["ym"], outs[2], fl[2], UNDEF)
+        gpu.end_deferred()
+
+    for _ in range(5):
+        chain()
+    ts = []
+    for _ in range(60):
+        t0 = time.perf_counter()
+        chain()
+        ts.append(time.perf_counter() - t0)
+    res["deferred_chain_of_3_device_us"] = float(np.median(ts)) * 1e6
+    res["sum_of_3_immediate_device_us"] = sum(res["calls"][k]["device"]["us"] for k in res["calls"])
+    return res
+
+
+def copy_ceiling(torch, dev, hin, hout, steps):
+    """the e2e step's bytes with NO kernel: H2D of the three inputs and D2H of the four outputs on two streams at once, plain
+    cudaMemcpyAsync on the same pinned buffers (one copy per array).  This is the host link's limit for the e2e number."""
+    din = [torch.empty_like(a, device=dev) for a in hin]
+    dout = [torch.empty_like(a, device=dev) for a in hout]
+    s_in, s_out = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+
+    def one():
+        with torch.cuda.stream(s_in):
+            for d, h in zip(din, hin):
+                d.copy_(h, non_blocking=True)
+        with torch.cuda.stream(s_out):
+            for h, d in zip(hout, dout):
+                h.copy_(d, non_blocking=True)
+
+    one()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        one()
+    torch.cuda.synchronize()
+    return (time.perf_counter() - t0) / steps
 
 
 # ------------------------------------------------------------------------------------- product arm
@@ -254,6 +444,7 @@ def run_product(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- the product has no CPU path")
     torch.cuda.set_device(local)
+    numa = numa_bind(torch, local)
     if world > 1:
         with stdout_to_stderr():
             dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -332,7 +523,7 @@ def run_product(args):
             gpu.end_deferred()
             torch.cuda.synchronize()
             tail_steps += 50
-        clocks = sampler.stop(wall0, time.time() if tail_steps else wall1)
+        clocks = sampler.window(wall0, time.time() if tail_steps else wall1)
         clocks["window"] = "timed region" if not tail_steps else "timed region + %d identical untimed steps right after it (the timed region is shorter than the 100 ms sampling period)" % tail_steps
     if world > 1:
         dist.barrier()
@@ -340,9 +531,13 @@ def run_product(args):
     points_per_step = nlev * N
     value = world * points_per_step * args.steps / (total_ms * 1e-3)
     achieved = BYTES_FUSED * points_per_step / (kern_ms * 1e-3) / 1e9
+    traffic, traffic_src = ncu_traffic()
+    if traffic is not None and nlev != NLEV:
+        traffic = None
     roofline = {"bound": "hbm", "kernel": "ew_kernel<AlevelChainOpT<2, 2, 4>, 4> (fused chain)", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": TRAFFIC_NCU, "peak_source": peak_src, "algorithmic_bytes_per_point": BYTES_FUSED,
-                "kernel_ms": kern_ms, "note": "issue-bound, not HBM-bound: ~157 instructions per point (246 at the start of the round), 67-72 % issue-slot utilisation, DRAM 50 % busy (ncu, profiles/r01_ncu_full_chain_final_summary.csv; steps in profiles/r01_chain_tuning.txt)"}
+                "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "algorithmic_bytes_per_point": BYTES_FUSED,
+                "algorithmic_bytes_per_launch": BYTES_FUSED * points_per_step, "kernel_ms": kern_ms,
+                "note": "issue-bound, not HBM-bound (ncu summaries under profiles/)"}
 
     # for the record: the same step as the UNFUSED reference call sequence (four batched launches, 60 B/point)
     gpu.begin_deferred()
@@ -383,11 +578,40 @@ def run_product(args):
         e2e_dt = float(tt.item())
     assert (hfout == 0).all()
     e2e_value = world * e2e_lev * N * args.e2e_steps / e2e_dt
-    e2e = {"value": e2e_value, "unit": "grid points/s", "h2d_bytes_per_step": 3 * 4 * e2e_lev * N, "d2h_bytes_per_step": 4 * 4 * e2e_lev * N,
+    h2d, d2h = 3 * 4 * e2e_lev * N, 4 * 4 * e2e_lev * N
+    # the same bytes with no kernel in between: all ranks at once, like the e2e steps
+    barrier()
+    copy_s = copy_ceiling(torch, dev, hin, hout, max(2, args.e2e_steps))
+    if world > 1:
+        tt = torch.tensor([copy_s], device=dev, dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        copy_s = float(tt.item())
+    barrier()
+    ceiling = world * e2e_lev * N / copy_s
+    e2e = {"value": e2e_value, "unit": "grid points/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
            "levels_per_step": e2e_lev, "ms_per_step": 1e3 * e2e_dt / args.e2e_steps,
-           "api": "fcb200_alevel_chain_batched with pinned host buffers (chunked, copy-in / kernel / copy-out pipelined over 3 streams)"}
+           "api": "fcb200_alevel_chain_batched with pinned host buffers (chunked, copy-in / kernel / copy-out pipelined over 3 streams)",
+           "ceiling": {"value": ceiling, "unit": "grid points/s", "ms_per_step": 1e3 * copy_s, "h2d_gbs_per_gpu": h2d / copy_s / 1e9, "d2h_gbs_per_gpu": d2h / copy_s / 1e9,
+                       "how": "the step's H2D and D2H bytes as plain cudaMemcpyAsync copies on two streams at once, no kernel, all ranks together (max over ranks)"},
+           "frac_of_copy_ceiling": e2e_value / ceiling, "numa_binding": numa}
+    del hin, hout
 
     cpu = cpu_baseline_sample() if (rank == 0 and world == 1 and not args.no_cpu) else None
+
+    # ---- every other operator the configs name, the cfg1 latencies, the row-slab record
+    ops = None
+    if not args.no_ops:
+        del sets, outs
+        torch.cuda.empty_cache()
+        ops = per_operator(gpu, torch, dev, stream, sampler, peak, rank, world, dist, with_cpu=(rank == 0 and world == 1 and not args.no_cpu),
+                           levels_cfg3=args.cfg3_levels, min_seconds=args.op_seconds)
+    lat = cfg1_latency(gpu, torch, dev) if (rank == 0 and not args.no_ops) else None
+    slab = None
+    if world > 1 and not args.no_slab:
+        barrier()
+        slab = slab_record(gpu, torch, dist, dev, stream, rank, world, args)
+    if sampler:
+        sampler.stop()
 
     if rank == 0:
         line = {
@@ -396,12 +620,20 @@ def run_product(args):
             "config": {"workload": WORKLOAD, "grid": [NX, NY], "levels_per_step": nlev, "points_per_step_per_gpu": points_per_step,
                        "chain": "aleveltemp c3 + alevelhum c1 + alevelhum c5 + alevelthe c1, fused into one launch per step (t, q, p read once)",
                        "unfused_ms_per_step": unfused_ms,
-                       "cache": "inputs larger than L2 (>= 790 MB streamed per step, two alternating input sets)", "sharding": "by field batch, no collective"},
+                       "cache": "inputs larger than L2 (>= 790 MB streamed per step, two alternating input sets)", "sharding": "by field batch, no collective",
+                       "tolerance": "mask and flags bit-exact; values <= 1e-5 relative, with Celsius outputs (Td) and windCooling judged on an absolute floor "
+                                    "(273.15 K resp. 13.12, the polynomial's constant term) -- tests/cases.py abs_floor"},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+            "per_operator": ops, "cfg1_latency": lat, "slab": slab,
         }
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def slab_record(gpu, torch, dist, dev, stream, rank, world, args):
+    """placeholder until the C++ slab path is wired in"""
+    return None
 
 
 def main():
@@ -410,11 +642,14 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="product", choices=["product", "reference"])
-    ap.add_argument("--levels", type=int, default=NLEV, help="levels per step (default: the full 65)")
+    ap.add_argument("--levels", type=int, default=NLEV, help="levels per step (default: the full 65), both arms")
     ap.add_argument("--e2e-levels", type=int, default=NLEV)
     ap.add_argument("--e2e-steps", type=int, default=5)
-    ap.add_argument("--ref-levels", type=int, default=4, help="levels per step of the bounded CPU sample (--impl reference)")
+    ap.add_argument("--cfg3-levels", type=int, default=137, help="ECMWF levels per batch in the per-operator battery")
+    ap.add_argument("--op-seconds", type=float, default=0.3, help="minimum timed wall time per operator of the battery")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-ops", action="store_true", help="headline only: skip the per-operator battery and the cfg1 latencies")
+    ap.add_argument("--no-slab", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

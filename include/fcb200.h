@@ -46,6 +46,8 @@ int fcb200_set_stream(void* cuda_stream, int use_it);
  * call time, so a deferred call must not depend on the flag of an earlier deferred call. */
 int fcb200_begin_deferred(void);
 int fcb200_end_deferred(void);
+/* 1 if the calling thread is between fcb200_begin_deferred() and fcb200_end_deferred() */
+int fcb200_in_deferred(void);
 /* wait for the calling thread's stream */
 int fcb200_synchronize(void);
 /* kernels launched by this library since it was loaded (all threads) */

@@ -12,6 +12,7 @@
 
 #include "../../include/fcb200.h"
 
+#include <algorithm>
 #include <vector>
 
 namespace fcb200 {
@@ -320,18 +321,30 @@ struct SumArgs
   unsigned long long* counter;
 };
 
-__global__ void __launch_bounds__(256) sum_fields_kernel(const SumArgs a)
+// `table` = nullptr: the member pointers travel by value in the kernel parameters (up to MAX_SUM_FIELDS);
+// otherwise they are read from a device table (any number of fields)
+__global__ void __launch_bounds__(256) sum_fields_kernel(const SumArgs a, const float* const* __restrict__ table)
 {
   unsigned nundef = 0;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < a.n; i += (long long)gridDim.x * blockDim.x) {
     float s = 0.f;
     bool ok = true;
-    for (int j = 0; j < a.nfields; ++j) {
-      const float v = a.f[j][i];
-      if (ok && (a.all || is_def(v, a.undef)))
-        s += v;
-      else
-        ok = false;
+    if (table == nullptr) {
+      for (int j = 0; j < a.nfields; ++j) {
+        const float v = a.f[j][i];
+        if (ok && (a.all || is_def(v, a.undef)))
+          s += v;
+        else
+          ok = false;
+      }
+    } else {
+      for (int j = 0; j < a.nfields && ok; ++j) {
+        const float v = table[j][i];
+        if (a.all || is_def(v, a.undef))
+          s += v;
+        else
+          ok = false;
+      }
     }
     a.out[i] = ok ? s : a.undef;
     nundef += ok ? 0u : 1u;
@@ -339,6 +352,33 @@ __global__ void __launch_bounds__(256) sum_fields_kernel(const SumArgs a)
   const unsigned total = __reduce_add_sync(0xffffffffu, nundef);
   if ((threadIdx.x & 31) == 0 && total)
     atomicAdd(a.counter, (unsigned long long)total);
+}
+
+// values2classes with more than MAX_CLASS_VALUES limits: the same point function, limits in device memory
+__global__ void __launch_bounds__(256) classes_table_kernel(const float* __restrict__ in, float* __restrict__ out, long long n, const float* __restrict__ values,
+                                                            int nvalues, float fmin, float fmax, float undef, const FieldMeta* __restrict__ meta,
+                                                            unsigned long long* counters)
+{
+  const int field = blockIdx.y;
+  const bool all = meta[field].all != 0;
+  const float* src = in + (long long)field * n;
+  float* dst = out + (long long)field * n;
+  unsigned nundef = 0;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float v = src[i];
+    if ((all || is_def(v, undef)) && v >= fmin && v < fmax) {
+      int j = 1;
+      while (j < nvalues && values[j] < v)
+        j++;
+      dst[i] = (float)(j - 1);
+    } else {
+      dst[i] = undef;
+      nundef += 1;
+    }
+  }
+  const unsigned total = __reduce_add_sync(0xffffffffu, nundef);
+  if ((threadIdx.x & 31) == 0 && total)
+    atomicAdd(counters + field, (unsigned long long)total);
 }
 
 template <class Op>
@@ -472,9 +512,39 @@ int fcb200_values2classes_batched(int nx, int ny, int nfields, const float* fval
 { // FC.cc:2462-2499
   if (nvalues < 2)
     return 0;
-  if (nvalues > MAX_CLASS_VALUES) {
-    set_error("fcb200: values2classes supports at most %d limits (got %d)", MAX_CLASS_VALUES, nvalues);
-    return -1;
+  if (nvalues > MAX_CLASS_VALUES) { // more limits than fit the functor: the table kernel
+    const long long n = (long long)nx * ny;
+    if (nx <= 0 || ny <= 0 || nfields <= 0 || nfields > 65535 || n >= 0x7fffffffLL) {
+      set_error("fcb200: invalid grid or batch size (nx=%d ny=%d nfields=%d)", nx, ny, nfields);
+      return -1;
+    }
+    Call call;
+    const float* d_in = call.in(fvalue, (size_t)n * nfields);
+    float* d_out = call.out(fclass, (size_t)n * nfields);
+    const float* d_values = static_cast<const float*>(call.upload_small(values, sizeof(float) * (size_t)nvalues));
+    FieldMeta* meta = call.meta_host(nfields);
+    if (!call.ok())
+      return -1;
+    for (int k = 0; k < nfields; ++k) {
+      meta[k].all = (fDefined[k] == ALL_DEFINED) ? 1 : 0;
+      meta[k].a = meta[k].b = meta[k].c = 0.f;
+    }
+    const FieldMeta* d_meta = call.upload_meta();
+    unsigned long long* counters = call.counters(nfields);
+    if (!call.ok())
+      return -1;
+    long long blocks = (n + 255) / 256;
+    const long long cap = std::max(1LL, (long long)sm_count() * 16 / nfields);
+    if (blocks > cap)
+      blocks = cap;
+    classes_table_kernel<<<dim3((unsigned)blocks, (unsigned)nfields), 256, 0, call.stream()>>>(d_in, d_out, n, d_values, nvalues - 2, values[0], values[nvalues - 1],
+                                                                                                undef, d_meta, counters);
+    count_launch();
+    const unsigned long long un = (unsigned long long)n;
+    return call.finish([=](const unsigned long long* cnt) {
+      for (int k = 0; k < nfields; ++k)
+        fDefined[k] = check_defined(cnt[k], un);
+    });
   }
   ClassesOp op;
   op.nvalues = nvalues - 2;
@@ -649,16 +719,20 @@ int fcb200_sumFields(int nx, int ny, const float* const* fields, int nfields, fl
     set_error("fcb200: invalid grid (nx=%d ny=%d nfields=%d)", nx, ny, nfields);
     return -1;
   }
-  if (nfields > MAX_SUM_FIELDS) {
-    set_error("fcb200: sumFields supports at most %d fields (got %d)", MAX_SUM_FIELDS, nfields);
-    return -1;
-  }
   Call call;
   if (!call.ok())
     return -1;
   SumArgs a;
-  for (int j = 0; j < nfields; ++j)
-    a.f[j] = call.in(fields[j], (size_t)n);
+  const float* const* d_table = nullptr;
+  if (nfields <= MAX_SUM_FIELDS) {
+    for (int j = 0; j < nfields; ++j)
+      a.f[j] = call.in(fields[j], (size_t)n);
+  } else { // any number of fields: the pointer table goes to device memory
+    std::vector<const float*> ptrs((size_t)nfields);
+    for (int j = 0; j < nfields; ++j)
+      ptrs[j] = call.in(fields[j], (size_t)n);
+    d_table = static_cast<const float* const*>(call.upload_small(ptrs.data(), sizeof(float*) * (size_t)nfields));
+  }
   a.nfields = nfields;
   a.n = n;
   a.undef = undef;
@@ -671,7 +745,7 @@ int fcb200_sumFields(int nx, int ny, const float* const* fields, int nfields, fl
   const long long cap = (long long)sm_count() * 16;
   if (blocks > cap)
     blocks = cap;
-  sum_fields_kernel<<<(unsigned)blocks, 256, 0, call.stream()>>>(a);
+  sum_fields_kernel<<<(unsigned)blocks, 256, 0, call.stream()>>>(a, d_table);
   count_launch();
   const unsigned long long un = (unsigned long long)n;
   return call.finish([=](const unsigned long long* cnt) { *fDefined = check_defined(cnt[0], un); });

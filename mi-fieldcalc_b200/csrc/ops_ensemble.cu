@@ -36,6 +36,7 @@ struct EnsArgs
   long long n;
   int nmembers, ntimes, chunks, align0;
   int compute;
+  int tables_global; // member tables are read from device memory instead of shared memory (very large ensembles)
   int check_above, check_below;
   float v_above, v_below;
   float undef;
@@ -53,7 +54,7 @@ struct EnsArgs
 // bits).  Zero, tiny, huge and non-finite deltas take the IEEE division.
 template <int MODE, int W, bool FAST>
 __device__ __forceinline__ void ensemble_points(const EnsArgs& a, const float* const* mptr, const int* mflag, const float2* recip, int time,
-                                                long long base, float* out, bool in_all, unsigned& nundef)
+                                                long long base, float* out, bool in_all, unsigned& nundef, long long moff = 0)
 {
   const float undef = a.undef;
   const int M = a.nmembers;
@@ -78,13 +79,13 @@ __device__ __forceinline__ void ensemble_points(const EnsArgs& a, const float* c
       ny = recip[j];
     float x[W];
     if constexpr (W == 4) {
-      const float4 q = *reinterpret_cast<const float4*>(mptr[j] + base);
+      const float4 q = *reinterpret_cast<const float4*>(mptr[j] + moff + base);
       x[0] = q.x;
       x[1] = q.y;
       x[2] = q.z;
       x[3] = q.w;
     } else {
-      x[0] = mptr[j][base];
+      x[0] = mptr[j][moff + base];
     }
 #pragma unroll
     for (int w = 0; w < W; ++w) {
@@ -124,7 +125,7 @@ __device__ __forceinline__ void ensemble_points(const EnsArgs& a, const float* c
   if (MODE == EN_STDDEV && FAST && !(dmin >= 1e-30f && dmax <= 1e30f)) {
     // a zero, tiny, huge or infinite delta: the correction above is only proven for normal operands -- redo
     // these points with the IEEE division
-    ensemble_points<MODE, W, false>(a, mptr, mflag, recip, time, base, out, in_all, nundef);
+    ensemble_points<MODE, W, false>(a, mptr, mflag, recip, time, base, out, in_all, nundef, moff);
     return;
   }
   float r[W];
@@ -171,20 +172,31 @@ template <int MODE, int W>
 __global__ void __launch_bounds__(EN_THREADS) ensemble_kernel(const EnsArgs a)
 {
   extern __shared__ unsigned char smem_raw[];
-  const float** mptr = reinterpret_cast<const float**>(smem_raw);
-  float2* recip = reinterpret_cast<float2*>(smem_raw + sizeof(float*) * a.nmembers);
-  int* mflag = reinterpret_cast<int*>(smem_raw + (sizeof(float*) + sizeof(float2)) * a.nmembers);
-
   const int time = blockIdx.x / a.chunks;
   const int chunk = blockIdx.x - time * a.chunks;
   const int M = a.nmembers;
   const long long n = a.n;
-  for (int j = threadIdx.x; j < M; j += EN_THREADS) {
-    mptr[j] = a.members[j] + (long long)time * n;
-    mflag[j] = a.member_flags[(long long)time * M + j];
-    recip[j] = reinterpret_cast<const float2*>(a.recip)[j];
+  // the member tables of this time step: staged in shared memory, or -- for ensembles too large for that
+  // (tables_global) -- read from the device tables directly, the time offset added at each use
+  const float* const* mptr = a.members;
+  const int* mflag = a.member_flags + (long long)time * M;
+  const float2* recip = reinterpret_cast<const float2*>(a.recip);
+  long long moff = (long long)time * n;
+  if (!a.tables_global) {
+    const float** s_ptr = reinterpret_cast<const float**>(smem_raw);
+    float2* s_recip = reinterpret_cast<float2*>(smem_raw + sizeof(float*) * M);
+    int* s_flag = reinterpret_cast<int*>(smem_raw + (sizeof(float*) + sizeof(float2)) * M);
+    for (int j = threadIdx.x; j < M; j += EN_THREADS) {
+      s_ptr[j] = a.members[j] + moff;
+      s_flag[j] = mflag[j];
+      s_recip[j] = recip[j];
+    }
+    __syncthreads();
+    mptr = s_ptr;
+    mflag = s_flag;
+    recip = s_recip;
+    moff = 0;
   }
-  __syncthreads();
 
   // per-time peel so that the float4 groups are 16-byte aligned (see elementwise.cuh)
   const int head = (W == 4) ? ((4 - ((a.align0 + (int)(((long long)time * n) & 3)) & 3)) & 3) : 0;
@@ -197,9 +209,9 @@ __global__ void __launch_bounds__(EN_THREADS) ensemble_kernel(const EnsArgs a)
   const long long g = (long long)chunk * EN_THREADS + threadIdx.x;
   if (g < groups) {
     if (fast)
-      ensemble_points<MODE, W, true>(a, mptr, mflag, recip, time, head + g * W, out, in_all, nundef);
+      ensemble_points<MODE, W, true>(a, mptr, mflag, recip, time, head + g * W, out, in_all, nundef, moff);
     else
-      ensemble_points<MODE, W, false>(a, mptr, mflag, recip, time, head + g * W, out, in_all, nundef);
+      ensemble_points<MODE, W, false>(a, mptr, mflag, recip, time, head + g * W, out, in_all, nundef, moff);
   }
 
   if (W == 4 && chunk == 0) {
@@ -211,7 +223,7 @@ __global__ void __launch_bounds__(EN_THREADS) ensemble_kernel(const EnsArgs a)
     else if (threadIdx.x >= 32 && (int)threadIdx.x - 32 < ntail)
       idx = tail0 + (threadIdx.x - 32);
     if (idx >= 0)
-      ensemble_points<MODE, 1, false>(a, mptr, mflag, recip, time, idx, out, in_all, nundef);
+      ensemble_points<MODE, 1, false>(a, mptr, mflag, recip, time, idx, out, in_all, nundef, moff);
   }
 
   dev::block_add_counter(nundef, a.counters + time);
@@ -237,10 +249,6 @@ int run_ensemble(const EnsHost& h)
     return -1;
   }
   const int M = h.nmembers > 0 ? h.nmembers : 0;
-  if (M > 4096) {
-    set_error("fcb200: at most 4096 ensemble members per call (got %d)", M);
-    return -1;
-  }
   const long long n = (long long)h.nx * h.ny;
   Call call;
 
@@ -309,7 +317,8 @@ int run_ensemble(const EnsHost& h)
       all_members = meta[t].all != 0;
     meta[t].a = 0.f;
     meta[t].b = (float)counted;
-    meta[t].c = (all_members && M > 0) ? 1.f : 0.f;
+    // (the reciprocal form of the Welford update is proven for divisors up to 4096 only)
+    meta[t].c = (all_members && M > 0 && !(h.mode == EN_STDDEV && M > 4096)) ? 1.f : 0.f;
     pdiv[t] = counted / 100.0; // FC.cc:2855
   }
   const unsigned char* d_blob = static_cast<const unsigned char*>(call.upload_small(blob.data(), blob_bytes));
@@ -344,7 +353,9 @@ int run_ensemble(const EnsHost& h)
     set_error("fcb200: batch too large for one launch (%lld CTAs)", grid);
     return -1;
   }
-  const size_t smem = (sizeof(float*) + sizeof(float2) + sizeof(int)) * Mp;
+  // 20 bytes of shared memory per member: up to 2048 members fit the 48 KB every device grants without an opt-in
+  a.tables_global = M > 2048 ? 1 : 0;
+  const size_t smem = a.tables_global ? 0 : (sizeof(float*) + sizeof(float2) + sizeof(int)) * Mp;
 
 #define FCB_LAUNCH_ENS(MODE)                                                                                                                         \
   do {                                                                                                                                               \

@@ -16,6 +16,7 @@
 #include "../../include/fcb200.h"
 
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdlib>
 #include <vector>
@@ -1112,18 +1113,28 @@ bool launch_stencil(Call& call, const Op& op, int nx, int ny, int nfields, float
     while (t.stages > 1 && L::smem_bytes(t.stages) > 110 * 1024)
       t.stages -= 1;
     const size_t smem = L::smem_bytes(t.stages);
-    static bool attr_set = false; // per instantiation
-    if (!attr_set) {
+    // the opt-in to more than 48 KB of dynamic shared memory is a PER-DEVICE attribute of the kernel: one bit per
+    // device and instantiation (a host thread per GPU is the recommended multi-GPU set-up)
+    static std::atomic<unsigned long long> attr_set{0};
+    int device = 0;
+    if (!cuda_ok(cudaGetDevice(&device), "cudaGetDevice"))
+      return false;
+    const unsigned long long dev_bit = (device >= 0 && device < 64) ? (1ull << device) : 0ull;
+    if (!(attr_set.load(std::memory_order_acquire) & dev_bit) || dev_bit == 0) {
       if (!cuda_ok(cudaFuncSetAttribute(tile::stencil_tile_kernel<Op>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::smem_bytes(tile::MAX_STAGES)),
                    "cudaFuncSetAttribute(stencil_tile_kernel)"))
         return false;
-      attr_set = true;
+      attr_set.fetch_or(dev_bit, std::memory_order_release);
     }
-    if (tiles > 65535 || (nfields + t.fb - 1) / t.fb > 0x7fffffff) {
-      set_error("fcb200: grid too large for one launch (%lld tiles)", tiles);
+    // one-dimensional grid, field blocks fastest (CTAs in flight share their tile's map ratios in L2): gridDim.x
+    // holds 2^31-1 CTAs, so any grid with nx*ny < 2^31 fits
+    t.field_blocks = (nfields + t.fb - 1) / t.fb;
+    const long long ctas = tiles * t.field_blocks;
+    if (ctas > 0x7fffffffLL) {
+      set_error("fcb200: batch too large for one launch (%lld CTAs)", ctas);
       return false;
     }
-    tile::stencil_tile_kernel<Op><<<dim3((unsigned)((nfields + t.fb - 1) / t.fb), (unsigned)tiles), tile::TILE_THREADS, smem, call.stream()>>>(op, t);
+    tile::stencil_tile_kernel<Op><<<(unsigned)ctas, tile::TILE_THREADS, smem, call.stream()>>>(op, t);
     tile::stencil_edge_kernel<Op><<<edge_grid, tile::EDGE_THREADS, 0, call.stream()>>>(op, nx, ny, nfields, g.lo, g.hi, undef, meta, counters, true);
     count_launch(2);
     return true;

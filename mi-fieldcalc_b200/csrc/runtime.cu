@@ -623,6 +623,11 @@ int fcb200_begin_deferred(void)
   return 1;
 }
 
+int fcb200_in_deferred(void)
+{
+  return thread_state().deferred ? 1 : 0;
+}
+
 int fcb200_end_deferred(void)
 {
   auto& ts = thread_state();

@@ -128,6 +128,17 @@ bool done(int rc, const int& flag, ValuesDefined& fDefined) // `flag` by referen
     }
     throw std::runtime_error(msg && *msg ? msg : "mi-fieldcalc (B200): runtime error");
   }
+  // Deferred mode (fcb200_begin_deferred, thread-local state shared with libfcb200) applies to the C-ABI only, where the
+  // caller owns the flag storage.  Here the flag lives in the calling wrapper's stack frame and the reference's contract
+  // is "output and flag are final on return": drain now, while `flag` is alive, and stay in deferred mode for the
+  // caller's own fcb200_* calls.
+  if (rc >= 0 && fcb200_in_deferred()) {
+    if (fcb200_end_deferred() < 0) {
+      fcb200_begin_deferred();
+      return done(-1, flag, fDefined);
+    }
+    fcb200_begin_deferred();
+  }
   fDefined = static_cast<ValuesDefined>(flag);
   return rc == 1;
 }

@@ -73,6 +73,7 @@ struct TileGeom
   int nx, ny, n;
   int nfields;
   int tiles_x, tiles_y;
+  int field_blocks; // CTAs per tile: the grid is one-dimensional, blockIdx.x = tile * field_blocks + field block
   int fb;      // fields per CTA
   int stages;  // pipeline depth: fields in flight per CTA
   int period;  // fields k and k + period share their 16-byte alignment: 1, 2 or 4
@@ -224,11 +225,11 @@ __global__ void __launch_bounds__(TILE_THREADS, 2) stencil_tile_kernel(const Op 
   __shared__ unsigned s_count[MAX_FB];
 
   const int nx = g.nx, ny = g.ny;
-  const int tile = blockIdx.y;
+  const int tile = blockIdx.x / g.field_blocks;
   const int ty = tile / g.tiles_x, tx = tile - ty * g.tiles_x;
   const int x0 = 1 + tx * TX, y0 = 1 + ty * TY; // first output column / row of the tile
   const int xlast = min(x0 + TX - 1, nx - 2), ylast = min(y0 + TY - 1, ny - 2);
-  const int f0 = blockIdx.x * g.fb;
+  const int f0 = (blockIdx.x - tile * g.field_blocks) * g.fb;
   const int nf = min(g.fb, g.nfields - f0);
   const int S = g.stages;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;

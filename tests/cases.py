@@ -412,7 +412,9 @@ def compare(case, got, want, rtol=0.0):
                 rel = np.where(err == 0, 0.0, err / scale)
                 # both infinite with the same sign counts as equal
                 rel = np.where(np.isinf(g[d]) & (g[d] == w[d]), 0.0, rel)
-            if rel.size and np.nanmax(rel) > rtol:
-                worst = int(np.nanargmax(rel))
-                problems.append("output %d: max relative error %.3g > %.1g (got %r, want %r)" % (k, float(np.nanmax(rel)), rtol, g[d][worst], w[d][worst]))
+                # anything else that is not a number (inf against -inf, inf against a finite value ...) is a mismatch, not a value to skip
+                rel = np.where(np.isnan(rel), np.inf, rel)
+            if rel.size and np.max(rel) > rtol:
+                worst = int(np.argmax(rel))
+                problems.append("output %d: max relative error %.3g > %.1g (got %r, want %r)" % (k, float(np.max(rel)), rtol, g[d][worst], w[d][worst]))
     return problems

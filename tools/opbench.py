@@ -1,12 +1,11 @@
 #!/usr/bin/env python
-"""Per-operator device-resident throughput against the HBM roofline (run on a B200 via gpurun).
+"""Per-operator device-resident throughput against the HBM roofline (run on a B200 via gpurun) -- the development
+companion of bench.py's per_operator record: the same rows (tools/oplib.py), plus the rest of the operator surface.
 
-    python tools/opbench.py [--ops relvort,advection,...] [--reps 10] [--json out.json]
+    python tools/opbench.py [--ops relvort,advection,...] [--all] [--mask 0.3] [--seconds 0.3] [--json out.json]
 
-Every operator runs on a batch sized so that one launch streams >= ~1 GB (far beyond the 126 MB
-L2); inputs alternate between two batches; time = CUDA events on the launching stream around
-`reps` deferred launches.  Algorithmic bytes per point follow SURVEY.md 8(a) ("batched" figures:
-grid-constant map arrays are counted once per batch, i.e. ~0 per point).
+Every operator runs on a batch far larger than the 126 MB L2; time = CUDA events on the launching stream around deferred
+launches; a clock sample (nvidia-smi, 100 ms) is taken under each operator's own load.
 """
 import argparse
 import importlib
@@ -14,271 +13,51 @@ import json
 import os
 import sys
 
-import numpy as np
-
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
-
-MEPS = (949, 1069)
-ECMWF = (3600, 1801)
-UNDEF = 1.0e35
+sys.path.insert(0, os.path.join(ROOT, "tools"))
 
 
 def main():
     import torch
+    import oplib
+    from bench import ClockSampler, peaks
     ap = argparse.ArgumentParser()
     ap.add_argument("--ops", default="")
-    ap.add_argument("--reps", type=int, default=10)
+    ap.add_argument("--all", action="store_true", help="also the operators outside BASELINE.json's configs (SURVEY.md 8a rest, 8f)")
+    ap.add_argument("--seconds", type=float, default=0.3)
+    ap.add_argument("--cfg3-levels", type=int, default=32)
     ap.add_argument("--json", default="")
     ap.add_argument("--mask", type=float, default=0.0, help="fraction of undefined points in every maskable input (flag SOME_DEFINED)")
     args = ap.parse_args()
-    pkg = importlib.import_module("mi-fieldcalc_b200")
-    gpu = pkg.load()
+    gpu = importlib.import_module("mi-fieldcalc_b200").load()
     dev = torch.device("cuda", 0)
-    peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"] if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
+    peak, _ = peaks()
     stream = torch.cuda.current_stream()
     gpu.set_stream(stream.cuda_stream, True)
-    gen = torch.Generator(device=dev)
-    gen.manual_seed(1234)
-
-    def rnd(shape, lo, hi, maskable=True):
-        a = torch.rand(shape, device=dev, generator=gen, dtype=torch.float32) * (hi - lo) + lo
-        if maskable and args.mask > 0:
-            a[torch.rand(shape, device=dev, generator=gen) < args.mask] = UNDEF
-        return a
-
-    flag_in = 2 if args.mask > 0 else 0
-
-    def batch(grid, nf):
-        nx, ny = grid
-        return (nf, ny, nx)
-
-    # name -> (grid, nfields, bytes/pt, builder(nf, grid) -> (callname, args-with-out-and-flags))
-    def mk_stencil(name, nin, extra=()):
-        def build(grid, nf):
-            nx, ny = grid
-            fields = [rnd(batch(grid, nf), 250, 300) if k == 0 else rnd(batch(grid, nf), -30, 30) for k in range(nin)]
-            xm = rnd((ny, nx), 1.9e-4, 2.1e-4, False)
-            ym = rnd((ny, nx), 1.9e-4, 2.1e-4, False)
-            out = torch.empty(batch(grid, nf), device=dev)
-            flags = np.full(nf, flag_in, np.int32)
-            return [nx, ny, nf] + fields + [xm, ym] + list(extra) + [out, flags, UNDEF]
-        return build
-
-    def b_absvort(grid, nf):
-        nx, ny = grid
-        a = mk_stencil("absvort", 2)(grid, nf)
-        fc = rnd((ny, nx), 1.1e-4, 1.4e-4, False)
-        return a[:7] + [fc] + a[7:]
-
-    def b_gwind(grid, nf):
-        nx, ny = grid
-        m = rnd(batch(grid, nf), 4800, 5900)
-        xm, ym, fc = rnd((ny, nx), 1.9e-4, 2.1e-4, False), rnd((ny, nx), 1.9e-4, 2.1e-4, False), rnd((ny, nx), 1.1e-4, 1.4e-4, False)
-        return [nx, ny, nf, m, xm, ym, fc, torch.empty(batch(grid, nf), device=dev), torch.empty(batch(grid, nf), device=dev), np.full(nf, flag_in, np.int32), UNDEF]
-
-    def b_shapiro(grid, nf):
-        nx, ny = grid
-        return [nx, ny, nf, rnd(batch(grid, nf), 250, 300), torch.empty(batch(grid, nf), device=dev), np.full(nf, flag_in, np.int32), UNDEF]
-
-    def b_ew(kinds, scalars_before_out=(), lead=()):
-        def build(grid, nf):
-            nx, ny = grid
-            rng = {"t": (215, 305), "q": (1e-6, 2e-2), "p": (300, 1040), "w": (-30, 30), "any": (-50, 50), "tc": (-25, 5), "sst": (-1, 8), "sal": (30, 35),
-                   "aice": (0, 0.6), "wave": (0, 8), "rh01": (0.4, 1), "pmsl": (960, 1030), "pw": (3, 12), "depth": (20, 3000), "rh": (1, 100), "z": (100, 5900),
-                   "precip": (0, 5), "snow": (0, 0.6), "pos": (0.05, 900), "snoww": (-0.5, 20), "t2m": (255, 278)}
-            fields = [rnd(batch(grid, nf), *rng[k]) for k in kinds]
-            return list(lead) + [nx, ny, nf] + fields + list(scalars_before_out) + [torch.empty(batch(grid, nf), device=dev), np.full(nf, flag_in, np.int32), UNDEF]
-        return build
-
-    def b_pleveltemp(compute):
-        def build(grid, nf):
-            nx, ny = grid
-            return [nx, ny, nf, rnd(batch(grid, nf), 215, 305), np.full(nf, 500.0, np.float32), "kelvin", compute, torch.empty(batch(grid, nf), device=dev),
-                    np.full(nf, flag_in, np.int32), UNDEF]
-        return build
-
-    def b_plevelhum(compute):
-        def build(grid, nf):
-            nx, ny = grid
-            return [nx, ny, nf, rnd(batch(grid, nf), 215, 305), rnd(batch(grid, nf), 1e-6, 2e-2), np.full(nf, 850.0, np.float32), "celsius", compute,
-                    torch.empty(batch(grid, nf), device=dev), np.full(nf, flag_in, np.int32), UNDEF]
-        return build
-
-    def b_ens(name, M=30, lead=(), limits=None):
-        def build(grid, nt):
-            nx, ny = grid
-            members = [rnd(batch(grid, nt), 250, 300) for _ in range(M)]
-            a = list(lead) + [nx, ny, nt, members, M]
-            if name != "extremeValue":
-                a.append(np.full(nt * M, flag_in, np.int32))
-            if limits is not None:
-                a += [np.array(limits, np.float32), len(limits)]
-            return a + [torch.empty(batch(grid, nt), device=dev), np.full(nt, flag_in, np.int32), UNDEF]
-        return build
-
-    def b_hlevel(kinds, tail):
-        """hybrid levels: per-field arrays, one shared surface-pressure field, alevel / blevel per field (65 MEPS-like levels, repeated)"""
-        def build(grid, nf):
-            nx, ny = grid
-            rng = {"t": (215, 305), "q": (1e-6, 2e-2)}
-            fields = [rnd(batch(grid, nf), *rng[k]) for k in kinds]
-            ps = rnd((ny, nx), 950, 1040)
-            eta = (np.arange(nf) % 65 + 0.5) / 65.0
-            a = (200.0 * (1 - eta) * eta * 2.0 + 10.0 * (1 - eta)).astype(np.float32)
-            b = (eta ** 1.5).astype(np.float32)
-            return [nx, ny, nf] + fields + [ps, a, b] + list(tail) + [torch.empty(batch(grid, nf), device=dev), np.full(nf, flag_in, np.int32), UNDEF]
-        return build
-
-    def b_chain(grid, nf):
-        nx, ny = grid
-        return [nx, ny, nf, rnd(batch(grid, nf), 215, 305), rnd(batch(grid, nf), 1e-6, 2e-2), rnd(batch(grid, nf), 300, 1040), "celsius"] + \
-               [torch.empty(batch(grid, nf), device=dev) for _ in range(4)] + [np.full(nf, flag_in, np.int32), np.zeros(4 * nf, np.int32), UNDEF]
-
-    def b_classes(grid, nf):
-        nx, ny = grid
-        lim = np.array([230.0, 250.0, 262.5, 270.0, 280.0, 300.0], np.float32)
-        return [nx, ny, nf, rnd(batch(grid, nf), 215, 305), torch.empty(batch(grid, nf), device=dev), lim, len(lim), np.full(nf, flag_in, np.int32), UNDEF]
-
-    def b_geo(grid, nf):
-        nx, ny = grid
-        z = rnd(batch(grid, nf), 4800, 5900)
-        xm, ym, fc = rnd((ny, nx), 1.9e-4, 2.1e-4, False), rnd((ny, nx), 1.9e-4, 2.1e-4, False), rnd((ny, nx), 1.1e-4, 1.4e-4, False)
-        return [nx, ny, nf, z, xm, ym, fc, torch.empty(batch(grid, nf), device=dev), np.full(nf, flag_in, np.int32), UNDEF]
-
-    def b_qvec(grid, nf):
-        nx, ny = grid
-        z, t = rnd(batch(grid, nf), 4800, 5900), rnd(batch(grid, nf), 215, 305)
-        xm, ym, fc = rnd((ny, nx), 1.9e-4, 2.1e-4, False), rnd((ny, nx), 1.9e-4, 2.1e-4, False), rnd((ny, nx), 1.1e-4, 1.4e-4, False)
-        return [nx, ny, nf, z, t, xm, ym, fc, 700.0, 1, torch.empty(batch(grid, nf), device=dev), np.full(nf, flag_in, np.int32), UNDEF]
-
-    def b_neigh(constants, compute):
-        def build(grid, nf):
-            nx, ny = grid
-            c = np.array(constants, np.float32)
-            return [nx, ny, nf, rnd(batch(grid, nf), 250, 300, False), c, len(c), compute, torch.zeros(batch(grid, nf), device=dev), np.zeros(nf, np.int32), UNDEF]
-        return build
-
-    def b_hchain(grid, nf):
-        nx, ny = grid
-        eta = (np.arange(nf) % 65 + 0.5) / 65.0
-        a = (200.0 * (1 - eta) * eta * 2.0 + 10.0 * (1 - eta)).astype(np.float32)
-        b = (eta ** 1.5).astype(np.float32)
-        return [nx, ny, nf, rnd(batch(grid, nf), 215, 305), rnd(batch(grid, nf), 1e-6, 2e-2), rnd((ny, nx), 950, 1040), a, b, "celsius"] + \
-               [torch.empty(batch(grid, nf), device=dev) for _ in range(4)] + [np.full(nf, flag_in, np.int32), np.zeros(4 * nf, np.int32), UNDEF]
-
-    icing6 = ["tc", "sst", "w", "w", "sal", "aice"]
-    icing11 = ["sal", "wave", "w", "w", "tc", "rh01", "sst", "pmsl", "pw", "aice", "depth"]
-    OPS = {
-        # stencils (batched B/pt: maps amortised)
-        "relvort": ("relvort_batched", MEPS, 64, 12, mk_stencil("relvort", 2)),
-        "absvort": ("absvort_batched", MEPS, 64, 12, b_absvort),
-        "divergence": ("divergence_batched", MEPS, 64, 12, mk_stencil("divergence", 2)),
-        "advection": ("advection_batched", ECMWF, 12, 16, mk_stencil("advection", 3, extra=(1.0,))),
-        "gradient_c3": ("gradient_batched", ECMWF, 16, 8, mk_stencil("gradient", 1, extra=(3,))),
-        "jacobian": ("jacobian_batched", MEPS, 64, 12, mk_stencil("jacobian", 2)),
-        "ilevelgwind": ("ilevelgwind_batched", MEPS, 64, 12, b_gwind),
-        "thermalFrontParameter": ("thermalFrontParameter_batched", ECMWF, 16, 8, mk_stencil("tfp", 1)),
-        "shapiro2_filter": ("shapiro2_filter_batched", ECMWF, 16, 8, b_shapiro),
-        # elementwise
-        "pleveltemp_c3": ("pleveltemp_batched", MEPS, 128, 8, b_pleveltemp(3)),
-        "pleveltemp_c4": ("pleveltemp_batched", MEPS, 128, 8, b_pleveltemp(4)),
-        "plevelhum_c1": ("plevelhum_batched", MEPS, 96, 12, b_plevelhum(1)),
-        "plevelhum_c7": ("plevelhum_batched", MEPS, 96, 12, b_plevelhum(7)),
-        "hleveltemp_c3": ("hleveltemp_batched", MEPS, 96, 8, b_hlevel(["t"], ("kelvin", 3))),
-        "hlevelhum_c1": ("hlevelhum_batched", MEPS, 65, 12, b_hlevel(["t", "q"], ("celsius", 1))),
-        "hlevelhum_c5": ("hlevelhum_batched", MEPS, 65, 12, b_hlevel(["t", "q"], ("celsius", 5))),
-        "aleveltemp_c3": ("aleveltemp_batched", MEPS, 96, 12, b_ew(["t", "p"], ("kelvin", 3))),
-        "alevelhum_c1": ("alevelhum_batched", MEPS, 65, 16, b_ew(["t", "q", "p"], ("celsius", 1))),
-        "alevelhum_c5": ("alevelhum_batched", MEPS, 65, 16, b_ew(["t", "q", "p"], ("celsius", 5))),
-        "alevelhum_c7": ("alevelhum_batched", MEPS, 65, 16, b_ew(["t", "rh", "p"], ("celsius", 7))),
-        "alevelthe_c1": ("alevelthe_batched", MEPS, 65, 16, b_ew(["t", "q", "p"], (1,))),
-        "alevelducting_c1": ("alevelducting_batched", MEPS, 65, 16, b_ew(["t", "q", "p"], (1,))),
-        "alevel_chain": ("alevel_chain_batched", MEPS, 65, 28, b_chain),
-        "hlevel_chain": ("hlevel_chain_batched", MEPS, 65, 24, b_hchain),
-        "windCooling": ("windCooling_batched", MEPS, 65, 16, b_ew(["t", "w", "w"], (1,))),
-        "fieldOPERfield_add": ("fieldOPERfield_batched", MEPS, 96, 12, b_ew(["any", "any"], (), lead=(1,))),
-        "fieldOPERfield_div": ("fieldOPERfield_batched", MEPS, 96, 12, b_ew(["any", "any"], (), lead=(4,))),
-        "vesselIcingOverland": ("vesselIcingOverland_batched", MEPS, 40, 28, b_ew(icing6)),
-        "vesselIcingMertins": ("vesselIcingMertins_batched", MEPS, 40, 28, b_ew(icing6)),
-        "vesselIcingModStall": ("vesselIcingModStall_batched", MEPS, 4, 48, b_ew(icing11, (5.0, 2.6, 4.0, 4.0))),
-        "vesselIcingMincog": ("vesselIcingMincog_batched", MEPS, 4, 48, b_ew(icing11, (5.0, 2.6, 4.0, 4.0, 1))),
-        # fixed-level indices and level-independent conversions (the rest of the Python subset); showalterIndex reads its
-        # output too (points with an undefined input stay untouched)
-        "kIndex": ("kIndex_batched", MEPS, 48, 24, b_ew(["t", "t", "rh", "t", "rh"], (500.0, 700.0, 850.0, 1))),
-        "ductingIndex": ("ductingIndex_batched", MEPS, 96, 12, b_ew(["t", "rh"], (850.0, 1))),
-        "showalterIndex": ("showalterIndex_batched", MEPS, 64, 20, b_ew(["t", "t", "rh"], (500.0, 850.0, 1))),
-        "boydenIndex": ("boydenIndex_batched", MEPS, 64, 16, b_ew(["t", "z", "z"], (700.0, 1000.0, 1))),
-        "sweatIndex": ("sweatIndex_batched", MEPS, 32, 36, b_ew(["t", "t", "t", "t", "w", "w", "w", "w"])),
-        "seaSoundSpeed": ("seaSoundSpeed_batched", MEPS, 96, 12, b_ew(["sst", "sal"], (50.0, 1))),
-        "cvtemp_c1": ("cvtemp_batched", MEPS, 128, 8, b_ew(["t"], (1,))),
-        "cvhum_c1": ("cvhum_batched", MEPS, 96, 12, b_ew(["t", "rh"], ("kelvin", 1))),
-        "abshum": ("abshum_batched", MEPS, 96, 12, b_ew(["t", "rh"])),
-        "underCooledRain": ("underCooledRain_batched", MEPS, 64, 16, b_ew(["precip", "snow", "t"], (0.5, 0.1, 0.0))),
-        # field arithmetic, element functions, p-level siblings (a sample of the 22 operators of ops_arith.cu)
-        "plevelthe_c1": ("plevelthe_batched", MEPS, 96, 12, b_ew(["t", "rh"], (850.0, 1))),
-        "vectorabs": ("vectorabs_batched", MEPS, 96, 12, b_ew(["w", "w"])),
-        "fieldOPERconstant_mul": ("fieldOPERconstant_batched", MEPS, 128, 8, b_ew(["any"], (2.5,), lead=(3,))),
-        "logField": ("logField_batched", MEPS, 128, 8, b_ew(["pos"])),
-        "pressure2FlightLevel": ("pressure2FlightLevel_batched", MEPS, 128, 8, b_ew(["p"])),
-        "values2classes": ("values2classes_batched", MEPS, 128, 8, b_classes),
-        "snow_in_cm": ("snow_in_cm_batched", MEPS, 64, 16, b_ew(["snoww", "t2m", "t2m"])),
-        # geostrophic stencil siblings (maps amortised over the batch)
-        "plevelgwind_ycomp": ("plevelgwind_ycomp_batched", MEPS, 64, 8, b_geo),
-        "plevelgvort": ("plevelgvort_batched", MEPS, 64, 8, b_geo),
-        "plevelqvector_c1": ("plevelqvector_batched", MEPS, 48, 12, b_qvec),
-        # neighbourhood functions (field by field; they require ALL_DEFINED input: skipped in --mask runs)
-        "neighbourProb_r3": ("neighbourProbFunctions_batched", MEPS, 16, 8, b_neigh((275.0, 3.0), 5)),
-        "neighbourFunctions_mean_r3s3": ("neighbourFunctions_batched", MEPS, 16, 8, b_neigh((3.0, 3.0), 1)),
-        "neighbourFunctions_pct90_r3s3": ("neighbourFunctions_batched", MEPS, 16, 8, b_neigh((90.0, 3.0, 3.0), 4)),
-        # ensemble, 30 members: bytes per OUTPUT point = 4*(M+1)
-        "meanValue": ("meanValue_batched", MEPS, 8, 124, b_ens("meanValue")),
-        "stddevValue": ("stddevValue_batched", MEPS, 8, 124, b_ens("stddevValue")),
-        "extremeValue_max": ("extremeValue_batched", MEPS, 8, 124, b_ens("extremeValue", lead=(1,))),
-        "probability_above": ("probability_batched", MEPS, 8, 124, b_ens("probability", lead=(1,), limits=[275.0])),
-    }
-    wanted = [o for o in args.ops.split(",") if o] or list(OPS)
+    inputs = oplib.Inputs(torch, dev)
+    rows = oplib.rows(levels_cfg3=args.cfg3_levels) + (oplib.extra_rows() if args.all or args.ops else [])
+    wanted = [o for o in args.ops.split(",") if o]
+    sampler = ClockSampler(0)
     results = []
-    print("%-24s %-10s %7s %9s %9s %8s %6s" % ("operator", "grid", "fields", "ms", "Gpt/s", "GB/s", "frac"))
-    for name in wanted:
-        if args.mask > 0 and name.startswith("neighbour"):
+    print("%-32s %-5s %-10s %6s %5s %9s %9s %8s %6s %6s" % ("operator", "cfg", "grid", "fields", "mask", "ms", "Gpt/s", "GB/s", "frac", "MHz"))
+    for row in rows:
+        if wanted and row.name not in wanted:
             continue
-        call, grid, nf, bpp, build = OPS[name]
-        sets = [build(grid, nf), build(grid, nf)]
-        pts = grid[0] * grid[1] * nf
-        saved = [[a.copy() if isinstance(a, np.ndarray) and a.dtype == np.int32 else None for a in s] for s in sets]
-        for s in sets:  # warm-up (also checks the call is accepted)
-            r = gpu.call(call, *s)
-            assert r == 1, (name, r)
-        torch.cuda.synchronize()
-        for s, sv in zip(sets, saved):  # the timed (deferred) calls see the same input flags as the warm-up did
-            for a, b in zip(s, sv):
-                if b is not None:
-                    a[...] = b
-        # two identical deferred passes, the second one is reported: in deferred mode the per-thread device arena is not
-        # recycled between calls, so operators with scratch fields (plevelqvector) grow it (cudaMalloc) during the first pass
-        for _pass in range(2):
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            gpu.begin_deferred()
-            e0.record(stream)
-            for k in range(args.reps):
-                gpu.call(call, *sets[k % 2])
-            e1.record(stream)
-            gpu.end_deferred()
-            torch.cuda.synchronize()
-            for s_, sv in zip(sets, saved):
-                for a, b in zip(s_, sv):
-                    if b is not None:
-                        a[...] = b
-        ms = e0.elapsed_time(e1) / args.reps
-        gbs = bpp * pts / (ms * 1e-3) / 1e9
-        res = {"operator": name, "grid": list(grid), "fields": nf, "ms": ms, "gpts": pts / (ms * 1e-3) / 1e9, "gbs": gbs, "frac": gbs / peak, "bytes_per_point": bpp,
-               "mask": args.mask}
+        b = oplib.Built(row, inputs, args.mask)
+        ms, launches, w0, w1 = oplib.time_row(gpu, torch, stream, b, args.seconds, sampler)
+        gbs = row.bpp * b.points / (ms * 1e-3) / 1e9
+        clk = sampler.window(w0, w1)
+        res = {"operator": row.name, "config": row.cfg, "grid": list(row.grid), "fields": row.nf, "ms": ms, "gpts": b.points / (ms * 1e-3) / 1e9, "gbs": gbs,
+               "frac": gbs / peak, "bytes_per_point": row.bpp, "mask": b.mask, "clocks": clk, "launches_timed": launches}
         results.append(res)
-        print("%-24s %-10s %7d %9.4f %9.2f %8.1f %6.3f" % (name, "%dx%d" % grid, nf, ms, res["gpts"], gbs, res["frac"]))
-        del sets
+        print("%-32s %-5s %-10s %6d %5.2f %9.4f %9.2f %8.1f %6.3f %6s" % (row.name, row.cfg, "%dx%d" % row.grid, row.nf, b.mask, ms, res["gpts"], gbs, res["frac"],
+                                                                         "%.0f" % clk["sm_mhz"] if clk["sm_mhz"] else "-"))
+        sys.stdout.flush()
+        del b
         torch.cuda.empty_cache()
+    sampler.stop()
     if args.json:
         json.dump({"peak_gbs": peak, "results": results}, open(args.json, "w"), indent=1)
 
