@@ -632,8 +632,10 @@ def run_product(args):
 
 
 def slab_record(gpu, torch, dist, dev, stream, rank, world, args):
-    """placeholder until the C++ slab path is wired in"""
-    return None
+    """BASELINE.json configs[2] on N GPUs: one 3600x1801 grid, all levels, cut into row slabs (tools/slab_run.py)"""
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import slab_run
+    return slab_run.slab_record(gpu, torch, dist, dev, stream, rank, world, levels=args.slab_levels, steps=args.slab_steps)
 
 
 def main():
@@ -650,6 +652,8 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-ops", action="store_true", help="headline only: skip the per-operator battery and the cfg1 latencies")
     ap.add_argument("--no-slab", action="store_true")
+    ap.add_argument("--slab-levels", type=int, default=137, help="levels of the row-slab record (N > 1)")
+    ap.add_argument("--slab-steps", type=int, default=5)
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -53,6 +53,31 @@ int fcb200_synchronize(void);
 /* kernels launched by this library since it was loaded (all threads) */
 unsigned long long fcb200_launch_count(void);
 
+/* ---- row slabs: ONE large grid over several GPUs (one process or host thread per GPU) -------------
+ * The reference has no counterpart (it is a single-host library): BASELINE.json configs[2] asks for
+ * "row-slab sharded across 8 GPUs with NVLink halo exchange".  A rank owns rows [r0, r1) of every field and holds the
+ * extended slab [lo, hi) = its rows + `halo` rows of each neighbour (1 for the five-point stencils, 2 for
+ * thermalFrontParameter and shapiro2_filter); it calls the ordinary fcb200_<op>_batched(nx, hi - lo, ...) on the extended
+ * slab and keeps its own rows.  NCCL (bound at run time, libnccl.so.2) moves the halo rows. */
+/* 128-byte NCCL unique id: call on ONE rank, hand the bytes to every rank (any transport: MPI, torch.distributed, a file) */
+int fcb200_slab_unique_id(char* id128);
+/* join the communicator with the calling thread's current device; nranks == 1 is valid (every slab call is then a no-op) */
+int fcb200_slab_init(int rank, int nranks, const char* id128);
+int fcb200_slab_finalize(void);
+int fcb200_slab_rank(void);
+int fcb200_slab_nranks(void);
+/* rows [r0, r1) owned by `rank` and rows [lo, hi) of its extended slab; 0 if ny is too small for nranks slabs of this halo */
+int fcb200_slab_partition(int ny, int halo, int rank, int nranks, int* r0, int* r1, int* lo, int* hi);
+/* halo exchange of `nfields` extended slabs (DEVICE memory, field k at ext + k*ext_rows*nx, owned rows already in place):
+ * the first / last `halo` owned rows go to rank-1 / rank+1, theirs arrive in this slab's halo rows.  Enqueued on the calling
+ * thread's stream (ordered against the operators before and after it); every rank of the communicator must call it. */
+int fcb200_slab_exchange(float* ext, int nx, int ext_rows, int nfields, int halo);
+/* global flags from the per-rank flags of a sharded operator (HOST array, in/out): ALL iff every rank says ALL, NONE iff every
+ * rank says NONE, else SOME.  Synchronises the calling thread first (local flags must be final); collective. */
+int fcb200_slab_combine_flags(int* fDefined, int nfields);
+/* payload bytes this process has sent through fcb200_slab_exchange */
+unsigned long long fcb200_slab_bytes_sent(void);
+
 /* ---- operators ----------------------------------------------------------------------------- */
 #define FC_FN(name, args) int fcb200_##name args;
 #include "fcb200_api.inc"

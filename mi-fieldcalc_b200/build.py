@@ -28,7 +28,7 @@ CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "lib")
 
-CUDA_SOURCES = ["runtime.cu", "ops_elementwise.cu", "ops_diagnostics.cu", "ops_arith.cu", "ops_neighbour.cu", "ops_stencil.cu", "ops_ensemble.cu", "ops_icing.cu"]
+CUDA_SOURCES = ["runtime.cu", "slab.cu", "ops_elementwise.cu", "ops_diagnostics.cu", "ops_arith.cu", "ops_neighbour.cu", "ops_stencil.cu", "ops_ensemble.cu", "ops_icing.cu"]
 
 NVCC_FLAGS = [
     "-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-fmad=false",

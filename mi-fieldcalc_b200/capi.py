@@ -137,6 +137,12 @@ class Fcb200(Api):
         L.fcb200_launch_count.restype = ctypes.c_ulonglong
         L.fcb200_set_stream.argtypes = [ctypes.c_void_p, ctypes.c_int]
         L.fcb200_set_device.argtypes = [ctypes.c_int]
+        L.fcb200_slab_unique_id.argtypes = [ctypes.c_char_p]
+        L.fcb200_slab_init.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_char_p]
+        L.fcb200_slab_partition.argtypes = [ctypes.c_int] * 4 + [ctypes.POINTER(ctypes.c_int)] * 4
+        L.fcb200_slab_exchange.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int]
+        L.fcb200_slab_combine_flags.argtypes = [ctypes.c_void_p, ctypes.c_int]
+        L.fcb200_slab_bytes_sent.restype = ctypes.c_ulonglong
 
     def last_error(self) -> str:
         return self.lib.fcb200_last_error().decode()
@@ -164,6 +170,36 @@ class Fcb200(Api):
 
     def launch_count(self) -> int:
         return int(self.lib.fcb200_launch_count())
+
+    # ---- row slabs (include/fcb200.h): one large grid over several GPUs, NCCL halo exchange
+    def slab_unique_id(self) -> bytes:
+        buf = ctypes.create_string_buffer(128)
+        self._check(self.lib.fcb200_slab_unique_id(buf))
+        return buf.raw
+
+    def slab_init(self, rank: int, nranks: int, unique_id: bytes) -> None:
+        self._check(self.lib.fcb200_slab_init(rank, nranks, ctypes.create_string_buffer(unique_id, 128)))
+
+    def slab_finalize(self) -> None:
+        self.lib.fcb200_slab_finalize()
+
+    def slab_partition(self, ny: int, halo: int, rank: int, nranks: int):
+        """(r0, r1, lo, hi): owned rows and extended-slab rows of `rank`, or None if ny is too small"""
+        v = [ctypes.c_int() for _ in range(4)]
+        if self.lib.fcb200_slab_partition(ny, halo, rank, nranks, *[ctypes.byref(x) for x in v]) != 1:
+            return None
+        return tuple(x.value for x in v)
+
+    def slab_exchange(self, ext, nx: int, ext_rows: int, nfields: int, halo: int) -> None:
+        addr, _keep = _addr(ext)
+        self._check(self.lib.fcb200_slab_exchange(addr, nx, ext_rows, nfields, halo))
+
+    def slab_combine_flags(self, flags: np.ndarray) -> None:
+        assert flags.dtype == np.int32 and flags.flags["C_CONTIGUOUS"]
+        self._check(self.lib.fcb200_slab_combine_flags(flags.ctypes.data, flags.size))
+
+    def slab_bytes_sent(self) -> int:
+        return int(self.lib.fcb200_slab_bytes_sent())
 
     def _check(self, r: int) -> int:
         if r < 0:

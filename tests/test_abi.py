@@ -19,7 +19,14 @@ def test_library_exports_every_declared_symbol():
     sigs.update(capi.parse_inc(os.path.join(capi.INCLUDE, "fcb200_batched.inc"), "FCB_FN"))
     assert len(sigs) >= 64
     runtime = ["fcb200_version", "fcb200_last_error", "fcb200_device_count", "fcb200_set_device", "fcb200_set_stream", "fcb200_begin_deferred",
-               "fcb200_end_deferred", "fcb200_synchronize", "fcb200_launch_count"]
+               "fcb200_end_deferred", "fcb200_in_deferred", "fcb200_synchronize", "fcb200_launch_count", "fcb200_slab_unique_id", "fcb200_slab_init",
+               "fcb200_slab_finalize", "fcb200_slab_rank", "fcb200_slab_nranks", "fcb200_slab_partition", "fcb200_slab_exchange",
+               "fcb200_slab_combine_flags", "fcb200_slab_bytes_sent"]
+    # every prototype of fcb200.h outside the two .inc lists is in `runtime` (the header is the contract)
+    import re
+    header = open(os.path.join(capi.INCLUDE, "fcb200.h")).read()
+    declared = set(re.findall(r"\b(fcb200_\w+)\s*\(", re.sub(r"/\*.*?\*/", "", header, flags=re.S)))
+    assert declared == set(runtime), sorted(declared ^ set(runtime))
     missing = [n for n in ["fcb200_" + k for k in sigs] + runtime if not hasattr(lib, n)]
     assert not missing, missing
 
@@ -46,3 +53,20 @@ def test_no_silent_fallback_without_a_gpu():
     with pytest.raises(RuntimeError):
         api.call("fieldOPERfield", 1, 4, 4, a, a, a.copy(), flag, 1e35)
     assert "fcb200" in api.last_error()
+
+
+def test_slab_partition_is_the_python_partition():
+    """fcb200_slab_partition (C++, what a slab caller uses) == distributed.partition_rows / slab_bounds (what the gloo tests prove)"""
+    D = importlib.import_module("mi-fieldcalc_b200.distributed")
+    api = pkg.load()
+    for ny in (3, 9, 41, 1069, 1801):
+        for world in (1, 2, 3, 8):
+            for halo in (1, 2):
+                for rank in range(world):
+                    got = api.slab_partition(ny, halo, rank, world)
+                    r0, r1 = D.partition_rows(ny, world)[rank]
+                    lo, hi = D.slab_bounds(r0, r1, ny, halo)
+                    if D.min_rows_ok(ny, world, halo):
+                        assert got == (r0, r1, lo, hi), (ny, world, halo, rank, got)
+                    elif got is not None:
+                        assert got == (r0, r1, lo, hi)
