@@ -103,6 +103,10 @@ def _run(gpu, torch, dist, dev, stream, rank, world, nx, ny, nf, steps, mask, se
         slab_fn(flags_slab)
         gpu.synchronize()
         import time
+        warm = flags_slab.copy()
+        gpu.slab_combine_flags(warm)  # the first all-reduce of a communicator sets its connections up: not part of a step
+        if world > 1:
+            dist.barrier()
         t0 = time.perf_counter()
         gpu.slab_combine_flags(flags_slab)
         combine_us = (time.perf_counter() - t0) * 1e6
