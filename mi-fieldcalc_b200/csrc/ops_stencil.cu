@@ -12,6 +12,7 @@
 // Citations: FC.cc = the reference's src/mi_fieldcalc/FieldCalculations.cc.
 #include "device_common.cuh"
 #include "stencil_tile.cuh"
+#include "tfp_tile.cuh"
 
 #include "../../include/fcb200.h"
 
@@ -19,6 +20,7 @@
 #include <atomic>
 #include <cmath>
 #include <cstdlib>
+#include <cstring>
 #include <vector>
 
 namespace fcb200 {
@@ -1161,6 +1163,54 @@ bool launch_stencil(Call& call, const Op& op, int nx, int ny, int nfields, float
   return true;
 }
 
+// thermalFrontParameter in one pass (tfp_tile.cuh): interior points by the marching tile kernel, then the border ring
+template <class Op>
+bool launch_tfp_tile(Call& call, const Op& op, int nx, int ny, int nfields, float undef, const FieldMeta* meta, unsigned long long* counters)
+{
+  tfp2::Geom t;
+  t.nx = nx;
+  t.ny = ny;
+  t.n = nx * ny;
+  t.nfields = nfields;
+  t.tiles_x = (nx - 2 + tfp2::TXO - 1) / tfp2::TXO;
+  t.tiles_y = (ny - 2 + tfp2::TY - 1) / tfp2::TY;
+  t.period = (t.n % 4 == 0) ? 1 : (t.n % 2 == 0) ? 2 : 4;
+  t.undef = undef;
+  t.meta = meta;
+  t.counters = counters;
+  const long long tiles = (long long)t.tiles_x * t.tiles_y;
+  t.fb = 16;
+  while (t.fb > 1 && tiles * ((nfields + t.fb - 1) / t.fb) < 6LL * sm_count())
+    t.fb /= 2;
+  if (t.fb > nfields)
+    t.fb = nfields;
+  t.stages = t.fb < tfp2::MAX_STAGES ? t.fb : tfp2::MAX_STAGES;
+  const size_t smem = tfp2::smem_bytes(t.stages);
+  static std::atomic<unsigned long long> attr_set{0}; // per device (see launch_stencil)
+  int device = 0;
+  if (!cuda_ok(cudaGetDevice(&device), "cudaGetDevice"))
+    return false;
+  const unsigned long long dev_bit = (device >= 0 && device < 64) ? (1ull << device) : 0ull;
+  if (!(attr_set.load(std::memory_order_acquire) & dev_bit) || dev_bit == 0) {
+    if (!cuda_ok(cudaFuncSetAttribute(tfp2::tfp_tile_kernel<Op>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tfp2::smem_bytes(tfp2::MAX_STAGES)),
+                 "cudaFuncSetAttribute(tfp_tile_kernel)"))
+      return false;
+    attr_set.fetch_or(dev_bit, std::memory_order_release);
+  }
+  t.field_blocks = (nfields + t.fb - 1) / t.fb;
+  const long long ctas = tiles * t.field_blocks;
+  if (ctas > 0x7fffffffLL) {
+    set_error("fcb200: batch too large for one launch (%lld CTAs)", ctas);
+    return false;
+  }
+  tfp2::tfp_tile_kernel<Op><<<(unsigned)ctas, tfp2::THREADS, smem, call.stream()>>>(op, t);
+  const int ring = 2 * nx + 2 * (ny - 2);
+  const dim3 edge_grid((ring + tile::EDGE_THREADS - 1) / tile::EDGE_THREADS, nfields < 4096 ? nfields : 4096);
+  tile::stencil_edge_kernel<Op><<<edge_grid, tile::EDGE_THREADS, 0, call.stream()>>>(op, nx, ny, nfields, nx, t.n - nx, undef, meta, counters, true);
+  count_launch(2);
+  return true;
+}
+
 bool grid_ok(int nx, int ny, int nfields)
 {
   if (nfields <= 0 || (long long)nx * ny >= 0x7fffffffLL) {
@@ -1754,12 +1804,12 @@ int fcb200_thermalFrontParameter_batched(int nx, int ny, int nfields, const floa
   unsigned long long* counters = call.counters(2 * nfields); // [0, nfields): undefined elements of T, [nfields, 2 nfields): pass 2
   if (!call.ok())
     return -1;
-  // Default: the reference's own two passes through a scratch field -- gradient(c=3) on the tile engine, then TfpPass2Op --
-  // 20 B/point instead of the fused kernel's 8, but 1.7x faster (134 vs 79 Gpt/s on 16 ECMWF levels, 82 vs 53 with 30 % of
-  // T undefined; profiles/r01_tfp_unfused_vs_fused.txt): the fused kernel is bound by its ~210 instructions per point and
-  // four block barriers per field at 28 % occupancy, not by memory.  FCB200_TFP_FUSED=1 selects the fused kernel.
-  static const bool fused = getenv("FCB200_TFP_FUSED") != nullptr;
-  if (!fused) {
+  // Default: ONE pass over T (tfp_tile.cuh: 8 B/point, |grad T| in registers, float-float quotients).  FCB200_TFP=unfused selects the
+  // reference's own two passes through a scratch field (round 1's default: gradient(c=3) on the tile engine, then TfpPass2Op,
+  // 20 B/point); FCB200_TFP=fused_v1 round 1's fused kernel (|grad T| through shared memory, four block barriers per field).
+  static const char* mode_env = getenv("FCB200_TFP");
+  static const int mode = (mode_env && !strcmp(mode_env, "unfused")) ? 1 : (mode_env && !strcmp(mode_env, "fused_v1")) ? 2 : 0;
+  if (mode == 1) {
     float* d_ad = static_cast<float*>(call.scratch(sizeof(float) * n * nfields));
     if (!call.ok())
       return -1;
@@ -1794,7 +1844,11 @@ int fcb200_thermalFrontParameter_batched(int nx, int ny, int nfields, const floa
   op.undef_ = undef;
   op.all1 = false;
   op.o = d_out;
-  if (!launch_stencil(call, op, nx, ny, nfields, undef, meta, counters + nfields))
+  const bool tiled = nx >= 34 && n >= 8192 && !std::isnan(undef); // the tile engine's threshold (smaller grids: the flat scalar kernel); the march tests definedness with one ordered comparison
+  if (mode == 0 && tiled) {
+    if (!launch_tfp_tile(call, op, nx, ny, nfields, undef, meta, counters + nfields))
+      return -1;
+  } else if (!launch_stencil(call, op, nx, ny, nfields, undef, meta, counters + nfields))
     return -1;
   return call.finish(flags_from_counters(fDefined, nfields, n - 2 * (size_t)nx, nfields));
 }
