@@ -1184,15 +1184,15 @@ bool launch_tfp_tile(Call& call, const Op& op, int nx, int ny, int nfields, floa
     t.fb /= 2;
   if (t.fb > nfields)
     t.fb = nfields;
-  t.stages = t.fb < tfp2::MAX_STAGES ? t.fb : tfp2::MAX_STAGES;
-  const size_t smem = tfp2::smem_bytes(t.stages);
+  t.stages = tfp2::STAGES;
+  const size_t smem = tfp2::smem_bytes();
   static std::atomic<unsigned long long> attr_set{0}; // per device (see launch_stencil)
   int device = 0;
   if (!cuda_ok(cudaGetDevice(&device), "cudaGetDevice"))
     return false;
   const unsigned long long dev_bit = (device >= 0 && device < 64) ? (1ull << device) : 0ull;
   if (!(attr_set.load(std::memory_order_acquire) & dev_bit) || dev_bit == 0) {
-    if (!cuda_ok(cudaFuncSetAttribute(tfp2::tfp_tile_kernel<Op>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tfp2::smem_bytes(tfp2::MAX_STAGES)),
+    if (!cuda_ok(cudaFuncSetAttribute(tfp2::tfp_tile_kernel<Op>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tfp2::smem_bytes()),
                  "cudaFuncSetAttribute(tfp_tile_kernel)"))
       return false;
     attr_set.fetch_or(dev_bit, std::memory_order_release);
