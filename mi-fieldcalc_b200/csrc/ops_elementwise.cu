@@ -10,6 +10,7 @@
 #include "../../include/fcb200.h"
 
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -464,9 +465,10 @@ enum : unsigned {
 // KIND = HLEVEL: the last input is the surface pressure, p = alevel + blevel * ps with the field's FieldMeta::a, ::b
 // (FC.cc:303-306) -- hleveltemp, hlevelhum, whose humidity modes test `ps != undef` (no NaN test, FC.cc:1187) where the
 // a-level ones test nothing.
-template <int U_, int MB_, int J_ = 1, unsigned OUTS = O_ALL, int KIND = ALEVEL>
+template <int U_, int MB_, int J_ = 1, unsigned OUTS = O_ALL, int KIND = ALEVEL, int PK_ = 1>
 struct AlevelChainOpT
 {
+  static constexpr int PACK = PK_; // 1: two points per packed FP32 instruction (fast2), 0: one point at a time (fast)
   static constexpr bool HAS_Q = (OUTS & (O_RH | O_TD | O_THE | O_TDRH)) != 0; // q (or RH) is an input
   static constexpr bool HAS_TAB = (OUTS & (O_RH | O_TD | O_THESAT | O_TDRH)) != 0; // the saturation table is used
   static constexpr bool USES_P = (OUTS & ~O_TDRH) != 0;                          // the pressure enters the arithmetic
@@ -605,6 +607,84 @@ struct AlevelChainOpT
     return plausible;
   }
 
+  // `fast` for TWO points at once: the float arithmetic on Blackwell's packed FP32 instructions (FMUL2 / FFMA2 / FADD2: one issue
+  // slot for both points; these kernels are issue-bound, the FMA pipe is not).  Same operations, same roundings -- the packed
+  // instructions are IEEE round-to-nearest like the scalar ones; every reference expression that adds a rounded product is
+  // written with a scalar add (ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 even with -fmad=false).  The table
+  // lookups, the Exner function and the double-precision RH quotient stay per point.  Returns the implausible points as bits 0, 1.
+  __device__ __forceinline__ unsigned fast2(float2 t, float2 q, float2 p, float pi_field, const dev::EwtTable& tab, const dev::PowTable& pw, Raw& r0, Raw& r1) const
+  {
+    using namespace dev;
+    bool pl0 = !USES_P || (__float_as_uint(p.x) - 0x3c000000u < 0x09000000u); // 2^-7 <= p < 2^11
+    bool pl1 = !USES_P || (__float_as_uint(p.y) - 0x3c000000u < 0x09000000u);
+    if (Q_IS_RATIO) {
+      const unsigned u0 = __float_as_uint(q.x) & 0x7fffffffu, u1 = __float_as_uint(q.y) & 0x7fffffffu;
+      pl0 = pl0 && ((u0 - 0x12800000u < 0x37000000u) || __float_as_uint(q.x) == 0u); // 2^-90 <= |q| < 2^20, or +0
+      pl1 = pl1 && ((u1 - 0x12800000u < 0x37000000u) || __float_as_uint(q.y) == 0u);
+    }
+    if (!HAS_TAB) {
+      pl0 = pl0 && ((__float_as_uint(t.x) & 0x7fffffffu) - 0x22000000u < 0x3b000000u); // 2^-59 <= |t| < 2^59
+      pl1 = pl1 && ((__float_as_uint(t.y) & 0x7fffffffu) - 0x22000000u < 0x3b000000u);
+    }
+    float2 pi = make_float2(pi_field, pi_field);
+    if (HAS_POW) {
+      const float2 arg = pk_mul(p, K_P0INV);                                                                       // FC.cc:308-311
+      const float2 pidcp = make_float2(pw.pow_normal<POW_KAPPA>(arg.x), pw.pow_normal<POW_KAPPA>(arg.y));
+      pi = pk_mul(pidcp, K_CP);                                                                                    // FC.cc:313-316
+      if (OUTS & O_THETA) {
+        const float2 th = pk_div_midrange(t, pidcp);
+        r0.theta = th.x, r1.theta = th.y;
+      }
+      if (OUTS & O_THE) {
+        const float2 the = pk_div_midrange(pk_add_products(pk_mul(t, K_CP), pk_mul(q, K_XLH)), pi);
+        r0.the = the.x, r1.the = the.y;
+      }
+    }
+    if (HAS_TAB) {
+      const float2 tc = pk_add(t, -K_T0);
+      const float x0 = (float)(((double)tc.x + 100.) * c_dconst[0]), x1 = (float)(((double)tc.y + 100.) * c_dconst[0]); // Ewt::Ewt, MC.h:66
+      pl0 = pl0 && (__float_as_uint(x0) < 0x42200000u); // +0 <= x < 40
+      pl1 = pl1 && (__float_as_uint(x1) < 0x42200000u);
+      const int l0 = pl0 ? (int)x0 : 0, l1 = pl1 ? (int)x1 : 0;
+      const float2 e0 = tab.e[l0], e1 = tab.e[l1];
+      const float2 et = make_float2(e0.x + e0.y * (x0 - (float)l0), e1.x + e1.y * (x1 - (float)l1)); // MC.h:78
+      const float2 qsat = pk_div_midrange(pk_mul(et, K_EPS), p);
+      if (OUTS & O_THESAT) {
+        const float2 ts = pk_div_midrange(pk_add_products(pk_mul(t, K_CP), pk_mul(qsat, K_XLH)), pi); // t_thesat, FC.cc:196-205
+        r0.thesat = ts.x, r1.thesat = ts.y;
+      }
+      if (OUTS & O_RH) {
+        r0.rh = (float)div_midrange(100. * (double)q.x, (double)qsat.x); // FC.cc:229
+        r1.rh = (float)div_midrange(100. * (double)q.y, (double)qsat.y);
+      }
+      // dew point from a relative humidity (see `fast`)
+      auto dewpoint2 = [&](float2 rh) {
+        const float2 rhc = make_float2(rh.x < K_RHMIN ? K_RHMIN : (rh.x > K_RHMAX ? K_RHMAX : rh.x), rh.y < K_RHMIN ? K_RHMIN : (rh.y > K_RHMAX ? K_RHMAX : rh.y));
+        const float2 etd = pk_mul(rhc, et);
+        int b0 = (int)(__float_as_uint(etd.x) >> 21) - EWT_LUT0, b1 = (int)(__float_as_uint(etd.y) >> 21) - EWT_LUT0;
+        b0 = min(max(b0, 0), EWT_NLUT - 1), b1 = min(max(b1, 0), EWT_NLUT - 1);
+        int ll0 = min((int)tab.lut[b0], l0), ll1 = min((int)tab.lut[b1], l1);
+        const int k0 = min(ll0 + 1, l0), k1 = min(ll1 + 1, l1);
+        ll0 = (tab.e[k0].x > etd.x) ? ll0 : k0;
+        ll1 = (tab.e[k1].x > etd.y) ? ll1 : k1;
+        const float2 f0 = tab.e[ll0], f1 = tab.e[ll1];
+        const float2 quo = pk_div_midrange(make_float2(etd.x - f0.x, etd.y - f1.x), make_float2(f0.y, f1.y));
+        const float2 y = pk_add(make_float2((float)ll0, (float)ll1), quo);
+        return pk_add(pk_fma(make_float2(5.f, 5.f), y, make_float2(-100.f, -100.f)), tdconv);
+      };
+      if (OUTS & O_TD) {
+        const float2 td = dewpoint2(pk_div_midrange(q, qsat));
+        r0.td = td.x, r1.td = td.y;
+      }
+      if (OUTS & O_TDRH) {
+        const float2 td = dewpoint2(make_float2((float)(0.01 * (double)q.x), (float)(0.01 * (double)q.y)));
+        r0.tdrh = td.x, r1.tdrh = td.y;
+      }
+    }
+    r0.edef = true, r1.edef = true;
+    return (pl0 ? 0u : 1u) | (pl1 ? 0u : 2u);
+  }
+
   // definedness tests of the reference calls + one counter per output
   template <bool ALL>
   __device__ __forceinline__ void finish(float t, float q, float p, const Raw& r, const PointCtx& c, float* out, unsigned* nundef) const
@@ -671,6 +751,25 @@ struct AlevelChainOpT
     return plausible || !live;
   }
 
+  // `eval` for two points (bits 0, 1 of the result: the point needs the IEEE redo)
+  template <bool ALL>
+  __device__ __forceinline__ unsigned eval2(float2 t, float2 q, float2 praw, const PointCtx& c, Raw& r0, Raw& r1) const
+  {
+    const bool dq0 = ALL || !HAS_Q || is_def(q.x, c.undef), dq1 = ALL || !HAS_Q || is_def(q.y, c.undef);
+    const float2 qe = make_float2(dq0 ? q.x : 0.f, dq1 ? q.y : 0.f);
+    const float2 pl = make_float2(level_p(praw.x, c), level_p(praw.y, c));
+    const unsigned implausible = fast2(t, qe, pl, c.m.b, c.tab, c.pw, r0, r1);
+    if (ALL)
+      return implausible;
+    auto live = [&](float tt, bool dq, float pr) {
+      const bool dt = is_def(tt, c.undef), dp = KIND == PLEVEL || is_def(pr, c.undef);
+      const bool hum_live = (OUTS & (O_RH | O_TD)) != 0 && dq && (KIND != HLEVEL || pr != c.undef);
+      return dt && (hum_live || ((OUTS & O_TDRH) && dq && (KIND != ALEVEL || pr != c.undef)) || ((OUTS & O_THESAT) && dp) ||
+                    (HAS_POW && dp && ((OUTS & O_THETA) || dq)));
+    };
+    return (((implausible & 1u) && live(t.x, dq0, praw.x)) ? 1u : 0u) | (((implausible & 2u) && live(t.y, dq1, praw.y)) ? 2u : 0u);
+  }
+
   // The IEEE redo of one point.  If the field is not ALL_DEFINED and p (ps) itself is undefined, theta and theta_e are undefined
   // whatever the arithmetic says and only RH / Td -- into which the undefined p flows (FC.cc:1429) -- are needed: that redo is
   // the humidity-only instantiation, without the Exner function.
@@ -680,8 +779,8 @@ struct AlevelChainOpT
     constexpr unsigned HUM = OUTS & (O_RH | O_TD);
     if constexpr (!ALL && HUM != 0 && HUM != OUTS && KIND != PLEVEL) {
       if (!is_def(praw, c.undef)) {
-        typename AlevelChainOpT<U_, MB_, J_, HUM, KIND>::Raw h;
-        AlevelChainOpT<U_, MB_, J_, HUM, KIND>::ieee_raw(t, q, level_p(praw, c), c.tab, c.pw, tdconv, c.m.b, h);
+        typename AlevelChainOpT<U_, MB_, J_, HUM, KIND, PK_>::Raw h;
+        AlevelChainOpT<U_, MB_, J_, HUM, KIND, PK_>::ieee_raw(t, q, level_p(praw, c), c.tab, c.pw, tdconv, c.m.b, h);
         r.rh = h.rh;
         r.td = h.td;
         r.edef = h.edef;
@@ -709,10 +808,20 @@ struct AlevelChainOpT
   {
     Raw r[4];
     unsigned bad = 0;
+    if constexpr (PACK != 0) {
 #pragma unroll
-    for (int w = 0; w < 4; ++w) {
-      const float q = HAS_Q ? in[1][w] : 0.f;
-      bad |= eval<ALL>(in[0][w], q, KIND == PLEVEL ? 0.f : in[NIN - 1][w], c, r[w]) ? 0u : (1u << w);
+      for (int w = 0; w < 4; w += 2) {
+        const float2 t = make_float2(in[0][w], in[0][w + 1]);
+        const float2 q = HAS_Q ? make_float2(in[1][w], in[1][w + 1]) : make_float2(0.f, 0.f);
+        const float2 pr = KIND == PLEVEL ? make_float2(0.f, 0.f) : make_float2(in[NIN - 1][w], in[NIN - 1][w + 1]);
+        bad |= eval2<ALL>(t, q, pr, c, r[w], r[w + 1]) << w;
+      }
+    } else {
+#pragma unroll
+      for (int w = 0; w < 4; ++w) {
+        const float q = HAS_Q ? in[1][w] : 0.f;
+        bad |= eval<ALL>(in[0][w], q, KIND == PLEVEL ? 0.f : in[NIN - 1][w], c, r[w]) ? 0u : (1u << w);
+      }
     }
     if (bad) {
 #pragma unroll
@@ -1157,7 +1266,10 @@ int fcb200_alevel_chain_batched(int nx, int ny, int nfields, const float* t, con
   // Kernel shape (measured on B200, profiles/r01_chain_tuning.txt): 2 float4 groups per thread and round, 4 rounds per
   // item, 2 CTAs of 256 threads per SM (<= 128 registers: the straight-line code of 8 interleaved points needs
   // them; 64- and 80-register builds spill and lose 10-15 %).
-  return run(AlevelChainOpT<2, 2, 4, O_ALL>{tdconv});
+  // The four-output chain keeps the one-point-at-a-time form: with eight points in flight per thread at 127 registers the packed
+  // form (fast2) measured 146.6 Gpt/s against 150.7 (151.8 with one group per round) -- profiles/r02_chain_packed.txt; the one- and
+  // two-output operators, which have registers to spare, gain 2 - 7 % from it.
+  return run(AlevelChainOpT<2, 2, 4, O_ALL, ALEVEL, 0>{tdconv});
 }
 
 int fcb200_hlevel_chain_batched(int nx, int ny, int nfields, const float* t, const float* q, const float* ps, const float* alevel, const float* blevel,
@@ -1169,7 +1281,7 @@ int fcb200_hlevel_chain_batched(int nx, int ny, int nfields, const float* t, con
   if (nfields > 0 && any_bad_hlevel(make_batch(nx, ny, nfields), alevel, blevel))
     return 0; // FC.cc:1070, 1121, 1170
   const int td_compute = hum_compute(5, td_unit);
-  EwJob<AlevelChainOpT<2, 2, 4, O_ALL, HLEVEL>> job;
+  EwJob<AlevelChainOpT<2, 2, 4, O_ALL, HLEVEL, 0>> job;
   job.nx = nx;
   job.ny = ny;
   job.nfields = nfields;
@@ -1190,7 +1302,7 @@ int fcb200_hlevel_chain_batched(int nx, int ny, int nfields, const float* t, con
     m.a = alevel[k];
     m.b = blevel[k];
   };
-  return run_ew_job(AlevelChainOpT<2, 2, 4, O_ALL, HLEVEL>{(td_compute >= 9) ? H_T0 : 0.f}, job);
+  return run_ew_job(AlevelChainOpT<2, 2, 4, O_ALL, HLEVEL, 0>{(td_compute >= 9) ? H_T0 : 0.f}, job);
 }
 
 } // extern "C"
