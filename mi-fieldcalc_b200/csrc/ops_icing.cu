@@ -183,12 +183,19 @@ struct ModStallOp
       cw = 1.0;
       double err = 1.0;
       int j = 0;
+      // The reference iterates until |c_new - c| <= 1e-5 or 10001 times, then gives up with c = 0.  An iterate that EQUALS the one
+      // two steps back closes a cycle: the same two values and the same error repeat for ever, so if that error is above the
+      // tolerance the loop can only end at its cap, with c = 0 -- decided here at once, same result.  (An undefined period,
+      // which the reference does not test, FC VI.cc:208, makes c jump between 1 and g*depth: 10001 tanh per point otherwise.)
+      double c_before = __longlong_as_double(0x7ff8000000000000LL); // NaN: equals nothing
       while (err > 1e-5) {
         const double c_new = (9.81 * (double)Pw / (2 * M_PI)) * tanh(2 * M_PI * (double)depth / ((double)Pw * cw));
         err = fabs(c_new - cw);
+        const bool cycle = c_new == c_before && err > 1e-5;
+        c_before = cw;
         cw = c_new;
         j = j + 1;
-        if (j > 10000) {
+        if (j > 10000 || cycle) {
           cw = 0.0;
           break;
         }
@@ -328,12 +335,19 @@ struct MincogOp
       int j = 0;
       const float a = (float)(2 * M_PI * (double)depth / (double)Pw);
 #pragma unroll 1
+      float c_before = __int_as_float(0x7fc00000); // NaN: equals nothing
       for (; j < 1000; ++j) {
         const float c_new = (float)((double)c_0 * tanh((double)(a / c)));
         const float err = fabsf(c_new - c);
+        const bool cycle = c_new == c_before; // (see ModStallOp: the iterates repeat with this error for ever)
+        c_before = c;
         c = c_new;
         if ((double)err <= 1e-5)
           break;
+        if (cycle) {
+          j = 1000;
+          break;
+        }
       }
       if (j >= 1000)
         c = 0;
