@@ -133,11 +133,11 @@ __global__ void __launch_bounds__(ST_THREADS) stencil_kernel(const Op op0, const
 
 __device__ __forceinline__ bool def2(float a, float b, float undef)
 {
-  return is_def(a, undef) && is_def(b, undef);
+  return is_def(a, undef) & is_def(b, undef);
 }
 __device__ __forceinline__ bool def4(float a, float b, float c, float d, float undef)
 {
-  return is_def(a, undef) && is_def(b, undef) && is_def(c, undef) && is_def(d, undef);
+  return is_def(a, undef) & is_def(b, undef) & is_def(c, undef) & is_def(d, undef); // (bitwise: no short-circuit branches)
 }
 
 // centred difference times map ratio, evaluated like `0.5 * mapr[i] * (f[i+d] - f[i-d])`:
@@ -251,8 +251,8 @@ struct VortDivOp
     bool ok = true;
     if (!ALL)
       ok = (MODE == 2) ? def4(r.ta, r.tb, r.tc, r.td, undef) : def4(r.a, r.b, r.c, r.d, undef);
-    if (!ok)
-      return false;
+    // (no early return: a warp computes as soon as ONE of its points is defined, so the undefined ones cost nothing extra and
+    // the branch around the arithmetic only adds instructions and divergence; the caller selects by `ok`)
     // 0.5*xm*dx -+ 0.5*ym*dy: the products of two floats are exact in double and so is the scaling by 0.5,
     // hence RN(0.5*px -+ 0.5*py) = 0.5 * RN(px -+ py) = 0.5 * fma(-+ym, dy, px): three double instructions
     const double px = (double)r.xm * (double)(r.b - r.a);
@@ -329,9 +329,7 @@ struct AdvectionOp
   {
     bool ok = true;
     if (!ALL)
-      ok = def2(r.ui, r.vi, undef) && def4(r.fd, r.fl, r.fr, r.fu, undef);
-    if (!ok)
-      return false;
+      ok = def2(r.ui, r.vi, undef) & def4(r.fd, r.fl, r.fr, r.fu, undef);
     const double ax = (double)r.ui * 0.5 * (double)r.xm * (double)(r.fr - r.fl);
     const double ay = (double)r.vi * 0.5 * (double)r.ym * (double)(r.fu - r.fd);
     val[0] = (float)((ax + ay) * (double)scale);
@@ -418,9 +416,7 @@ struct GradientOp
       else if (COMPUTE == 3)
         ok = def4(r.fd, r.fl, r.fr, r.fu, undef);
       else
-        ok = def4(r.fd, r.fl, r.fr, r.fu, undef) && is_def(r.fc, undef);
-      if (!ok)
-        return false;
+        ok = def4(r.fd, r.fl, r.fr, r.fu, undef) & is_def(r.fc, undef);
     }
     if (COMPUTE == 1) {
       val[0] = half_map_diff_f<FAST>(r.xm, r.fr, r.fl);
@@ -508,9 +504,7 @@ struct JacobianOp
   {
     bool ok = true;
     if (!ALL)
-      ok = def4(r.ad, r.al, r.ar, r.au, undef) && def4(r.bd, r.bl, r.br, r.bu, undef);
-    if (!ok)
-      return false;
+      ok = def4(r.ad, r.al, r.ar, r.au, undef) & def4(r.bd, r.bl, r.br, r.bu, undef);
     const float df1dx = half_map_diff_f<FAST>(r.xm, r.ar, r.al);
     const float df1dy = half_map_diff_f<FAST>(r.ym, r.au, r.ad);
     const float df2dx = half_map_diff_f<FAST>(r.xm, r.br, r.bl);
