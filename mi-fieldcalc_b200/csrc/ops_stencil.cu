@@ -425,7 +425,10 @@ struct GradientOp
     } else if (COMPUTE == 3) {
       const float dfdx = half_map_diff_f<FAST>(r.xm, r.fr, r.fl);
       const float dfdy = half_map_diff_f<FAST>(r.ym, r.fu, r.fd);
-      val[0] = dev::absval(dfdx, dfdy);
+      // dev::absval; an undefined point (its value is dropped by the caller) takes sqrtf(1): the huge sums of squares of `undef`
+      // operands would send its lane, and with it the warp, through sqrtf's out-of-range path
+      const float s2 = dfdx * dfdx + dfdy * dfdy;
+      val[0] = sqrtf(ALL ? s2 : (ok ? s2 : 1.f));
     } else {
       const float d2fdx = (float)((double)r.fl - 2.0 * (double)r.fc + (double)r.fr);
       const float d2fdy = (float)((double)r.fd - 2.0 * (double)r.fc + (double)r.fu);
