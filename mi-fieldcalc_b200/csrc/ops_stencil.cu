@@ -1289,6 +1289,23 @@ __device__ __forceinline__ float shapiro_point_float(float lo, float f, float hi
   inexact = inexact || !(err == 0.f);
   return __fmaf_rn(sf, T, f);
 }
+// shapiro_point_float for two adjacent columns at once on the packed FP32 instructions (FADD2 / FFMA2: one issue slot per pair;
+// same IEEE operations -- there is no product followed by an add here for ptxas to contract)
+__device__ __forceinline__ float2 shapiro_pair_float(float2 lo, float2 f, float2 hi, float sf, bool& inexact)
+{
+  const float2 S = __fadd2_rn(lo, hi);
+  const float2 b = __fadd2_rn(f, f);
+  const float2 nb = make_float2(-b.x, -b.y);
+  const float2 T = __fadd2_rn(S, nb);
+  const float2 a1 = __fadd2_rn(T, b);
+  const float2 b1 = __fadd2_rn(T, make_float2(-a1.x, -a1.y));
+  const float2 da = __fadd2_rn(S, make_float2(-a1.x, -a1.y));
+  const float2 db = __fadd2_rn(nb, make_float2(-b1.x, -b1.y));
+  const float2 err = __fadd2_rn(da, db);
+  inexact = inexact || !(err.x == 0.f) || !(err.y == 0.f);
+  return __ffma2_rn(make_float2(sf, sf), T, f);
+}
+
 template <int W, bool ALL, bool FLOATPATH>
 __device__ __forceinline__ void shapiro_pass(const float (&lo)[W], const float (&f)[W], const float (&hi)[W], float (&r)[W], float s, unsigned wbits)
 {
@@ -1300,9 +1317,18 @@ __device__ __forceinline__ void shapiro_pass(const float (&lo)[W], const float (
     }
   } else if (FLOATPATH) {
     bool inexact = false;
+    if constexpr (W == 4) {
 #pragma unroll
-    for (int j = 0; j < W; ++j)
-      r[j] = shapiro_point_float(lo[j], f[j], hi[j], s, inexact);
+      for (int j = 0; j < W; j += 2) {
+        const float2 v = shapiro_pair_float(make_float2(lo[j], lo[j + 1]), make_float2(f[j], f[j + 1]), make_float2(hi[j], hi[j + 1]), s, inexact);
+        r[j] = v.x;
+        r[j + 1] = v.y;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < W; ++j)
+        r[j] = shapiro_point_float(lo[j], f[j], hi[j], s, inexact);
+    }
     if (__any_sync(0xffffffffu, inexact)) { // rare, warp-uniform: a real branch, not a select
 #pragma unroll
       for (int j = 0; j < W; ++j)
@@ -1426,7 +1452,7 @@ __device__ __forceinline__ void shapiro_band(const float* __restrict__ src, floa
       shapiro_ypass<W, ALL, true>(a0, a1, a2, b, 0.25f, my, r - 1 <= 0 || r - 1 >= ny - 1);
       // iteration 2: x pass on row r-1, y pass on row r-2
       shapiro_xpass<W, ALL, true>(b, c2, -0.25f, mx_prev, copybits);
-      shapiro_ypass<W, ALL, false>(c0, c1, c2, d, -0.25f, my_prev, r - 2 <= 0 || r - 2 >= ny - 1);
+      shapiro_ypass<W, ALL, W == 4>(c0, c1, c2, d, -0.25f, my_prev, r - 2 <= 0 || r - 2 >= ny - 1); // (W = 4: the packed float form for all four passes)
       const int ro = r - 2;
       if (store_lane && ro >= r0 && ro < r1) {
         float* p = dst + (long long)ro * nx + x0;
