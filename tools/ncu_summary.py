@@ -56,6 +56,19 @@ def main():
     w = [max(len(r[c]) for r in table) for c in range(len(table[0]))]
     for r in table:
         print("  ".join(x.ljust(w[c]) if c == 0 else x.rjust(w[c]) for c, x in enumerate(r)))
+    if "--traffic" in sys.argv:
+        # dram__bytes_read.sum + dram__bytes_write.sum of the LAST profiled launch, for bench.py's roofline.traffic
+        import json
+        import os
+        out_path = sys.argv[sys.argv.index("--traffic") + 1]
+        rd_i, wr_i = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
+        scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+        r = rows[-1]
+        total = float(r[rd_i].replace(",", "")) * scale.get(units[rd_i], 1.0) + float(r[wr_i].replace(",", "")) * scale.get(units[wr_i], 1.0)
+        json.dump({"bytes_per_launch": total, "kernel": r[name_i][:120],
+                   "source": "%s (ncu --set full --clock-control none, dram__bytes_read.sum + dram__bytes_write.sum of one launch)" % os.path.basename(rep)},
+                  open(out_path, "w"), indent=1)
+        print("traffic: %.1f MB per launch -> %s" % (total / 1e6, out_path))
     if "--csv" in sys.argv:
         with open(sys.argv[sys.argv.index("--csv") + 1], "w", newline="") as f:
             csv.writer(f).writerows(table)

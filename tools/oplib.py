@@ -64,9 +64,10 @@ class Inputs:
 
 
 class Row:
-    def __init__(self, name, cfg, call, grid, nf, bpp, items, masked=None, cpu_rows=None, note=None):
+    def __init__(self, name, cfg, call, grid, nf, bpp, items, masked=None, cpu_rows=None, note=None, common_mask=False):
         self.name, self.cfg, self.call, self.grid, self.nf, self.bpp, self.items = name, cfg, call, grid, nf, bpp, items
         self.masked = masked          # None = follow the run's mask; a number pins it (cfg4's 5 %)
+        self.common_mask = common_mask  # the SAME points are undefined in every per-field input (a land/sea or below-ground mask)
         self.cpu_rows = cpu_rows      # rows of the grid in the CPU sample (None = the whole field)
         self.note = note
 
@@ -150,7 +151,11 @@ def rows(levels_cfg3=137, nt_cfg4=8):
         Row("jacobian_masked30", "cfg5", "jacobian_batched", MEPS, 64, 12, _stencil(2), masked=m),
         Row("thermalFrontParameter_masked30", "cfg5", "thermalFrontParameter_batched", MEPS, 96, 8, _stencil(1), masked=m),
         Row("shapiro2_filter_masked30", "cfg5", "shapiro2_filter_batched", MEPS, 96, 8, ["nx", "ny", "nf", ("F", "tens"), "OUT", "FLAGS", "UNDEF"], masked=m),
-        Row("alevelhum_c5_masked30", "cfg5", "alevelhum_batched", MEPS, 65, 16, _ew(["t", "q", "p"], ("celsius", 5)), masked=m),
+        Row("alevelhum_c5_masked30", "cfg5", "alevelhum_batched", MEPS, 65, 16, _ew(["t", "q", "p"], ("celsius", 5)), masked=m,
+            note="t, q and p undefined INDEPENDENTLY: 15 % of the points have a defined t, q over an undefined p, which the reference lets flow into "
+                 "RH and Td (FC.cc:1429) -- they take the IEEE redo"),
+        Row("alevelhum_c5_masked30_common", "cfg5", "alevelhum_batched", MEPS, 65, 16, _ew(["t", "q", "p"], ("celsius", 5)), masked=m, common_mask=True,
+            note="the same 30 % of the points undefined in t, q and p (one mask for the level, as below-ground points are)"),
     ]
     return r
 
@@ -210,6 +215,9 @@ class Built:
         grid_const = {}
         for _ in range(sets):
             args, flag_arrays = [], []
+            shared = None
+            if row.common_mask and self.mask > 0:
+                shared = torch.rand((nf, ny, nx), device=inputs.device, generator=inputs.gen) < self.mask
             for it in row.items:
                 if it == "nx":
                     args.append(nx)
@@ -229,7 +237,12 @@ class Built:
                     f = np.full(nf * self._M(), flag, np.int32)
                     args.append(f)
                 elif it[0] == "F":
-                    args.append(inputs.field(it[1], row.grid, nf, self.mask))
+                    if shared is not None:
+                        a = inputs.field(it[1], row.grid, nf, 0.0)
+                        a[shared] = UNDEF
+                        args.append(a)
+                    else:
+                        args.append(inputs.field(it[1], row.grid, nf, self.mask))
                 elif it[0] == "G":
                     if it[1] not in grid_const:
                         grid_const[it[1]] = inputs.field(it[1], row.grid)

@@ -88,7 +88,7 @@ def _run(gpu, torch, dist, dev, stream, rank, world, nx, ny, nf, steps, mask, se
     tmp_full = torch.empty((nf, ny, nx), device=dev)
     results = []
 
-    def record(name, halo, full_fn, slab_fn, out_ext, part, exchanges_per_step):
+    def record(name, halo, full_fn, slab_fn, out_ext, part, exchanges_per_step, exchange_fn=None, compute_fn=None):
         r0, r1, lo, hi = part
         flags_full = np.full(nf, flag_in, np.int32)
         flags_slab = np.full(nf, flag_in, np.int32)
@@ -116,7 +116,14 @@ def _run(gpu, torch, dist, dev, stream, rank, world, nx, ny, nf, steps, mask, se
             dist.all_reduce(stats, op=dist.ReduceOp.SUM)
         bad_all, sent_all, combine_sum = stats.tolist()
         step_ms = tn + combine_sum / world * 1e-3
-        results.append({"step": name, "halo_rows": halo, "ms_whole_grid_one_gpu": t1, "ms_slab_step": tn, "flag_combine_us": combine_sum / world,
+        # where the step goes: the halo exchange alone and the operators on the extended slab alone (each max over ranks)
+        parts = {}
+        if exchange_fn is not None:
+            parts["ms_exchange_only"] = timed(exchange_fn, steps)
+        if compute_fn is not None:
+            parts["ms_operators_only"] = timed(lambda: compute_fn(flags_slab), steps)
+        parts["ms_ideal"] = t1 / world
+        results.append({"breakdown": parts,"step": name, "halo_rows": halo, "ms_whole_grid_one_gpu": t1, "ms_slab_step": tn, "flag_combine_us": combine_sum / world,
                         "ms_slab_step_with_flags": step_ms, "speedup": t1 / step_ms, "efficiency_vs_one_gpu": t1 / (world * step_ms),
                         "nvlink_payload_bytes_per_step_all_ranks": sent_all, "exchanges_per_step": exchanges_per_step,
                         "bit_identical_to_single_gpu": bad_all == 0, "mismatches": int(bad_all),
@@ -139,7 +146,11 @@ def _run(gpu, torch, dist, dev, stream, rank, world, nx, ny, nf, steps, mask, se
         gpu.slab_exchange(ef, nx, hi - lo, nf, 1)
         gpu.call("advection_batched", nx, hi - lo, nf, ef, eu, ev, exm, eym, 1.0, eo, flags, UNDEF)
 
-    record("advection", 1, adv_full, adv_slab, eo, p1, 1)
+    def adv_compute(flags):
+        flags[:] = flag_in
+        gpu.call("advection_batched", nx, hi - lo, nf, ef, eu, ev, exm, eym, 1.0, eo, flags, UNDEF)
+
+    record("advection", 1, adv_full, adv_slab, eo, p1, 1, lambda: gpu.slab_exchange(ef, nx, hi - lo, nf, 1), adv_compute)
     del ef, eu, ev, eo, u, v
     torch.cuda.empty_cache()
 
@@ -160,7 +171,11 @@ def _run(gpu, torch, dist, dev, stream, rank, world, nx, ny, nf, steps, mask, se
         gpu.slab_exchange(et, nx, hi - lo, nf, 2)
         gpu.call("thermalFrontParameter_batched", nx, hi - lo, nf, et, exm, eym, eo, flags, UNDEF)
 
-    record("thermalFrontParameter", 2, tfp_full, tfp_slab, eo, p2, 1)
+    def tfp_compute(flags):
+        flags[:] = flag_in
+        gpu.call("thermalFrontParameter_batched", nx, hi - lo, nf, et, exm, eym, eo, flags, UNDEF)
+
+    record("thermalFrontParameter", 2, tfp_full, tfp_slab, eo, p2, 1, lambda: gpu.slab_exchange(et, nx, hi - lo, nf, 2), tfp_compute)
 
     # ---- shapiro2_filter -> thermalFrontParameter: the smoothed field's halo rows have to be exchanged
     et = ext_of(f, lo, hi, r0, r1, False)  # static input scattered with its halo: no exchange needed for it
@@ -180,7 +195,13 @@ def _run(gpu, torch, dist, dev, stream, rank, world, nx, ny, nf, steps, mask, se
         flags[:] = 0
         gpu.call("thermalFrontParameter_batched", nx, hi - lo, nf, es, exm, eym, eo, flags, UNDEF)
 
-    record("shapiro2_filter->thermalFrontParameter", 2, chain_full, chain_slab, eo, p2, 1)
+    def chain_compute(flags):
+        sflags[:] = flag_in
+        gpu.call("shapiro2_filter_batched", nx, hi - lo, nf, et, es, sflags, UNDEF)
+        flags[:] = 0
+        gpu.call("thermalFrontParameter_batched", nx, hi - lo, nf, es, exm, eym, eo, flags, UNDEF)
+
+    record("shapiro2_filter->thermalFrontParameter", 2, chain_full, chain_slab, eo, p2, 1, lambda: gpu.slab_exchange(es, nx, hi - lo, nf, 2), chain_compute)
     rows = [gpu.slab_partition(ny, 2, r, world) for r in range(world)]
     return {"grid": [nx, ny], "levels": nf, "mask": mask, "ranks": world, "rows_per_rank": [p[1] - p[0] for p in rows],
             "transport": "ncclSend/ncclRecv from C++ (fcb200_slab_exchange): pack kernel -> one grouped send/recv pair per neighbour -> unpack kernel, "
