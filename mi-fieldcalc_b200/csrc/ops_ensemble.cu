@@ -87,29 +87,6 @@ __device__ __forceinline__ void ensemble_points(const EnsArgs& a, const float* c
     } else {
       x[0] = mptr[j][moff + base];
     }
-    if constexpr (MODE == EN_STDDEV && FAST && W == 4) {
-      // the all-defined Welford update for two points per instruction (FADD2 / FMUL2 / FFMA2: one issue slot per pair; the kernel is
-      // issue-bound).  Same operations and roundings as the scalar form below; `m2 += delta * (x - m)` adds a rounded PRODUCT, which
-      // ptxas would contract into an FFMA2 if the add were packed too (it does so even with -fmad=false): scalar adds there.
-      const float2 nn = make_float2(ny.x, ny.x), yy = make_float2(ny.y, ny.y);
-#pragma unroll
-      for (int w = 0; w < W; w += 2) {
-        const float2 xv = make_float2(x[w], x[w + 1]);
-        float2 m = make_float2(acc0[w], acc0[w + 1]);
-        const float2 delta = __fadd2_rn(xv, make_float2(-m.x, -m.y));
-        const float2 q0 = __fmul2_rn(delta, yy);
-        const float2 rem = __ffma2_rn(make_float2(-q0.x, -q0.y), nn, delta);
-        m = __fadd2_rn(m, __ffma2_rn(rem, yy, q0));
-        const float2 p = __fmul2_rn(delta, __fadd2_rn(xv, make_float2(-m.x, -m.y)));
-        acc0[w] = m.x;
-        acc0[w + 1] = m.y;
-        acc1[w] = __fadd_rn(acc1[w], p.x);
-        acc1[w + 1] = __fadd_rn(acc1[w + 1], p.y);
-        dmax = fmaxf(dmax, fmaxf(fabsf(delta.x), fabsf(delta.y))); // (a NaN delta makes the result NaN on either path)
-        dmin = fminf(dmin, fminf(fabsf(delta.x), fabsf(delta.y)));
-      }
-      continue;
-    }
 #pragma unroll
     for (int w = 0; w < W; ++w) {
       const float xv = x[w];
