@@ -168,7 +168,11 @@ __device__ __forceinline__ void ensemble_points(const EnsArgs& a, const float* c
     out[base] = r[0];
 }
 
-template <int MODE, int W>
+// TG (tables_global) = the member tables are too large for shared memory (more than 2048 members): read from the device tables
+// directly, the time offset added at each use.  A separate instantiation: the common kernel keeps its tables in shared memory
+// with shared-memory loads and no offset arithmetic (as one kernel with a run-time switch, generic loads and a 64-bit add per
+// member load cost stddevValue a fifth of its throughput: 0.82 -> 0.64 of the roofline).
+template <int MODE, int W, bool TG>
 __global__ void __launch_bounds__(EN_THREADS) ensemble_kernel(const EnsArgs a)
 {
   extern __shared__ unsigned char smem_raw[];
@@ -176,27 +180,21 @@ __global__ void __launch_bounds__(EN_THREADS) ensemble_kernel(const EnsArgs a)
   const int chunk = blockIdx.x - time * a.chunks;
   const int M = a.nmembers;
   const long long n = a.n;
-  // the member tables of this time step: staged in shared memory, or -- for ensembles too large for that
-  // (tables_global) -- read from the device tables directly, the time offset added at each use
-  const float* const* mptr = a.members;
-  const int* mflag = a.member_flags + (long long)time * M;
-  const float2* recip = reinterpret_cast<const float2*>(a.recip);
-  long long moff = (long long)time * n;
-  if (!a.tables_global) {
-    const float** s_ptr = reinterpret_cast<const float**>(smem_raw);
-    float2* s_recip = reinterpret_cast<float2*>(smem_raw + sizeof(float*) * M);
-    int* s_flag = reinterpret_cast<int*>(smem_raw + (sizeof(float*) + sizeof(float2)) * M);
+  const float** s_ptr = reinterpret_cast<const float**>(smem_raw);
+  float2* s_recip = reinterpret_cast<float2*>(smem_raw + sizeof(float*) * M);
+  int* s_flag = reinterpret_cast<int*>(smem_raw + (sizeof(float*) + sizeof(float2)) * M);
+  if (!TG) {
     for (int j = threadIdx.x; j < M; j += EN_THREADS) {
-      s_ptr[j] = a.members[j] + moff;
-      s_flag[j] = mflag[j];
-      s_recip[j] = recip[j];
+      s_ptr[j] = a.members[j] + (long long)time * n;
+      s_flag[j] = a.member_flags[(long long)time * M + j];
+      s_recip[j] = reinterpret_cast<const float2*>(a.recip)[j];
     }
     __syncthreads();
-    mptr = s_ptr;
-    mflag = s_flag;
-    recip = s_recip;
-    moff = 0;
   }
+  const float* const* mptr = TG ? a.members : s_ptr;
+  const int* mflag = TG ? a.member_flags + (long long)time * M : s_flag;
+  const float2* recip = TG ? reinterpret_cast<const float2*>(a.recip) : s_recip;
+  const long long moff = TG ? (long long)time * n : 0;
 
   // per-time peel so that the float4 groups are 16-byte aligned (see elementwise.cuh)
   const int head = (W == 4) ? ((4 - ((a.align0 + (int)(((long long)time * n) & 3)) & 3)) & 3) : 0;
@@ -359,10 +357,15 @@ int run_ensemble(const EnsHost& h)
 
 #define FCB_LAUNCH_ENS(MODE)                                                                                                                         \
   do {                                                                                                                                               \
-    if (vec)                                                                                                                                         \
-      ensemble_kernel<MODE, 4><<<(unsigned)grid, EN_THREADS, smem, call.stream()>>>(a);                                                             \
+    if (a.tables_global) {                                                                                                                           \
+      if (vec)                                                                                                                                       \
+        ensemble_kernel<MODE, 4, true><<<(unsigned)grid, EN_THREADS, smem, call.stream()>>>(a);                                                     \
+      else                                                                                                                                           \
+        ensemble_kernel<MODE, 1, true><<<(unsigned)grid, EN_THREADS, smem, call.stream()>>>(a);                                                     \
+    } else if (vec)                                                                                                                                  \
+      ensemble_kernel<MODE, 4, false><<<(unsigned)grid, EN_THREADS, smem, call.stream()>>>(a);                                                      \
     else                                                                                                                                             \
-      ensemble_kernel<MODE, 1><<<(unsigned)grid, EN_THREADS, smem, call.stream()>>>(a);                                                             \
+      ensemble_kernel<MODE, 1, false><<<(unsigned)grid, EN_THREADS, smem, call.stream()>>>(a);                                                      \
   } while (0)
   switch (h.mode) {
   case EN_MEAN:
