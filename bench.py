@@ -590,7 +590,7 @@ def run_product(args):
     ceiling = world * e2e_lev * N / copy_s
     e2e = {"value": e2e_value, "unit": "grid points/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
            "levels_per_step": e2e_lev, "ms_per_step": 1e3 * e2e_dt / args.e2e_steps,
-           "api": "fcb200_alevel_chain_batched with pinned host buffers (chunked, copy-in / kernel / copy-out pipelined over 3 streams)",
+           "api": "fcb200_alevel_chain_batched with pinned host buffers (chunked, copy-in / kernel / copy-out pipelined over 4 streams, chunks of 1, 2, 4 ... fields up to 192 MB)",
            "ceiling": {"value": ceiling, "unit": "grid points/s", "ms_per_step": 1e3 * copy_s, "h2d_gbs_per_gpu": h2d / copy_s / 1e9, "d2h_gbs_per_gpu": d2h / copy_s / 1e9,
                        "how": "the step's H2D and D2H bytes as plain cudaMemcpyAsync copies on two streams at once, no kernel, all ranks together (max over ranks)"},
            "frac_of_copy_ceiling": e2e_value / ceiling, "numa_binding": numa}

@@ -8,6 +8,10 @@
 //     H2D + kernel + D2H back to back.  Results are identical (the kernels see the same fields).
 #pragma once
 
+#include <algorithm>
+#include <cstdlib>
+#include <vector>
+
 #include "elementwise.cuh"
 
 #include <functional>
@@ -118,24 +122,40 @@ int run_ew_job(const Op& op, const EwJob<Op>& job)
           host_fields = false;
   }
   const size_t bytes_per_field = sizeof(float) * (size_t)n * (Op::NIN + Op::NOUT);
-  const size_t chunk_target = size_t(48) << 20;
-  int fields_per_chunk = (int)(chunk_target / bytes_per_field);
-  if (fields_per_chunk < 1)
-    fields_per_chunk = 1;
-  const int nchunks = (job.nfields + fields_per_chunk - 1) / fields_per_chunk;
-  if (!host_fields || nchunks < 2) {
+  // Chunk sizes (measured on the 65-level chain, pinned buffers, B200 + PCIe 5: profiles/r02_e2e_chunking.txt): a chunk costs
+  // ~40 us on top of its bytes, so big chunks -- but the first copy-in and the last copy-out overlap nothing, so SMALL chunks at
+  // both ends: 1, 2, 4, ... fields up to ~192 MB per chunk and down again.  (48 MB chunks throughout: 26.8 ms per step; 200 MB
+  // throughout: 24.5 ms; the copies alone: 20.3 ms.)
+  static const char* chunk_env = getenv("FCB200_CHUNK_MB"); // (development switch)
+  const size_t chunk_target = size_t(chunk_env ? atoi(chunk_env) : 192) << 20;
+  int max_fields = (int)(chunk_target / bytes_per_field);
+  if (max_fields < 1)
+    max_fields = 1;
+  if (!host_fields || job.nfields < 2 || bytes_per_field * (size_t)job.nfields < (size_t(96) << 20)) {
     Call call;
     return detail::run_ew_range(call, op, job, 0, job.nfields);
   }
+  std::vector<int> head, tail;
+  for (int left = job.nfields, h = 1; left > 0; h = (h < max_fields) ? 2 * h : h) {
+    const int a = std::min(std::min(h, max_fields), left);
+    head.push_back(a);
+    left -= a;
+    if (left <= 0)
+      break;
+    const int b = std::min(std::min(h, max_fields), left);
+    tail.push_back(b);
+    left -= b;
+  }
+  head.insert(head.end(), tail.rbegin(), tail.rend());
 
   if (!pipeline_fork())
     return -1;
-  int rc = 1;
-  for (int c = 0; c < nchunks && rc == 1; ++c) {
-    const int f0 = c * fields_per_chunk;
-    const int f1 = (f0 + fields_per_chunk < job.nfields) ? f0 + fields_per_chunk : job.nfields;
-    Call call(1 + c % PIPE_SLOTS);
+  int rc = 1, f0 = 0;
+  for (size_t c = 0; c < head.size() && rc == 1; ++c) {
+    const int f1 = f0 + head[c];
+    Call call(1 + (int)(c % PIPE_SLOTS));
     rc = detail::run_ew_range(call, op, job, f0, f1);
+    f0 = f1;
   }
   const int jr = pipeline_join();
   return (rc == 1) ? jr : rc;

@@ -54,7 +54,7 @@ typedef std::function<void(const unsigned long long* counters)> Finalizer;
 // Chunked host-pointer calls are software-pipelined over PIPE_SLOTS extra streams: while chunk c
 // computes, chunk c+1 is copied in and chunk c-1 is copied out (PCIe is full duplex and the copy
 // engines run beside the SMs).  Each slot owns a stream and a device arena.
-constexpr int PIPE_SLOTS = 3;
+constexpr int PIPE_SLOTS = 4;
 
 // fork the calling thread's pipeline streams off its main stream / join them back and drain.
 bool pipeline_fork();
