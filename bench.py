@@ -395,6 +395,22 @@ def cfg1_latency(gpu, torch, dev):
         chain()
         ts.append(time.perf_counter() - t0)
     res["deferred_chain_of_3_device_us"] = float(np.median(ts)) * 1e6
+    # the same three calls captured once into a CUDA graph (fcb200_graph_*): one launch, one synchronisation, three flags
+    gpu.graph_begin()
+    gpu.call("pleveltemp", NX, NY, device["t"], 500.0, "kelvin", 3, outs[0], fl[0], UNDEF)
+    gpu.call("relvort", NX, NY, device["u"], device["v"], device["xm"], device["ym"], outs[1], fl[1], UNDEF)
+    gpu.call("divergence", NX, NY, device["u"], device["v"], device["xm"], device["ym"], outs[2], fl[2], UNDEF)
+    graph = gpu.graph_end()
+    for _ in range(5):
+        gpu.graph_launch(graph)
+    ts = []
+    for _ in range(60):
+        t0 = time.perf_counter()
+        gpu.graph_launch(graph)
+        ts.append(time.perf_counter() - t0)
+    res["graph_chain_of_3_device_us"] = float(np.median(ts)) * 1e6
+    res["graph_kernels"] = gpu.graph_kernels(graph)
+    gpu.graph_destroy(graph)
     res["sum_of_3_immediate_device_us"] = sum(res["calls"][k]["device"]["us"] for k in res["calls"])
     return res
 

@@ -50,6 +50,22 @@ int fcb200_end_deferred(void);
 int fcb200_in_deferred(void);
 /* wait for the calling thread's stream */
 int fcb200_synchronize(void);
+/* graphs: a chain of calls captured ONCE into a CUDA graph and replayed with ONE launch (the reference has no counterpart:
+ * its callers chain single-field calls, e.g. pleveltemp -> relvort -> divergence, FieldCalculations.cc:328/1843/1910, and pay
+ * one kernel launch + one synchronisation per call on a GPU).  Between fcb200_graph_begin() and fcb200_graph_end() every
+ * fcb200_* call on DEVICE-resident fields is recorded instead of run (host-memory fields and operators that need a
+ * host-side decision, cvtemp compute 3, make the capture fail; fcb200_graph_end() then returns -1 and
+ * fcb200_last_error() names the call).  fcb200_graph_launch() runs the whole chain and returns when every output and
+ * every fDefined flag is final (in deferred mode: at fcb200_end_deferred()).  The field pointers and the fDefined pointers of
+ * the captured calls belong to the caller and must stay valid while the graph is in use; input flags and scalar arguments
+ * are frozen at capture time; new DATA in the same buffers is what a launch sees.  A graph belongs to the device it was
+ * captured on and is used by one host thread at a time. */
+int fcb200_graph_begin(void);
+int fcb200_graph_end(void** graph);
+int fcb200_graph_launch(void* graph);
+/* kernel nodes in the graph (what one launch adds to fcb200_launch_count()), < 0 if `graph` is NULL */
+int fcb200_graph_kernels(void* graph);
+int fcb200_graph_destroy(void* graph);
 /* kernels launched by this library since it was loaded (all threads) */
 unsigned long long fcb200_launch_count(void);
 

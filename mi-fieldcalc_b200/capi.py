@@ -137,6 +137,9 @@ class Fcb200(Api):
         L.fcb200_launch_count.restype = ctypes.c_ulonglong
         L.fcb200_set_stream.argtypes = [ctypes.c_void_p, ctypes.c_int]
         L.fcb200_set_device.argtypes = [ctypes.c_int]
+        L.fcb200_graph_end.argtypes = [ctypes.POINTER(ctypes.c_void_p)]
+        for f in (L.fcb200_graph_launch, L.fcb200_graph_kernels, L.fcb200_graph_destroy):
+            f.argtypes = [ctypes.c_void_p]
         L.fcb200_slab_unique_id.argtypes = [ctypes.c_char_p]
         L.fcb200_slab_init.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_char_p]
         L.fcb200_slab_partition.argtypes = [ctypes.c_int] * 4 + [ctypes.POINTER(ctypes.c_int)] * 4
@@ -170,6 +173,25 @@ class Fcb200(Api):
 
     def launch_count(self) -> int:
         return int(self.lib.fcb200_launch_count())
+
+    # ---- graphs (include/fcb200.h): a chain of calls on device-resident fields, captured once, replayed with one launch
+    def graph_begin(self) -> None:
+        self._check(self.lib.fcb200_graph_begin())
+
+    def graph_end(self) -> int:
+        """Close the capture; returns the graph handle.  Raises (with the failing call's error) if a captured call failed."""
+        h = ctypes.c_void_p()
+        self._check(self.lib.fcb200_graph_end(ctypes.byref(h)))
+        return h.value
+
+    def graph_launch(self, graph: int) -> None:
+        self._check(self.lib.fcb200_graph_launch(graph))
+
+    def graph_kernels(self, graph: int) -> int:
+        return self._check(self.lib.fcb200_graph_kernels(graph))
+
+    def graph_destroy(self, graph: int) -> None:
+        self._check(self.lib.fcb200_graph_destroy(graph))
 
     # ---- row slabs (include/fcb200.h): one large grid over several GPUs, NCCL halo exchange
     def slab_unique_id(self) -> bytes:

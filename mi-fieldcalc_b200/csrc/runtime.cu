@@ -93,6 +93,7 @@ struct Deferred
 };
 
 thread_local char g_error[512] = "";
+thread_local bool* t_capturing_failed = nullptr; // &Graph::failed of the graph this thread is capturing
 std::atomic<unsigned long long> g_launches{0};
 
 } // namespace
@@ -107,9 +108,46 @@ struct Slot
   Slot() { pin.pinned = true; }
 };
 
+// A captured chain of calls (fcb200_graph_begin .. fcb200_graph_end): the CUDA graph, the arenas its nodes refer to
+// (per-field metadata in pinned memory and its device copy, scratch fields, counters) and the finalisers that turn
+// the counters into ValuesDefined flags after every launch.
+struct Graph
+{
+  int device = -1;
+  Arena dev;
+  Arena pin;
+  std::vector<Deferred> queue;
+  cudaGraph_t graph = nullptr;
+  cudaGraphExec_t exec = nullptr;
+  unsigned kernels = 0; // kernel nodes (what one launch adds to fcb200_launch_count)
+  bool failed = false;  // a call between begin and end returned an error
+  // The counters of all captured calls come from ONE block: one memset node at the head of the graph, one device-to-host copy at
+  // its tail (a memset and a copy node per call cost ~5 us each per launch).  Per-field metadata and small tables never change after
+  // the capture (scalar arguments and input flags are frozen): they are uploaded once, on `side`, outside the graph.
+  static constexpr size_t CBLOCK = 4096;
+  unsigned long long* cblock = nullptr;
+  unsigned long long* cblock_host = nullptr;
+  size_t cused = 0;
+  cudaStream_t side = nullptr;
+  Graph() { pin.pinned = true; }
+  ~Graph()
+  {
+    if (exec)
+      cudaGraphExecDestroy(exec);
+    if (graph)
+      cudaGraphDestroy(graph);
+    if (side)
+      cudaStreamDestroy(side);
+    dev.release_all();
+    pin.release_all();
+    cudaGetLastError();
+  }
+};
+
 struct ThreadState
 {
   int device = -1;
+  Graph* capturing = nullptr; // between fcb200_graph_begin() and fcb200_graph_end()
   Slot slots[PIPE_SLOTS];
   cudaEvent_t fork_event = nullptr;
   bool pipe_used = false;
@@ -271,6 +309,8 @@ void set_error(const char* fmt, ...)
   va_start(ap, fmt);
   vsnprintf(g_error, sizeof(g_error), fmt, ap);
   va_end(ap);
+  if (t_capturing_failed)
+    *t_capturing_failed = true; // an error between fcb200_graph_begin() and _end(): the graph is not built
 }
 
 bool cuda_ok(cudaError_t e, const char* what)
@@ -313,9 +353,14 @@ Call::Call(int slot)
   ok_ = ts_->init();
   if (!ok_)
     return;
+  if (ts_->capturing && slot != 0) {
+    set_error("fcb200: host-memory fields cannot be captured into a graph (pass device pointers)");
+    ok_ = false;
+    return;
+  }
   if (slot == 0) {
     stream_ = ts_->stream();
-    if (!ts_->in_flight) {
+    if (!ts_->in_flight && !ts_->capturing) {
       ts_->dev.reset();
       ts_->pin.reset();
     }
@@ -341,7 +386,7 @@ void* Call::arena_alloc(size_t bytes)
 {
   if (!ok_)
     return nullptr;
-  void* p = (slot_ == 0 ? ts_->dev : ts_->slots[slot_ - 1].dev).alloc(bytes);
+  void* p = (ts_->capturing ? ts_->capturing->dev : slot_ == 0 ? ts_->dev : ts_->slots[slot_ - 1].dev).alloc(bytes);
   if (!p)
     ok_ = false;
   return p;
@@ -351,7 +396,7 @@ void* Call::pinned_alloc(size_t bytes)
 {
   if (!ok_)
     return nullptr;
-  void* p = (slot_ == 0 ? ts_->pin : ts_->slots[slot_ - 1].pin).alloc(bytes);
+  void* p = (ts_->capturing ? ts_->capturing->pin : slot_ == 0 ? ts_->pin : ts_->slots[slot_ - 1].pin).alloc(bytes);
   if (!p)
     ok_ = false;
   return p;
@@ -397,6 +442,11 @@ const float* Call::in(const float* p, size_t count)
   }
   if (dev)
     return p;
+  if (ts_->capturing) {
+    set_error("fcb200: host-memory fields cannot be captured into a graph (pass device pointers)");
+    ok_ = false;
+    return nullptr;
+  }
   for (const auto& q : pending_)
     if (q.host == p && q.bytes >= count * sizeof(float))
       return static_cast<const float*>(q.dev);
@@ -423,6 +473,11 @@ float* Call::out(float* p, size_t count)
   }
   if (dev)
     return p;
+  if (ts_->capturing) {
+    set_error("fcb200: host-memory fields cannot be captured into a graph (pass device pointers)");
+    ok_ = false;
+    return nullptr;
+  }
   for (auto& q : pending_) {
     if (q.host == p && q.bytes >= count * sizeof(float)) {
       q.copy_back = true;
@@ -481,6 +536,14 @@ const void* Call::upload_small(const void* host, size_t bytes)
   void* d = arena_alloc(bytes);
   if (!d)
     return nullptr;
+  if (ts_->capturing) { // frozen at capture time: uploaded now, not a node of the graph
+    if (!cuda_ok(cudaMemcpyAsync(d, src, bytes, cudaMemcpyHostToDevice, ts_->capturing->side), "cudaMemcpyAsync(H2D table, capture)") ||
+        !cuda_ok(cudaStreamSynchronize(ts_->capturing->side), "cudaStreamSynchronize(capture side stream)")) {
+      ok_ = false;
+      return nullptr;
+    }
+    return d;
+  }
   if (!cuda_ok(cudaMemcpyAsync(d, src, bytes, cudaMemcpyHostToDevice, stream_), "cudaMemcpyAsync(H2D table)")) {
     ok_ = false;
     return nullptr;
@@ -493,7 +556,16 @@ unsigned long long* Call::counters(int count)
   if (!ok_)
     return nullptr;
   counters_n_ = count;
-  counters_dev_ = ts_->pool_counters((size_t)count);
+  // (a captured call owns its counters: the graph clears them and copies them back itself at every launch)
+  if (Graph* g = ts_->capturing) {
+    if (g->cblock && g->cused + (size_t)count <= Graph::CBLOCK) {
+      counters_dev_ = g->cblock + g->cused;
+      counters_graph_ = true;
+      g->cused += (size_t)count;
+      return counters_dev_;
+    }
+  }
+  counters_dev_ = ts_->capturing ? nullptr : ts_->pool_counters((size_t)count);
   counters_pooled_ = counters_dev_ != nullptr;
   if (counters_pooled_)
     return counters_dev_;
@@ -512,8 +584,10 @@ int Call::finish(const Finalizer& fin)
   if (!ok_)
     return -1;
   finished_ = true;
-  if (!cuda_ok(cudaGetLastError(), "kernel launch"))
+  if (!cuda_ok(cudaGetLastError(), "kernel launch")) {
+    ok_ = false;
     return -1;
+  }
   for (const auto& q : pending_) {
     if (q.copy_back) {
       if (!cuda_ok(cudaMemcpyAsync(const_cast<void*>(q.host), q.dev, q.bytes, cudaMemcpyDeviceToHost, stream_), "cudaMemcpyAsync(D2H field)"))
@@ -521,18 +595,26 @@ int Call::finish(const Finalizer& fin)
     }
   }
   const unsigned long long* host_counters = nullptr;
-  if (counters_n_ > 0 && counters_pooled_) {
+  if (counters_n_ > 0 && counters_graph_) {
+    host_counters = ts_->capturing->cblock_host + (counters_dev_ - ts_->capturing->cblock); // filled by the graph's last node
+  } else if (counters_n_ > 0 && counters_pooled_) {
     host_counters = ts_->counter_mirror + (counters_dev_ - ts_->counter_pool); // filled by drain()
   } else if (counters_n_ > 0) {
     // counters are read by the finaliser when the whole call drains: they live in the main pinned
     // arena, which is not recycled while work is in flight
-    void* pin = ts_->pin.alloc(sizeof(unsigned long long) * (size_t)counters_n_);
-    if (!pin)
+    void* pin = (ts_->capturing ? ts_->capturing->pin : ts_->pin).alloc(sizeof(unsigned long long) * (size_t)counters_n_);
+    if (!pin) {
+      ok_ = false;
       return -1;
+    }
     if (!cuda_ok(cudaMemcpyAsync(pin, counters_dev_, sizeof(unsigned long long) * (size_t)counters_n_, cudaMemcpyDeviceToHost, stream_),
                  "cudaMemcpyAsync(D2H counters)"))
       return -1;
     host_counters = static_cast<const unsigned long long*>(pin);
+  }
+  if (ts_->capturing) { // the finaliser runs after every launch of the graph
+    ts_->capturing->queue.push_back({fin, host_counters});
+    return 1;
   }
   ts_->queue.push_back({fin, host_counters});
   ts_->in_flight = true;
@@ -551,6 +633,11 @@ int Call::finish(const Finalizer& fin)
 bool pipeline_fork()
 {
   ThreadState& ts = thread_state();
+  if (ts.capturing) {
+    set_error("fcb200: host-memory fields cannot be captured into a graph (pass device pointers)");
+    ts.capturing->failed = true;
+    return false;
+  }
   if (!ts.init() || !ts.init_slots())
     return false;
   // everything already queued on the main stream happens before the chunks
@@ -609,6 +696,10 @@ int fcb200_set_device(int device)
 int fcb200_set_stream(void* cuda_stream, int use_it)
 {
   auto& ts = thread_state();
+  if (ts.capturing) {
+    fcb200::set_error("fcb200: fcb200_set_stream() inside fcb200_graph_begin() .. fcb200_graph_end()");
+    return -1;
+  }
   if (ts.in_flight && !ts.drain())
     return -1;
   ts.user_stream = static_cast<cudaStream_t>(cuda_stream);
@@ -619,6 +710,10 @@ int fcb200_set_stream(void* cuda_stream, int use_it)
 int fcb200_begin_deferred(void)
 {
   auto& ts = thread_state();
+  if (ts.capturing) {
+    fcb200::set_error("fcb200: fcb200_begin_deferred() inside fcb200_graph_begin() .. fcb200_graph_end()");
+    return -1;
+  }
   ts.deferred = true;
   return 1;
 }
@@ -631,6 +726,10 @@ int fcb200_in_deferred(void)
 int fcb200_end_deferred(void)
 {
   auto& ts = thread_state();
+  if (ts.capturing) {
+    fcb200::set_error("fcb200: fcb200_end_deferred() inside fcb200_graph_begin() .. fcb200_graph_end()");
+    return -1;
+  }
   ts.deferred = false;
   if (!ts.in_flight)
     return 1;
@@ -642,11 +741,142 @@ int fcb200_end_deferred(void)
 int fcb200_synchronize(void)
 {
   auto& ts = thread_state();
+  if (ts.capturing) {
+    fcb200::set_error("fcb200: fcb200_synchronize() inside fcb200_graph_begin() .. fcb200_graph_end()");
+    return -1;
+  }
   if (!ts.init())
     return -1;
   if (ts.in_flight)
     return ts.drain() ? 1 : -1;
   return fcb200::cuda_ok(cudaStreamSynchronize(ts.stream()), "cudaStreamSynchronize") ? 1 : -1;
+}
+
+// ---- graphs: a chain of calls on device-resident fields, captured once and replayed with one launch ----------------------
+// Between begin and end every fcb200_* call is recorded instead of run (stream capture): its kernels, the upload of its
+// per-field metadata, the clearing and the read-back of its counters.  Everything the nodes refer to that the library owns
+// lives in the graph object; the field pointers and the fDefined pointers belong to the caller and must stay valid for as
+// long as the graph is launched.  Input flags are read at capture time (as in deferred mode).
+
+int fcb200_graph_begin(void)
+{
+  auto& ts = thread_state();
+  if (!ts.init())
+    return -1;
+  if (ts.capturing || ts.deferred) {
+    fcb200::set_error("fcb200: fcb200_graph_begin() inside %s", ts.capturing ? "another capture" : "deferred mode");
+    return -1;
+  }
+  if (ts.in_flight && !ts.drain())
+    return -1;
+  auto* g = new fcb200::Graph;
+  g->device = ts.device;
+  g->cblock = static_cast<unsigned long long*>(g->dev.alloc(fcb200::Graph::CBLOCK * sizeof(unsigned long long)));
+  g->cblock_host = static_cast<unsigned long long*>(g->pin.alloc(fcb200::Graph::CBLOCK * sizeof(unsigned long long)));
+  if (!g->cblock || !g->cblock_host || !fcb200::cuda_ok(cudaStreamCreateWithFlags(&g->side, cudaStreamNonBlocking), "cudaStreamCreate(capture side stream)")) {
+    delete g;
+    return -1;
+  }
+  // relaxed mode: a call may grow the graph's arenas (cudaMalloc) and upload its tables on `side` while the capture is open
+  if (!fcb200::cuda_ok(cudaStreamBeginCapture(ts.stream(), cudaStreamCaptureModeRelaxed), "cudaStreamBeginCapture")) {
+    delete g;
+    return -1;
+  }
+  ts.capturing = g;
+  ts.deferred = true;
+  fcb200::t_capturing_failed = &g->failed;
+  if (!fcb200::cuda_ok(cudaMemsetAsync(g->cblock, 0, fcb200::Graph::CBLOCK * sizeof(unsigned long long), ts.stream()), "cudaMemsetAsync(graph counters)"))
+    return -1; // (the capture stays open and poisoned: fcb200_graph_end() cleans up)
+  return 1;
+}
+
+int fcb200_graph_end(void** graph)
+{
+  auto& ts = thread_state();
+  if (graph)
+    *graph = nullptr;
+  fcb200::Graph* g = ts.capturing;
+  if (!g) {
+    fcb200::set_error("fcb200: fcb200_graph_end() without fcb200_graph_begin()");
+    return -1;
+  }
+  if (!g->failed && g->cused > 0)
+    fcb200::cuda_ok(cudaMemcpyAsync(g->cblock_host, g->cblock, g->cused * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ts.stream()),
+                    "cudaMemcpyAsync(D2H graph counters)");
+  ts.capturing = nullptr;
+  ts.deferred = false;
+  fcb200::t_capturing_failed = nullptr;
+  const cudaError_t e = cudaStreamEndCapture(ts.stream(), &g->graph); // (always called: it also closes a broken capture)
+  if (g->failed || !graph) {
+    cudaGetLastError();
+    delete g; // keeps the error text of the call that failed
+    if (!graph)
+      fcb200::set_error("fcb200: fcb200_graph_end(NULL)");
+    return -1;
+  }
+  if (!fcb200::cuda_ok(e, "cudaStreamEndCapture") || !fcb200::cuda_ok(cudaGraphInstantiate(&g->exec, g->graph, 0), "cudaGraphInstantiate")) {
+    delete g;
+    return -1;
+  }
+  size_t n = 0;
+  if (cudaGraphGetNodes(g->graph, nullptr, &n) == cudaSuccess && n > 0) {
+    std::vector<cudaGraphNode_t> nodes(n);
+    if (cudaGraphGetNodes(g->graph, nodes.data(), &n) == cudaSuccess) {
+      for (size_t i = 0; i < n; ++i) {
+        cudaGraphNodeType t;
+        if (cudaGraphNodeGetType(nodes[i], &t) == cudaSuccess && t == cudaGraphNodeTypeKernel)
+          ++g->kernels;
+      }
+    }
+  }
+  cudaGetLastError();
+  *graph = g;
+  return 1;
+}
+
+int fcb200_graph_launch(void* graph)
+{
+  auto* g = static_cast<fcb200::Graph*>(graph);
+  auto& ts = thread_state();
+  if (!g || !g->exec) {
+    fcb200::set_error("fcb200: fcb200_graph_launch(): not a graph");
+    return -1;
+  }
+  if (!ts.init())
+    return -1;
+  if (ts.capturing || ts.device != g->device) {
+    fcb200::set_error(ts.capturing ? "fcb200: fcb200_graph_launch() inside a capture" : "fcb200: the graph was captured on device %d", g->device);
+    return -1;
+  }
+  if (!fcb200::cuda_ok(cudaGraphLaunch(g->exec, ts.stream()), "cudaGraphLaunch"))
+    return -1;
+  fcb200::count_launch(g->kernels);
+  for (const auto& d : g->queue)
+    ts.queue.push_back(d);
+  ts.in_flight = true;
+  if (ts.deferred)
+    return 1;
+  return ts.drain() ? 1 : -1;
+}
+
+int fcb200_graph_kernels(void* graph)
+{
+  auto* g = static_cast<fcb200::Graph*>(graph);
+  return g ? (int)g->kernels : -1;
+}
+
+int fcb200_graph_destroy(void* graph)
+{
+  auto* g = static_cast<fcb200::Graph*>(graph);
+  if (!g)
+    return 1;
+  auto& ts = thread_state();
+  if (ts.in_flight && !ts.drain()) { // a deferred launch of this graph may still be running
+    delete g;
+    return -1;
+  }
+  delete g;
+  return 1;
 }
 
 unsigned long long fcb200_launch_count(void)

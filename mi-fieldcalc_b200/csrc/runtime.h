@@ -122,6 +122,7 @@ private:
   unsigned long long* counters_dev_ = nullptr;
   int counters_n_ = 0;
   bool counters_pooled_ = false;
+  bool counters_graph_ = false; // from the counter block of the graph being captured
   bool finished_ = false;
 };
 
