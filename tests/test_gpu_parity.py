@@ -152,6 +152,27 @@ def test_fused_alevel_chain_values_at_the_edges_of_the_fast_path(gpu, flag):
     _chain_against_reference_calls(gpu, 949, 23, 2, "none", flag, "celsius", (True,), edge_values=True)
 
 
+def test_exner_fast_path_error(gpu):
+    """theta = t / (p/1000)^kappa on the branch-free path uses the reciprocal Exner factor from MUFU.LG2 / MUFU.EX2
+    (csrc/device_common.cuh exner_recip) instead of powf + division: north_star's tolerance for these outputs is 1e-5 relative,
+    "transcendental differences documented".  Measured here against double precision over the WHOLE plausible pressure range
+    (2^-7 .. 2^11 hPa, log-uniform) and over the meteorological one: the bound the header states is 7e-7."""
+    nx, ny = 4096, 256
+    rng = np.random.default_rng(2024)
+    kappa = float(np.float32(287.0) / np.float32(1004.0))
+    for lo, hi in ((-7.0, 11.0), (np.log2(5.0), np.log2(1100.0))):
+        p = np.exp2(rng.uniform(lo, hi, (ny, nx))).astype(np.float32)
+        p = np.clip(p, np.float32(2.0 ** -7), np.nextafter(np.float32(2048.0), np.float32(0)))
+        t = rng.uniform(180.0, 330.0, (ny, nx)).astype(np.float32)
+        out, f = np.empty((ny, nx), np.float32), np.array([cases.ALL], np.int32)
+        assert gpu.call("aleveltemp", nx, ny, t, p, "kelvin", 3, out, f, float(cases.UNDEF)) == 1
+        x = (p * np.float32(1.0 / np.float32(1000.0))).astype(np.float64)
+        want = t.astype(np.float64) / x ** kappa
+        err = np.abs(out.astype(np.float64) - want) / want
+        assert err.max() < 7e-7, err.max()
+        print("exner fast path: max relative error %.3g, mean %.3g over log2 p in [%.1f, %.1f]" % (err.max(), err.mean(), lo, hi))
+
+
 @pytest.mark.parametrize("mask,flag", [("none", cases.ALL), ("none", cases.SOME), ("bernoulli", cases.SOME), ("nan", cases.SOME), ("nan", cases.ALL)])
 @pytest.mark.parametrize("unit", ["celsius", "kelvin"])
 def test_fused_hlevel_chain_equals_four_reference_calls(gpu, mask, flag, unit):
