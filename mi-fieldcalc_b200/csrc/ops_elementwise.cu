@@ -983,8 +983,10 @@ int impl_xlevelthe(const Batch& b, const float* t, const float* q, const float* 
     return run_elementwise(b, op, in, pf, the, fDefined, undef, FLAG_FROM_COUNT, levels);
   }
   const float* in[3] = {t, q, pin};
-  // (the one-output form of the fused chain, AlevelChainOpT<.., O_THE>, was measured at 0.65 - 0.69 of the roofline for 2 - 4
-  // CTAs/SM against 0.72 for this generic operator: not used)
+  // compute 1 (T, q -> theta_e): the one-output form of the fused chain's branch-free code (reciprocal Exner factor from the
+  // special-function unit, two multiplications); compute 2 (theta, q -> theta_e) keeps the generic operator
+  if (compute == 1)
+    return run_elementwise(b, AlevelChainOpT<2, 3, 2, O_THE, KIND>{0.f}, in, pf, the, fDefined, undef, FLAG_FROM_COUNT, levels);
   TheOp<KIND> op{compute};
   return run_elementwise(b, op, in, pf, the, fDefined, undef, FLAG_FROM_COUNT, levels);
 }
