@@ -550,10 +550,36 @@ def run_product(args):
     traffic, traffic_src = ncu_traffic()
     if traffic is not None and nlev != NLEV:
         traffic = None
-    roofline = {"bound": "hbm", "kernel": "ew_kernel<AlevelChainOpT<2, 2, 4>, 4> (fused chain)", "achieved": achieved, "peak": peak, "unit": "GB/s",
+    roofline = {"bound": "hbm", "kernel": "ew_kernel<AlevelChainOpT<1, 3, 4, O_ALL, ALEVEL>, 4> (fused chain)", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "algorithmic_bytes_per_point": BYTES_FUSED,
                 "algorithmic_bytes_per_launch": BYTES_FUSED * points_per_step, "kernel_ms": kern_ms,
-                "note": "issue-bound, not HBM-bound (ncu summaries under profiles/)"}
+                "note": "113 instructions per point; issue / latency-bound, not HBM-bound (ncu summaries under profiles/)"}
+
+    # the same chain on HYBRID levels (fcb200_hlevel_chain_batched: p = a + b * ps with one surface-pressure field for the batch, 24 B/point)
+    ps = sets[0][2][0].clone().mul_(0.1).add_(930.0)
+    eta = (np.arange(nlev) + 0.5) / nlev
+    ah, bh = (200.0 * (1 - eta) * eta * 2.0 + 10.0 * (1 - eta)).astype(np.float32), (eta ** 1.5).astype(np.float32)
+
+    def hybrid_step(t, q):
+        gpu.call("hlevel_chain_batched", NX, NY, nlev, t, q, ps, ah, bh, "celsius", outs[0], outs[1], outs[2], outs[3], fin, fout, UNDEF)
+
+    gpu.begin_deferred()
+    for w in range(3):
+        hybrid_step(*sets[w % 2][:2])
+    gpu.end_deferred()
+    barrier()
+    h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    hsteps = max(4, args.steps // 2)
+    gpu.begin_deferred()
+    h0.record(stream)
+    for k in range(hsteps):
+        hybrid_step(*sets[k % 2][:2])
+    h1.record(stream)
+    gpu.end_deferred()
+    barrier()
+    hms = h0.elapsed_time(h1) / hsteps
+    hybrid = {"call": "fcb200_hlevel_chain_batched", "levels": nlev, "ms_per_step": hms, "gpts": points_per_step / (hms * 1e-3) / 1e9,
+              "algorithmic_bytes_per_point": 24, "gbs": 24 * points_per_step / (hms * 1e-3) / 1e9, "frac": 24 * points_per_step / (hms * 1e-3) / 1e9 / peak}
 
     # for the record: the same step as the UNFUSED reference call sequence (four batched launches, 60 B/point)
     gpu.begin_deferred()
@@ -635,9 +661,10 @@ def run_product(args):
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "grid": [NX, NY], "levels_per_step": nlev, "points_per_step_per_gpu": points_per_step,
                        "chain": "aleveltemp c3 + alevelhum c1 + alevelhum c5 + alevelthe c1, fused into one launch per step (t, q, p read once)",
-                       "unfused_ms_per_step": unfused_ms,
+                       "unfused_ms_per_step": unfused_ms, "hybrid_level_chain": hybrid,
                        "cache": "inputs larger than L2 (>= 790 MB streamed per step, two alternating input sets)", "sharding": "by field batch, no collective",
-                       "tolerance": "mask and flags bit-exact; values <= 1e-5 relative, with Celsius outputs (Td) and windCooling judged on an absolute floor "
+                       "tolerance": "mask and flags bit-exact; RH and Td bit-exact; theta / theta_e <= 6e-7 relative measured (reciprocal Exner factor from MUFU.LG2/EX2, "
+                                    "tests/test_gpu_parity.py::test_exner_fast_path_error) against north_star's 1e-5; elsewhere values <= 1e-5 relative, with Celsius outputs (Td) and windCooling judged on an absolute floor "
                                     "(273.15 K resp. 13.12, the polynomial's constant term) -- tests/cases.py abs_floor"},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
             "per_operator": ops, "cfg1_latency": lat, "slab": slab,

@@ -1295,13 +1295,12 @@ int fcb200_alevel_chain_batched(int nx, int ny, int nfields, const float* t, con
     job.undef = undef;
     return run_ew_job(op, job);
   };
-  // Kernel shape (measured on B200, profiles/r01_chain_tuning.txt): 2 float4 groups per thread and round, 4 rounds per
-  // item, 2 CTAs of 256 threads per SM (<= 128 registers: the straight-line code of 8 interleaved points needs
-  // them; 64- and 80-register builds spill and lose 10-15 %).
-  // The four-output chain keeps the one-point-at-a-time form: with eight points in flight per thread at 127 registers the packed
-  // form (fast2) measured 146.6 Gpt/s against 150.7 (151.8 with one group per round) -- profiles/r02_chain_packed.txt; the one- and
-  // two-output operators, which have registers to spare, gain 2 - 7 % from it.
-  return run(AlevelChainOpT<2, 2, 4, O_ALL, ALEVEL, 0>{tdconv});
+  // Kernel shape (measured on B200): one float4 group per thread and round, 4 rounds per item, 3 CTAs of 256 threads per SM
+  // (80 registers, 84 bytes of spill).  With the FP64 Exner power of round 1 the straight-line code of 8 interleaved points
+  // needed 127 registers (2 CTAs/SM: profiles/r01_chain_tuning.txt); with the reciprocal Exner factor from the special-function
+  // unit the kernel is 113 instructions per point and latency-bound at 2 CTAs/SM (issue 58 %, DRAM 59 %): 168 Gpt/s there,
+  // 179 Gpt/s with 3 (profiles/r02aq_chain_variants.txt; 4 CTAs at 64 registers 166, the packed form 177).
+  return run(AlevelChainOpT<1, 3, 4, O_ALL, ALEVEL, 0>{tdconv});
 }
 
 int fcb200_hlevel_chain_batched(int nx, int ny, int nfields, const float* t, const float* q, const float* ps, const float* alevel, const float* blevel,
@@ -1313,7 +1312,7 @@ int fcb200_hlevel_chain_batched(int nx, int ny, int nfields, const float* t, con
   if (nfields > 0 && any_bad_hlevel(make_batch(nx, ny, nfields), alevel, blevel))
     return 0; // FC.cc:1070, 1121, 1170
   const int td_compute = hum_compute(5, td_unit);
-  EwJob<AlevelChainOpT<2, 2, 4, O_ALL, HLEVEL, 0>> job;
+  EwJob<AlevelChainOpT<1, 3, 4, O_ALL, HLEVEL, 0>> job;
   job.nx = nx;
   job.ny = ny;
   job.nfields = nfields;
@@ -1334,7 +1333,7 @@ int fcb200_hlevel_chain_batched(int nx, int ny, int nfields, const float* t, con
     m.a = alevel[k];
     m.b = blevel[k];
   };
-  return run_ew_job(AlevelChainOpT<2, 2, 4, O_ALL, HLEVEL, 0>{(td_compute >= 9) ? H_T0 : 0.f}, job);
+  return run_ew_job(AlevelChainOpT<1, 3, 4, O_ALL, HLEVEL, 0>{(td_compute >= 9) ? H_T0 : 0.f}, job);
 }
 
 } // extern "C"
