@@ -269,7 +269,9 @@ struct ThreadState
     return true;
   }
 
-  cudaStream_t stream() const { return use_user_stream ? user_stream : own_stream; }
+  // A capture always runs on the library's own stream: the caller's stream may be the legacy default stream, which cannot be
+  // captured.  The graph is LAUNCHED on the caller's stream like any other work.
+  cudaStream_t stream() const { return (use_user_stream && !capturing) ? user_stream : own_stream; }
 
   bool drain()
   {
@@ -778,7 +780,7 @@ int fcb200_graph_begin(void)
     return -1;
   }
   // relaxed mode: a call may grow the graph's arenas (cudaMalloc) and upload its tables on `side` while the capture is open
-  if (!fcb200::cuda_ok(cudaStreamBeginCapture(ts.stream(), cudaStreamCaptureModeRelaxed), "cudaStreamBeginCapture")) {
+  if (!fcb200::cuda_ok(cudaStreamBeginCapture(ts.own_stream, cudaStreamCaptureModeRelaxed), "cudaStreamBeginCapture")) {
     delete g;
     return -1;
   }
@@ -806,7 +808,7 @@ int fcb200_graph_end(void** graph)
   ts.capturing = nullptr;
   ts.deferred = false;
   fcb200::t_capturing_failed = nullptr;
-  const cudaError_t e = cudaStreamEndCapture(ts.stream(), &g->graph); // (always called: it also closes a broken capture)
+  const cudaError_t e = cudaStreamEndCapture(ts.own_stream, &g->graph); // (always called: it also closes a broken capture)
   if (g->failed || !graph) {
     cudaGetLastError();
     delete g; // keeps the error text of the call that failed

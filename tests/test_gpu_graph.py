@@ -212,3 +212,33 @@ def test_what_cannot_be_captured_fails_loudly(gpu):
     gpu.graph_launch(g)
     gpu.graph_destroy(g)
     torch.cuda.synchronize()
+
+
+@pytest.mark.parametrize("which", ["legacy_default", "torch_side_stream"])
+def test_capture_with_a_caller_stream_installed(gpu, which):
+    """fcb200_set_stream(torch's current stream) -- the legacy default stream cannot be captured: the capture runs on the library's
+    own stream, the launch on the caller's (bench.py's set-up)"""
+    import torch
+    arb = _arbiter()
+    nx, ny = 300, 67
+    d = _inputs(21, nx, ny, False)
+    side = torch.cuda.Stream() if which == "torch_side_stream" else None
+    stream = side if side is not None else torch.cuda.current_stream()
+    bufs = {k: _dev(d[k]) for k in d}
+    out = torch.empty((ny, nx), dtype=torch.float32, device="cuda")
+    f = np.array([cases.ALL], np.int32)
+    torch.cuda.synchronize()
+    gpu.set_stream(stream.cuda_stream, True)
+    try:
+        gpu.graph_begin()
+        gpu.call("relvort", nx, ny, bufs["u"], bufs["v"], bufs["xm"], bufs["ym"], out, f, UNDEF)
+        g = gpu.graph_end()
+        for _ in range(2):
+            out.fill_(0)
+            torch.cuda.synchronize()
+            gpu.graph_launch(g)
+            want = _cfg1_reference(arb, nx, ny, d, cases.ALL)["relvort"]
+            assert np.array_equal(out.cpu().numpy(), want[0]) and int(f[0]) == want[1]
+        gpu.graph_destroy(g)
+    finally:
+        gpu.set_stream(None, False)
