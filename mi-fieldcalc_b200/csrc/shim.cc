@@ -61,7 +61,9 @@ ValuesDefined combineDefined(ValuesDefined a, ValuesDefined b)
 // build's answer (openmp_tools.cc:78).
 int compute_num_threads(long) { return 1; }
 
-// ---- MetConstants.cc:51-131 of the reference: ICAO standard atmosphere, seven layers of constant lapse rate up to
+// ---- OUT OF SCOPE, ABI FILLER: host scalars that the drop-in library must export so that `nm -D`
+// matches the reference's (tests/test_cpp_api.py); nothing on the GPU path calls them and they are not counted as product work.
+// MetConstants.cc:51-131 of the reference: ICAO standard atmosphere, seven layers of constant lapse rate up to
 // 84.852 km.  Layer k starts at height H[k] (km) with temperature T[k] (K) and pressure P[k] (hPa) and has the
 // temperature gradient L[k] (K/km).  Inside a layer: p/P = (1 + dh L/T)^(-g/(L R)) for L != 0, exp(-dh g/(R T)) for L = 0.
 namespace constants {
