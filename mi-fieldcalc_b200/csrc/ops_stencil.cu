@@ -343,6 +343,7 @@ struct GradientOp
 {
   static constexpr int NOUT = 1;
   static constexpr bool TESTS_WHEN_ALL = false;
+  static constexpr int TILE_CTAS = 4; // one staged array: small stages, 56 registers are enough (0.66 / 0.63 / 0.68 with 2 / 3 / 4 CTAs per SM)
   const float *f, *xm, *ym;
   float* o;
   template <bool ALL>
@@ -1108,8 +1109,12 @@ bool launch_stencil(Call& call, const Op& op, int nx, int ny, int nfields, float
     if (t.fb > nfields)
       t.fb = nfields;
     // pipeline depth: up to 3 fields in flight, two CTAs per SM
+    // CTAs per SM (tile::tile_ctas<Op>: 3, gradient 4): measured per operator on B200 (profiles/r02at_tile_ctas.txt) -- with 2
+    // CTAs of 9 warps the consumers mostly wait on each other's dependent instructions (ncu: `wait` 2.9 warps per issue,
+    // occupancy 27 %); the third CTA costs a pipeline stage (shared memory) and 24 registers per thread and wins 3 - 19 %
+    constexpr int CTAS = tile::tile_ctas<Op>::value;
     t.stages = t.fb < tile::MAX_STAGES ? t.fb : tile::MAX_STAGES;
-    while (t.stages > 1 && L::smem_bytes(t.stages) > 110 * 1024)
+    while (t.stages > 1 && L::smem_bytes(t.stages) > (CTAS == 4 ? 54 : CTAS == 3 ? 73 : 110) * 1024)
       t.stages -= 1;
     const size_t smem = L::smem_bytes(t.stages);
     // the opt-in to more than 48 KB of dynamic shared memory is a PER-DEVICE attribute of the kernel: one bit per
@@ -1120,7 +1125,7 @@ bool launch_stencil(Call& call, const Op& op, int nx, int ny, int nfields, float
       return false;
     const unsigned long long dev_bit = (device >= 0 && device < 64) ? (1ull << device) : 0ull;
     if (!(attr_set.load(std::memory_order_acquire) & dev_bit) || dev_bit == 0) {
-      if (!cuda_ok(cudaFuncSetAttribute(tile::stencil_tile_kernel<Op>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::smem_bytes(tile::MAX_STAGES)),
+      if (!cuda_ok(cudaFuncSetAttribute(tile::stencil_tile_kernel<Op, CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::smem_bytes(tile::MAX_STAGES)),
                    "cudaFuncSetAttribute(stencil_tile_kernel)"))
         return false;
       attr_set.fetch_or(dev_bit, std::memory_order_release);
@@ -1133,7 +1138,7 @@ bool launch_stencil(Call& call, const Op& op, int nx, int ny, int nfields, float
       set_error("fcb200: batch too large for one launch (%lld CTAs)", ctas);
       return false;
     }
-    tile::stencil_tile_kernel<Op><<<(unsigned)ctas, tile::TILE_THREADS, smem, call.stream()>>>(op, t);
+    tile::stencil_tile_kernel<Op, CTAS><<<(unsigned)ctas, tile::TILE_THREADS, smem, call.stream()>>>(op, t);
     tile::stencil_edge_kernel<Op><<<edge_grid, tile::EDGE_THREADS, 0, call.stream()>>>(op, nx, ny, nfields, g.lo, g.hi, undef, meta, counters, true);
     count_launch(2);
     return true;

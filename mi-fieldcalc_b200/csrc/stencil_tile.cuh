@@ -26,6 +26,8 @@
 
 #include "device_common.cuh"
 
+#include <type_traits>
+
 namespace fcb200 {
 namespace tile {
 
@@ -212,8 +214,18 @@ __device__ __forceinline__ void mbar_arrive(unsigned long long* bar)
 // segments, which complete on the stage's "full" barrier.  The other warps are CONSUMERS: wait for
 // "full", compute their column of the tile, store, release the stage.  Nothing else synchronises the
 // CTA, so the producer runs up to `stages` fields ahead.
+// resident CTAs per SM the kernel is compiled for (and the host sizes its pipeline for): Op::TILE_CTAS if the operator says so
+template <class Op, class = void>
+struct tile_ctas : std::integral_constant<int, 3>
+{
+};
 template <class Op>
-__global__ void __launch_bounds__(TILE_THREADS, 2) stencil_tile_kernel(const Op op0, const TileGeom g)
+struct tile_ctas<Op, std::void_t<decltype(Op::TILE_CTAS)>> : std::integral_constant<int, Op::TILE_CTAS>
+{
+};
+
+template <class Op, int MINB = tile_ctas<Op>::value>
+__global__ void __launch_bounds__(TILE_THREADS, MINB) stencil_tile_kernel(const Op op0, const TileGeom g)
 {
   typedef TileLayout<Op> L;
   constexpr int TY = Op::TY, NARR = Op::NARR, NMAPS = Op::NMAPS;
