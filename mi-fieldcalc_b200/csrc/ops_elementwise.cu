@@ -939,6 +939,7 @@ int impl_plevelhum(const Batch& b, const float* t, const float* huminp, const fl
 
 // ---- hybrid / atmospheric levels --------------------------------------------------------------------
 
+
 template <int KIND>
 int impl_xleveltemp(const Batch& b, const float* tinp, const float* pin, const float* alevel, const float* blevel, int compute, float* tout,
                     int* fDefined, float undef)
@@ -958,6 +959,10 @@ int impl_xleveltemp(const Batch& b, const float* tinp, const float* pin, const f
   const float* in[2] = {tinp, pin};
   // T -> theta: the fused chain's branch-free code with one output.  Shapes measured on B200 (MEPS x 96, fraction of the HBM
   // roofline): 3 CTAs/SM 0.65, 4 CTAs/SM 0.63, 2 CTAs/SM 0.56; the generic TempOp 0.55.
+  // (round 2, after the Exner factor moved to the special-function unit: a-level 0.89 with 3 CTAs/SM, 0.84 with 4; hybrid level -- one
+  // input field less to wait for -- 0.65 with 3, 0.72 with 4; one float4 group per thread or 5 CTAs/SM change nothing)
+  if (compute == 3 && KIND == HLEVEL)
+    return run_elementwise(b, AlevelChainOpT<2, 4, 2, O_THETA, KIND>{0.f}, in, pf, tout, fDefined, undef, FLAG_FROM_COUNT, levels);
   if (compute == 3)
     return run_elementwise(b, AlevelChainOpT<2, 3, 2, O_THETA, KIND>{0.f}, in, pf, tout, fDefined, undef, FLAG_FROM_COUNT, levels);
   if (compute == 4)
