@@ -473,6 +473,7 @@ struct AlevelChainOpT
   static constexpr bool HAS_TAB = (OUTS & (O_RH | O_TD | O_THESAT | O_TDRH)) != 0; // the saturation table is used
   static constexpr bool USES_P = (OUTS & ~O_TDRH) != 0;                          // the pressure enters the arithmetic
   static constexpr bool Q_IS_RATIO = (OUTS & (O_RH | O_TD | O_THE)) != 0;          // q is divided / divides: its range matters
+  static constexpr bool WIDE_P = KIND == ALEVEL && (OUTS & (O_RH | O_TD)) != 0; // an undefined p is an operand of a live output (see `fast`)
   static constexpr bool HAS_POW = (OUTS & (O_THETA | O_THE)) != 0 || ((OUTS & O_THESAT) != 0 && KIND != PLEVEL); // the Exner function is used
   static constexpr bool SHARED_INPUT = (KIND == HLEVEL);
   static constexpr int ITEM_ROUNDS = J_;
@@ -550,10 +551,21 @@ struct AlevelChainOpT
   // no classification of its argument and the table indices need no clamps -- straight-line code without a single
   // branch, so the compiler interleaves the four points of a thread.  Returns false (after computing harmless
   // garbage) when the inputs are not plausible; the caller then redoes the point with `ieee`.
+  //
+  // WIDE (a-level humidity outputs of a field that is not ALL_DEFINED): alevelhum tests t and q only, so an UNDEFINED p -- the
+  // huge undefined value itself, 1e35 -- flows into RH and Td (FC.cc:1429).  With independent masks that is one point in seven,
+  // and the IEEE redo of those points, one lane at a time, halved the masked operators.  The same straight-line code is valid
+  // for them: the preconditions of div_midrange (divisor, quotient and dividend * 2^-24 normal) hold for 2^64 <= p < 2^126 as long
+  // as qsat = eps * et / p comes out NORMAL and |q| < 2 (q / qsat < 2^128; the double quotient has range to spare); RH then
+  // overflows to +inf in the float conversion exactly as in the reference, and Td sees the clamped ratio.  Tested per point.
+  template <bool WIDE = false>
   __device__ __forceinline__ bool fast(float t, float q, float p, float pi_field, const dev::EwtTable& tab, const dev::PowTable& pw, Raw& r) const
   {
     float pi = pi_field;
     bool plausible = !USES_P || (__float_as_uint(p) - 0x3c000000u < 0x09000000u); // 2^-7 <= p < 2^11
+    const bool wide = WIDE && (__float_as_uint(p) - 0x5f800000u < 0x1f000000u);    // 2^64 <= p < 2^126
+    if (WIDE)
+      plausible = plausible || (wide && (__float_as_uint(q) & 0x7fffffffu) < 0x40000000u);
     if (Q_IS_RATIO) {
       const unsigned uq = __float_as_uint(q) & 0x7fffffffu;
       plausible = plausible && ((uq - 0x12800000u < 0x37000000u) || __float_as_uint(q) == 0u); // 2^-90 <= |q| < 2^20, or +0
@@ -583,6 +595,8 @@ struct AlevelChainOpT
       const float2 e = tab.e[l];
       const float et = e.x + e.y * (x - (float)l); // MC.h:78
       const float qsat = dev::div_midrange(dev::K_EPS * et, p);
+      if (WIDE)
+        plausible = plausible && (!wide || __float_as_uint(qsat) - 0x00800000u < 0x7f000000u); // a positive normal qsat
       if (OUTS & O_THESAT) // t_thesat, FC.cc:196-205 (pi in [36, 1240] for plausible p; the field's own pi comes from the host's powf)
         r.thesat = (HAS_POW && KIND != PLEVEL) ? (K_CP * t + K_XLH * qsat) * rpi : dev::div_midrange(K_CP * t + K_XLH * qsat, pi);
       // (Evaluating this double quotient in float-float arithmetic with a midpoint test -- no conversions, no FP64 -- was
@@ -619,11 +633,17 @@ struct AlevelChainOpT
   // instructions are IEEE round-to-nearest like the scalar ones; every reference expression that adds a rounded product is
   // written with a scalar add (ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 even with -fmad=false).  The table
   // lookups, the Exner function and the double-precision RH quotient stay per point.  Returns the implausible points as bits 0, 1.
+  template <bool WIDE = false>
   __device__ __forceinline__ unsigned fast2(float2 t, float2 q, float2 p, float pi_field, const dev::EwtTable& tab, const dev::PowTable& pw, Raw& r0, Raw& r1) const
   {
     using namespace dev;
     bool pl0 = !USES_P || (__float_as_uint(p.x) - 0x3c000000u < 0x09000000u); // 2^-7 <= p < 2^11
     bool pl1 = !USES_P || (__float_as_uint(p.y) - 0x3c000000u < 0x09000000u);
+    const bool w0 = WIDE && (__float_as_uint(p.x) - 0x5f800000u < 0x1f000000u), w1 = WIDE && (__float_as_uint(p.y) - 0x5f800000u < 0x1f000000u); // see `fast`
+    if (WIDE) {
+      pl0 = pl0 || (w0 && (__float_as_uint(q.x) & 0x7fffffffu) < 0x40000000u);
+      pl1 = pl1 || (w1 && (__float_as_uint(q.y) & 0x7fffffffu) < 0x40000000u);
+    }
     if (Q_IS_RATIO) {
       const unsigned u0 = __float_as_uint(q.x) & 0x7fffffffu, u1 = __float_as_uint(q.y) & 0x7fffffffu;
       pl0 = pl0 && ((u0 - 0x12800000u < 0x37000000u) || __float_as_uint(q.x) == 0u); // 2^-90 <= |q| < 2^20, or +0
@@ -656,6 +676,10 @@ struct AlevelChainOpT
       const float2 e0 = tab.e[l0], e1 = tab.e[l1];
       const float2 et = make_float2(e0.x + e0.y * (x0 - (float)l0), e1.x + e1.y * (x1 - (float)l1)); // MC.h:78
       const float2 qsat = pk_div_midrange(pk_mul(et, K_EPS), p);
+      if (WIDE) {
+        pl0 = pl0 && (!w0 || __float_as_uint(qsat.x) - 0x00800000u < 0x7f000000u);
+        pl1 = pl1 && (!w1 || __float_as_uint(qsat.y) - 0x00800000u < 0x7f000000u);
+      }
       if (OUTS & O_THESAT) {
         const float2 num = pk_add_products(pk_mul(t, K_CP), pk_mul(qsat, K_XLH)); // t_thesat, FC.cc:196-205
         const float2 ts = (HAS_POW && KIND != PLEVEL) ? pk_mul(num, rpi) : pk_div_midrange(num, pi);
@@ -749,7 +773,7 @@ struct AlevelChainOpT
   {
     const bool dq = ALL || !HAS_Q || is_def(q, c.undef);
     const float qe = dq ? q : 0.f;
-    const bool plausible = fast(t, qe, level_p(praw, c), c.m.b, c.tab, c.pw, r);
+    const bool plausible = fast<WIDE_P && !ALL>(t, qe, level_p(praw, c), c.m.b, c.tab, c.pw, r);
     if (ALL)
       return plausible;
     const bool dt = is_def(t, c.undef), dp = KIND == PLEVEL || is_def(praw, c.undef);
@@ -766,7 +790,7 @@ struct AlevelChainOpT
     const bool dq0 = ALL || !HAS_Q || is_def(q.x, c.undef), dq1 = ALL || !HAS_Q || is_def(q.y, c.undef);
     const float2 qe = make_float2(dq0 ? q.x : 0.f, dq1 ? q.y : 0.f);
     const float2 pl = make_float2(level_p(praw.x, c), level_p(praw.y, c));
-    const unsigned implausible = fast2(t, qe, pl, c.m.b, c.tab, c.pw, r0, r1);
+    const unsigned implausible = fast2<WIDE_P && !ALL>(t, qe, pl, c.m.b, c.tab, c.pw, r0, r1);
     if (ALL)
       return implausible;
     auto live = [&](float tt, bool dq, float pr) {
