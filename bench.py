@@ -581,6 +581,43 @@ def run_product(args):
     hybrid = {"call": "fcb200_hlevel_chain_batched", "levels": nlev, "ms_per_step": hms, "gpts": points_per_step / (hms * 1e-3) / 1e9,
               "algorithmic_bytes_per_point": 24, "gbs": 24 * points_per_step / (hms * 1e-3) / 1e9, "frac": 24 * points_per_step / (hms * 1e-3) / 1e9 / peak}
 
+    # BASELINE config 5 flavour of the headline: 30 % of every input undefined -- independent masks per input (an undefined p then
+    # flows into RH / Td, FC.cc:1429) and ONE mask for t, q and p (how below-ground points are masked)
+    masked = {}
+    gm = torch.Generator(device=dev)
+    gm.manual_seed(4242 + rank)
+    fsome = np.full(nlev, 2, np.int32)  # SOME_DEFINED
+    mflags = np.full((4, nlev), -1, np.int32)
+    for kind in ("independent_masks", "common_mask", "hybrid_levels_independent_masks"):
+        mset = [a.clone() for a in sets[0]]
+        common = torch.rand(mset[0].shape, device=dev, generator=gm) < 0.3
+        for a in mset:
+            a[common if kind == "common_mask" else (torch.rand(a.shape, device=dev, generator=gm) < 0.3)] = UNDEF
+
+        def masked_step():
+            if kind.startswith("hybrid"):
+                gpu.call("hlevel_chain_batched", NX, NY, nlev, mset[0], mset[1], ps, ah, bh, "celsius", outs[0], outs[1], outs[2], outs[3], fsome, mflags, UNDEF)
+            else:
+                gpu.call("alevel_chain_batched", NX, NY, nlev, mset[0], mset[1], mset[2], "celsius", outs[0], outs[1], outs[2], outs[3], fsome, mflags, UNDEF)
+
+        gpu.begin_deferred()
+        masked_step()
+        gpu.end_deferred()
+        barrier()
+        m0, m1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        gpu.begin_deferred()
+        m0.record(stream)
+        for k in range(hsteps):
+            masked_step()
+        m1.record(stream)
+        gpu.end_deferred()
+        barrier()
+        mms = m0.elapsed_time(m1) / hsteps
+        masked[kind] = {"undefined_fraction_per_input": 0.3, "ms_per_step": mms, "gpts": points_per_step / (mms * 1e-3) / 1e9,
+                        "frac": (24 if kind.startswith("hybrid") else BYTES_FUSED) * points_per_step / (mms * 1e-3) / 1e9 / peak}
+        del mset, common
+    torch.cuda.empty_cache()
+
     # for the record: the same step as the UNFUSED reference call sequence (four batched launches, 60 B/point)
     gpu.begin_deferred()
     chain_calls(gpu, *sets[0], outs, flags)
@@ -661,7 +698,7 @@ def run_product(args):
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "grid": [NX, NY], "levels_per_step": nlev, "points_per_step_per_gpu": points_per_step,
                        "chain": "aleveltemp c3 + alevelhum c1 + alevelhum c5 + alevelthe c1, fused into one launch per step (t, q, p read once)",
-                       "unfused_ms_per_step": unfused_ms, "hybrid_level_chain": hybrid,
+                       "unfused_ms_per_step": unfused_ms, "hybrid_level_chain": hybrid, "masked_chain": masked,
                        "cache": "inputs larger than L2 (>= 790 MB streamed per step, two alternating input sets)", "sharding": "by field batch, no collective",
                        "tolerance": "mask and flags bit-exact; RH and Td bit-exact; theta / theta_e <= 6e-7 relative measured (reciprocal Exner factor from MUFU.LG2/EX2, "
                                     "tests/test_gpu_parity.py::test_exner_fast_path_error) against north_star's 1e-5; elsewhere values <= 1e-5 relative, with Celsius outputs (Td) and windCooling judged on an absolute floor "

@@ -1329,6 +1329,14 @@ int fcb200_alevel_chain_batched(int nx, int ny, int nfields, const float* t, con
   // needed 127 registers (2 CTAs/SM: profiles/r01_chain_tuning.txt); with the reciprocal Exner factor from the special-function
   // unit the kernel is 113 instructions per point and latency-bound at 2 CTAs/SM (issue 58 %, DRAM 59 %): 168 Gpt/s there,
   // 179 Gpt/s with 3 (profiles/r02aq_chain_variants.txt; 4 CTAs at 64 registers 166, the packed form 177).
+  // Fields with undefined points take another shape: the definedness tests, the `live` logic and four counters cost the masked
+  // instantiation the registers the 3-CTA shape does not have -- 2 CTAs/SM at 126 registers, two groups per thread, packed FP32:
+  // 0.63 of the roofline with 30 % undefined against 0.45 for the all-defined shape (which gets 0.72 / 0.77 from the two shapes).
+  bool all = true;
+  for (int k = 0; k < nfields; ++k)
+    all = all && fDefinedIn[k] == ALL_DEFINED;
+  if (!all)
+    return run(AlevelChainOpT<2, 2, 4, O_ALL, ALEVEL, 1>{tdconv});
   return run(AlevelChainOpT<1, 3, 4, O_ALL, ALEVEL, 0>{tdconv});
 }
 
@@ -1341,28 +1349,37 @@ int fcb200_hlevel_chain_batched(int nx, int ny, int nfields, const float* t, con
   if (nfields > 0 && any_bad_hlevel(make_batch(nx, ny, nfields), alevel, blevel))
     return 0; // FC.cc:1070, 1121, 1170
   const int td_compute = hum_compute(5, td_unit);
-  EwJob<AlevelChainOpT<1, 3, 4, O_ALL, HLEVEL, 0>> job;
-  job.nx = nx;
-  job.ny = ny;
-  job.nfields = nfields;
-  job.in[0] = t;
-  job.in[1] = q;
-  job.in[2] = ps;
-  job.per_field[0] = job.per_field[1] = true;
-  job.per_field[2] = false;
-  job.out[0] = theta;
-  job.out[1] = rh;
-  job.out[2] = td;
-  job.out[3] = thetae;
-  job.flags_in = fDefinedIn;
-  for (int o = 0; o < 4; ++o)
-    job.flags_out[o] = fDefinedOut + (size_t)o * (nfields > 0 ? nfields : 0);
-  job.undef = undef;
-  job.fill_meta = [&](int k, FieldMeta& m) {
-    m.a = alevel[k];
-    m.b = blevel[k];
+  auto run = [&](auto op) {
+    EwJob<decltype(op)> job;
+    job.nx = nx;
+    job.ny = ny;
+    job.nfields = nfields;
+    job.in[0] = t;
+    job.in[1] = q;
+    job.in[2] = ps;
+    job.per_field[0] = job.per_field[1] = true;
+    job.per_field[2] = false;
+    job.out[0] = theta;
+    job.out[1] = rh;
+    job.out[2] = td;
+    job.out[3] = thetae;
+    job.flags_in = fDefinedIn;
+    for (int o = 0; o < 4; ++o)
+      job.flags_out[o] = fDefinedOut + (size_t)o * (nfields > 0 ? nfields : 0);
+    job.undef = undef;
+    job.fill_meta = [&](int k, FieldMeta& m) {
+      m.a = alevel[k];
+      m.b = blevel[k];
+    };
+    return run_ew_job(op, job);
   };
-  return run_ew_job(AlevelChainOpT<1, 3, 4, O_ALL, HLEVEL, 0>{(td_compute >= 9) ? H_T0 : 0.f}, job);
+  const float tdconv = (td_compute >= 9) ? H_T0 : 0.f;
+  bool all = true; // (the shapes: see fcb200_alevel_chain_batched)
+  for (int k = 0; k < nfields; ++k)
+    all = all && fDefinedIn[k] == ALL_DEFINED;
+  if (!all)
+    return run(AlevelChainOpT<2, 2, 4, O_ALL, HLEVEL, 1>{tdconv});
+  return run(AlevelChainOpT<1, 3, 4, O_ALL, HLEVEL, 0>{tdconv});
 }
 
 } // extern "C"
