@@ -91,6 +91,13 @@ int fcb200_slab_exchange(float* ext, int nx, int ext_rows, int nfields, int halo
 /* global flags from the per-rank flags of a sharded operator (HOST array, in/out): ALL iff every rank says ALL, NONE iff every
  * rank says NONE, else SOME.  Synchronises the calling thread first (local flags must be final); collective. */
 int fcb200_slab_combine_flags(int* fDefined, int nfields);
+/* the same combination ON THE STREAM, for the calls queued so far in deferred mode: between fcb200_begin_deferred() and
+ * fcb200_end_deferred(), after the sharded operators, enqueue one tiny kernel + one ncclAllReduce over {no undefined point,
+ * all points undefined} per field; fcb200_end_deferred() then writes the GLOBAL flags into the fDefined arrays of those calls --
+ * one synchronisation per step instead of two and no host round trip before the collective.  Covers every operator whose flag
+ * is checkDefined(count, n) of its own counter (the stencil family); other calls keep their local flags (combine those with
+ * fcb200_slab_combine_flags).  Collective: every rank queues the same calls.  No-op for one rank. */
+int fcb200_slab_reduce_flags(void);
 /* payload bytes this process has sent through fcb200_slab_exchange */
 unsigned long long fcb200_slab_bytes_sent(void);
 

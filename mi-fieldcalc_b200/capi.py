@@ -220,6 +220,10 @@ class Fcb200(Api):
         assert flags.dtype == np.int32 and flags.flags["C_CONTIGUOUS"]
         self._check(self.lib.fcb200_slab_combine_flags(flags.ctypes.data, flags.size))
 
+    def slab_reduce_flags(self) -> None:
+        """deferred mode: enqueue the cross-rank combination of the flags of the calls queued so far (final at end_deferred)"""
+        self._check(self.lib.fcb200_slab_reduce_flags())
+
     def slab_bytes_sent(self) -> int:
         return int(self.lib.fcb200_slab_bytes_sent())
 

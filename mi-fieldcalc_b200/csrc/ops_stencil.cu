@@ -1234,14 +1234,6 @@ const FieldMeta* flags_to_meta(Call& call, const int* fDefined, int nfields)
   return call.upload_meta();
 }
 
-Finalizer flags_from_counters(int* fDefined, int nfields, unsigned long long denom, int counter_offset = 0)
-{
-  return [=](const unsigned long long* cnt) {
-    for (int k = 0; k < nfields; ++k)
-      fDefined[k] = check_defined(cnt[counter_offset + k], denom);
-  };
-}
-
 // ------------------------------------------------------------------------------------ shapiro2_filter
 // FC.cc:2076-2179.  Two iterations of (x pass, y pass); each pass stores float.  Mathematically a
 // separable 2-D filter with these boundary rules (the flat-loop wrap never survives, FC.cc:2117-2120):
@@ -1524,7 +1516,7 @@ int run_stencil(Call& call, const Op& op, int nx, int ny, int nfields, int* fDef
     return -1;
   if (!launch_stencil(call, op, nx, ny, nfields, undef, meta, counters, flat_range))
     return -1;
-  return call.finish(flags_from_counters(fDefined, nfields, denom));
+  return call.finish_counted(fDefined, nfields, denom);
 }
 
 template <int MODE>
@@ -1612,7 +1604,7 @@ int qvector(int nx, int ny, int nfields, const float* z, const float* t, const f
   if (!launch_stencil(call, gx, nx, ny, nfields, undef, meta_in, counters) || !launch_stencil(call, gy, nx, ny, nfields, undef, meta_none, counters + nfields) ||
       !launch_stencil(call, q, nx, ny, nfields, undef, meta_none, counters + 2 * nfields))
     return -1;
-  return call.finish(flags_from_counters(fDefined, nfields, n - 2 * (size_t)nx, 2 * nfields));
+  return call.finish_counted(fDefined, nfields, n - 2 * (size_t)nx, 2 * nfields);
 }
 
 } // namespace
@@ -1847,7 +1839,7 @@ int fcb200_thermalFrontParameter_batched(int nx, int ny, int nfields, const floa
     p2.tx = d_t, p2.ad = d_ad, p2.xm = d_xm, p2.ym = d_ym, p2.pass1_undef = counters, p2.o = d_out;
     if (!launch_stencil(call, p2, nx, ny, nfields, undef, meta, counters + nfields))
       return -1;
-    return call.finish(flags_from_counters(fDefined, nfields, n - 2 * (size_t)nx, nfields));
+    return call.finish_counted(fDefined, nfields, n - 2 * (size_t)nx, nfields);
   }
   bool any_masked = false;
   for (int k = 0; k < nfields; ++k)
@@ -1878,7 +1870,7 @@ int fcb200_thermalFrontParameter_batched(int nx, int ny, int nfields, const floa
       return -1;
   } else if (!launch_stencil(call, op, nx, ny, nfields, undef, meta, counters + nfields))
     return -1;
-  return call.finish(flags_from_counters(fDefined, nfields, n - 2 * (size_t)nx, nfields));
+  return call.finish_counted(fDefined, nfields, n - 2 * (size_t)nx, nfields);
 }
 int fcb200_thermalFrontParameter(int nx, int ny, const float* t, const float* xmapr, const float* ymapr, float* tfp, int* fDefined, float undef)
 {

@@ -90,7 +90,25 @@ struct Deferred
 {
   Finalizer fin;
   const unsigned long long* host_counters;
+  // Call::finish_counted: the flag rule in the open (pool_index < 0: an opaque finaliser)
+  int* flags = nullptr;
+  int nfields = 0;
+  unsigned long long denom = 0;
+  long long pool_index = -1; // of the rule's first counter in the thread's counter pool
 };
+
+std::atomic<SlabReduceFn> g_slab_reduce{nullptr};
+
+// {count == 0, count == denom} per pooled counter (denom 0 = no rule for this counter: {count == 0, 0})
+__global__ void flag_words_kernel(const unsigned long long* __restrict__ counters, const unsigned long long* __restrict__ denom, int* __restrict__ words, int n)
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    const unsigned long long c = counters[i], d = denom[i];
+    words[2 * i] = c == 0 ? 1 : 0;
+    words[2 * i + 1] = (d != 0 && c == d) ? 1 : 0;
+  }
+}
 
 thread_local char g_error[512] = "";
 thread_local bool* t_capturing_failed = nullptr; // &Graph::failed of the graph this thread is capturing
@@ -273,6 +291,51 @@ struct ThreadState
   // captured.  The graph is LAUNCHED on the caller's stream like any other work.
   cudaStream_t stream() const { return (use_user_stream && !capturing) ? user_stream : own_stream; }
 
+  // fcb200_slab_reduce_flags: the rules queued so far, their words all-reduced on the stream; read back by drain()
+  size_t reduced_counters = 0;       // pooled counters covered by the pending reduction (0 = none pending)
+  size_t reduced_queue = 0;          // queue entries covered
+  const int* reduced_words = nullptr; // pinned, 2 ints per pooled counter
+
+  int reduce_flags()
+  {
+    if (!deferred || capturing) {
+      set_error("fcb200: fcb200_slab_reduce_flags() belongs between fcb200_begin_deferred() and fcb200_end_deferred()");
+      return -1;
+    }
+    if (reduced_counters) {
+      set_error("fcb200: fcb200_slab_reduce_flags() was already called in this deferred region");
+      return -1;
+    }
+    const SlabReduceFn reduce = g_slab_reduce.load();
+    if (!reduce || counter_used == 0)
+      return 1; // one rank, or nothing to combine
+    const size_t n = counter_used;
+    unsigned long long* h_denom = static_cast<unsigned long long*>(pin.alloc(n * sizeof(unsigned long long)));
+    int* h_words = static_cast<int*>(pin.alloc(2 * n * sizeof(int)));
+    unsigned long long* d_denom = static_cast<unsigned long long*>(dev.alloc(n * sizeof(unsigned long long)));
+    int* d_words = static_cast<int*>(dev.alloc(2 * n * sizeof(int)));
+    if (!h_denom || !h_words || !d_denom || !d_words)
+      return -1;
+    memset(h_denom, 0, n * sizeof(unsigned long long));
+    for (const auto& d : queue)
+      if (d.pool_index >= 0)
+        for (int k = 0; k < d.nfields; ++k)
+          h_denom[d.pool_index + k] = d.denom;
+    cudaStream_t st = stream();
+    if (!cuda_ok(cudaMemcpyAsync(d_denom, h_denom, n * sizeof(unsigned long long), cudaMemcpyHostToDevice, st), "cudaMemcpyAsync(H2D flag rules)"))
+      return -1;
+    flag_words_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(counter_pool, d_denom, d_words, (int)n);
+    count_launch();
+    if (!reduce(d_words, 2 * n, st))
+      return -1;
+    if (!cuda_ok(cudaMemcpyAsync(h_words, d_words, 2 * n * sizeof(int), cudaMemcpyDeviceToHost, st), "cudaMemcpyAsync(D2H flag words)"))
+      return -1;
+    reduced_counters = n;
+    reduced_queue = queue.size();
+    reduced_words = h_words;
+    return 1;
+  }
+
   bool drain()
   {
     bool ok = true;
@@ -283,10 +346,21 @@ struct ThreadState
     counter_used = 0;
     ok = cuda_ok(cudaStreamSynchronize(stream()), "cudaStreamSynchronize") && ok;
     if (ok) {
-      for (auto& d : queue)
-        if (d.fin)
+      for (size_t i = 0; i < queue.size(); ++i) {
+        const Deferred& d = queue[i];
+        if (i < reduced_queue && d.pool_index >= 0 && (size_t)d.pool_index + (size_t)d.nfields <= reduced_counters) {
+          // the global flag: ALL iff no rank counted an undefined point, NONE iff every rank counted all of its points
+          for (int k = 0; k < d.nfields; ++k) {
+            const int* w = reduced_words + 2 * (d.pool_index + k);
+            d.flags[k] = w[0] ? ALL_DEFINED : w[1] ? NONE_DEFINED : SOME_DEFINED;
+          }
+        } else if (d.fin) {
           d.fin(d.host_counters);
+        }
+      }
     }
+    reduced_counters = reduced_queue = 0;
+    reduced_words = nullptr;
     queue.clear();
     in_flight = false;
     dev.reset();
@@ -630,6 +704,38 @@ int Call::finish(const Finalizer& fin)
   if (ts_->deferred)
     return 1;
   return ts_->drain() ? 1 : -1;
+}
+
+int Call::finish_counted(int* fDefined, int nfields, unsigned long long denom, int counter_offset)
+{
+  const Finalizer fin = [=](const unsigned long long* cnt) {
+    for (int k = 0; k < nfields; ++k)
+      fDefined[k] = check_defined(cnt[counter_offset + k], denom);
+  };
+  const bool pooled = counters_pooled_ && slot_ == 0 && !ts_->capturing;
+  const size_t before = ts_->queue.size();
+  const int rc = finish(fin); // (drains at once unless the thread is in deferred mode)
+  if (rc == 1 && pooled && ts_->deferred && ts_->queue.size() == before + 1) {
+    Deferred& d = ts_->queue.back();
+    d.flags = fDefined;
+    d.nfields = nfields;
+    d.denom = denom;
+    d.pool_index = (counters_dev_ - ts_->counter_pool) + counter_offset;
+  }
+  return rc;
+}
+
+void set_slab_reduce(SlabReduceFn fn)
+{
+  g_slab_reduce.store(fn);
+}
+
+int reduce_queued_flags()
+{
+  ThreadState& ts = thread_state();
+  if (!ts.init())
+    return -1;
+  return ts.reduce_flags();
 }
 
 bool pipeline_fork()

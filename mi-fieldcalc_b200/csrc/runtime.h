@@ -43,6 +43,11 @@ inline int check_defined(unsigned long long n_undefined, unsigned long long n)
 }
 
 void set_error(const char* fmt, ...);
+// slab.cu installs the cross-rank reduction (an in-place ncclAllReduce(MIN) of `n` ints on `stream`; false = error text set)
+typedef bool (*SlabReduceFn)(int* words, size_t n, cudaStream_t stream);
+void set_slab_reduce(SlabReduceFn fn);
+// enqueue the cross-rank combination of the flags of the calls queued so far in deferred mode (see Call::finish_counted)
+int reduce_queued_flags();
 bool cuda_ok(cudaError_t e, const char* what);
 void count_launch(unsigned n = 1);
 int sm_count();
@@ -96,6 +101,10 @@ public:
   // copy host outputs back, fetch the counters, synchronise and run `fin` -- or, in deferred mode,
   // queue all of that for fcb200_end_deferred().  Returns 1 on success, -1 on a runtime error.
   int finish(const Finalizer& fin);
+  // finish() for the common rule "fDefined[k] = check_defined(counters[counter_offset + k], denom)".  Calls that finish this way
+  // can have their flags combined across the ranks of a row-slab run ON THE STREAM (fcb200_slab_reduce_flags, slab.cu): the
+  // runtime knows the rule, so {count == 0, count == denom} can be formed and all-reduced on the device.
+  int finish_counted(int* fDefined, int nfields, unsigned long long denom, int counter_offset = 0);
   // bytes of host memory this call staged so far (0 = everything was device resident)
   size_t staged_bytes() const { return staged_; }
 

@@ -122,6 +122,18 @@ bool nccl_ok(const Nccl& n, int rc, const char* what)
   return false;
 }
 
+// the runtime's hook for fcb200_slab_reduce_flags: an in-place MIN over the ranks of {count == 0, count == denom} words
+bool slab_reduce_words(int* words, size_t n, cudaStream_t stream)
+{
+  SlabState& s = slab();
+  std::lock_guard<std::mutex> g(s.lock);
+  if (!s.comm) {
+    set_error("fcb200: fcb200_slab_init has not been called");
+    return false;
+  }
+  return nccl_ok(s.nccl, s.nccl.AllReduce(words, words, n, NCCL_INT32, NCCL_MIN, s.comm, stream), "ncclAllReduce(flag words)");
+}
+
 // One thread per float4 (or float) of a halo row.  Message layout: [field][halo row][nx], the same on both sides.
 //   PACK:   msg_up   <- owned rows [up, up + halo)              (goes to rank - 1)
 //           msg_down <- owned rows [up + rows - halo, up + rows) (goes to rank + 1)
@@ -198,6 +210,7 @@ int fcb200_slab_init(int rank, int nranks, const char* id128)
   memcpy(id.internal, id128, 128);
   if (!nccl_ok(s.nccl, s.nccl.CommInitRank(&s.comm, nranks, id, rank), "ncclCommInitRank"))
     return -1;
+  set_slab_reduce(&slab_reduce_words);
   return 1;
 }
 
@@ -205,6 +218,7 @@ int fcb200_slab_finalize(void)
 {
   SlabState& s = slab();
   std::lock_guard<std::mutex> g(s.lock);
+  set_slab_reduce(nullptr);
   if (s.comm)
     s.nccl.CommDestroy(s.comm);
   s.comm = nullptr;
@@ -304,6 +318,13 @@ int fcb200_slab_exchange(float* ext, int nx, int ext_rows, int nfields, int halo
   count_launch(2);
   g_bytes_sent.fetch_add((unsigned long long)(sizeof(float) * msg * ((up ? 1 : 0) + (down ? 1 : 0))), std::memory_order_relaxed);
   return call.finish(Finalizer());
+}
+
+int fcb200_slab_reduce_flags(void)
+{
+  if (slab().nranks == 1)
+    return 1;
+  return reduce_queued_flags();
 }
 
 int fcb200_slab_combine_flags(int* fDefined, int nfields)

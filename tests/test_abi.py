@@ -18,7 +18,7 @@ def test_library_exports_every_declared_symbol():
     sigs = capi.parse_inc(os.path.join(capi.INCLUDE, "fcb200_api.inc"), "FC_FN")
     sigs.update(capi.parse_inc(os.path.join(capi.INCLUDE, "fcb200_batched.inc"), "FCB_FN"))
     assert len(sigs) >= 64
-    runtime = ["fcb200_graph_begin", "fcb200_graph_end", "fcb200_graph_launch", "fcb200_graph_kernels", "fcb200_graph_destroy", "fcb200_version", "fcb200_last_error", "fcb200_device_count", "fcb200_set_device", "fcb200_set_stream", "fcb200_begin_deferred",
+    runtime = ["fcb200_slab_reduce_flags", "fcb200_graph_begin", "fcb200_graph_end", "fcb200_graph_launch", "fcb200_graph_kernels", "fcb200_graph_destroy", "fcb200_version", "fcb200_last_error", "fcb200_device_count", "fcb200_set_device", "fcb200_set_stream", "fcb200_begin_deferred",
                "fcb200_end_deferred", "fcb200_in_deferred", "fcb200_synchronize", "fcb200_launch_count", "fcb200_slab_unique_id", "fcb200_slab_init",
                "fcb200_slab_finalize", "fcb200_slab_rank", "fcb200_slab_nranks", "fcb200_slab_partition", "fcb200_slab_exchange",
                "fcb200_slab_combine_flags", "fcb200_slab_bytes_sent"]

@@ -41,7 +41,7 @@ def main():
     gpu.set_device(local)
     stream = torch.cuda.current_stream()
     gpu.set_stream(stream.cuda_stream, True)
-    out = [slab_run.slab_record(gpu, torch, dist, dev, stream, rank, world, nx=args.nx, ny=args.ny, levels=args.levels, steps=args.steps, mask=m) for m in (0.0, 0.3)]
+    out = [slab_run.slab_record(gpu, torch, dist, dev, stream, rank, world, nx=args.nx, ny=args.ny, levels=args.levels, steps=args.steps, mask=m) for m in (0.0, 0.3, -1.0)]
     sys.stdout.flush()
     os.dup2(saved, 1)
     os.close(saved)
