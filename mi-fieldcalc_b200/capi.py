@@ -242,5 +242,6 @@ _singleton = None
 def load() -> Fcb200:
     global _singleton
     if _singleton is None:
-        _singleton = Fcb200()
+        # FCB200_LIB: a development switch (tools/shape_variants.sh builds libraries that differ in one kernel shape)
+        _singleton = Fcb200(os.environ.get("FCB200_LIB") or LIB_PATH)
     return _singleton

@@ -41,11 +41,15 @@ __device__ __forceinline__ float ms2knots(float ff)
 }
 
 // kIndex, FC.cc:745-814.  Same construction as CvHumOp: branch-free inside the saturation table (both levels), redo outside.
+#ifndef FCB_KI_U
+#define FCB_KI_U 2
+#define FCB_KI_MB 2
+#endif
 struct KIndexOp
 {
-  static constexpr int NIN = 5, NOUT = 1, UNROLL = 2;
+  static constexpr int NIN = 5, NOUT = 1, UNROLL = FCB_KI_U;
   static constexpr int NCOUNT = 1;
-  static constexpr int MIN_BLOCKS = 2;
+  static constexpr int MIN_BLOCKS = FCB_KI_MB;
   static constexpr bool HEAVY = false;
   static constexpr bool USES_EWT = true, USES_POW = false;
   static constexpr bool QUAD = true;
@@ -131,11 +135,15 @@ struct KIndexOp
 };
 
 // ductingIndex, FC.cc:816-870.  Same construction as CvHumOp: branch-free inside the saturation table, redo outside.
+#ifndef FCB_DI_U
+#define FCB_DI_U 2
+#define FCB_DI_MB 4
+#endif
 struct DuctingIndexOp
 {
-  static constexpr int NIN = 2, NOUT = 1, UNROLL = 2;
+  static constexpr int NIN = 2, NOUT = 1, UNROLL = FCB_DI_U;
   static constexpr int NCOUNT = 1;
-  static constexpr int MIN_BLOCKS = 4;
+  static constexpr int MIN_BLOCKS = FCB_DI_MB;
   static constexpr bool HEAVY = false;
   static constexpr bool USES_EWT = true, USES_POW = false;
   static constexpr bool QUAD = true;
@@ -319,11 +327,15 @@ struct SweatOp
 };
 
 // seaSoundSpeed, FC.cc:1555-1602 (Ross 1978): double polynomials of the float temperature and salinity
+#ifndef FCB_SS_U
+#define FCB_SS_U 2
+#define FCB_SS_MB 5 // (0.74 -> 0.80 of the roofline against 4; profiles/r02ay_shape_variants.txt)
+#endif
 struct SeaSoundOp
 {
-  static constexpr int NIN = 2, NOUT = 1, UNROLL = 2;
+  static constexpr int NIN = 2, NOUT = 1, UNROLL = FCB_SS_U;
   static constexpr int NCOUNT = 1;
-  static constexpr int MIN_BLOCKS = 4;
+  static constexpr int MIN_BLOCKS = FCB_SS_MB;
   static constexpr bool HEAVY = false;
   static constexpr bool USES_EWT = false, USES_POW = false;
   float tconv;
@@ -383,11 +395,15 @@ struct CopyOp
 // cvhum, FC.cc:1738-1817.  Branch-free path for temperatures inside the saturation table (dev::EwtFast), the four points of a
 // float4 group in one basic block; points outside the table (their result is undefined or, just below -100 degC, extrapolated)
 // are redone by `exact`, the reference's expressions with the ordinary operators.
+#ifndef FCB_CV_U
+#define FCB_CV_U 2
+#define FCB_CV_MB 4
+#endif
 struct CvHumOp
 {
-  static constexpr int NIN = 2, NOUT = 1, UNROLL = 2;
+  static constexpr int NIN = 2, NOUT = 1, UNROLL = FCB_CV_U;
   static constexpr int NCOUNT = 1;
-  static constexpr int MIN_BLOCKS = 4;
+  static constexpr int MIN_BLOCKS = FCB_CV_MB;
   static constexpr bool HEAVY = false;
   static constexpr bool USES_EWT = true, USES_POW = false;
   static constexpr bool QUAD = true;
@@ -477,11 +493,15 @@ struct CvHumOp
 // unqualified sqrt(v) and exp(x) on float arguments are the C library's DOUBLE functions: v*sqrt(v) and
 // Pc*exp(..) are double expressions rounded to float on assignment.  exp() here is CUDA's (<= 1 ulp of a
 // double): the float result differs from glibc's in about one case in 2^29.
+#ifndef FCB_AH_U
+#define FCB_AH_U 1
+#define FCB_AH_MB 4
+#endif
 struct AbsHumOp
 {
-  static constexpr int NIN = 2, NOUT = 1, UNROLL = 1;
+  static constexpr int NIN = 2, NOUT = 1, UNROLL = FCB_AH_U;
   static constexpr int NCOUNT = 1;
-  static constexpr int MIN_BLOCKS = 4;
+  static constexpr int MIN_BLOCKS = FCB_AH_MB;
   static constexpr bool HEAVY = false;
   static constexpr bool USES_EWT = false, USES_POW = false;
   template <bool ALL>

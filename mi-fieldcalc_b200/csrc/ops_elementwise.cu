@@ -305,11 +305,20 @@ struct HPressureOp
 // double constants come from the constant bank), the four points of a float4 group in one basic block, and a non-inlined
 // redo with the ordinary operators for calm (u = v = 0), NaN, infinite or absurd winds.  The temperature needs no test: it only
 // enters double arithmetic that behaves identically for every bit pattern.
+#ifndef FCB_PL_U
+#define FCB_PL_U 2
+#define FCB_PL_MB 3
+#define FCB_PL_MB4 4
+#endif
+#ifndef FCB_WC_U
+#define FCB_WC_U 2
+#define FCB_WC_MB 3
+#endif
 struct WindCoolingOp
 {
-  static constexpr int NIN = 3, NOUT = 1, UNROLL = 2;
+  static constexpr int NIN = 3, NOUT = 1, UNROLL = FCB_WC_U;
   static constexpr int NCOUNT = 0;
-  static constexpr int MIN_BLOCKS = 3;
+  static constexpr int MIN_BLOCKS = FCB_WC_MB;
   static constexpr bool HEAVY = false;
   static constexpr bool USES_EWT = false, USES_POW = true;
   static constexpr bool QUAD = true;
@@ -918,7 +927,7 @@ int impl_pleveltemp(const Batch& b, const float* tinp, const float* p, const cha
     m.b = host_pidcp(p[k]) * H_CP;
   };
   if (compute == 4) // T -> theta_e,sat: one-output form of the fused chain's branch-free code (0.49 -> 0.61; 4 CTAs/SM beats 3 and 5)
-    return run_elementwise(b, AlevelChainOpT<2, 4, 2, O_THESAT, PLEVEL>{0.f}, in, pf, tout, fDefined, undef, FLAG_FROM_COUNT, fill);
+    return run_elementwise(b, AlevelChainOpT<FCB_PL_U, FCB_PL_MB4, 2, O_THESAT, PLEVEL>{0.f}, in, pf, tout, fDefined, undef, FLAG_FROM_COUNT, fill);
   TempOp<PLEVEL> op{compute};
   return run_elementwise(b, op, in, pf, tout, fDefined, undef, FLAG_FROM_COUNT, fill);
 }
@@ -947,11 +956,11 @@ int impl_plevelhum(const Batch& b, const float* t, const float* huminp, const fl
   };
   // T, q -> RH and T, q -> Td: the fused chain's branch-free code with one output and the field's scalar pressure
   if (to_ah[compute] == 1)
-    return run_elementwise(b, AlevelChainOpT<2, 3, 2, O_RH, PLEVEL>{0.f}, in, pf, humout, fDefined, undef, FLAG_FROM_COUNT, fill);
+    return run_elementwise(b, AlevelChainOpT<FCB_PL_U, FCB_PL_MB, 2, O_RH, PLEVEL>{0.f}, in, pf, humout, fDefined, undef, FLAG_FROM_COUNT, fill);
   if (to_ah[compute] == 5 || to_ah[compute] == 9)
-    return run_elementwise(b, AlevelChainOpT<2, 3, 2, O_TD, PLEVEL>{(compute >= 9) ? H_T0 : 0.f}, in, pf, humout, fDefined, undef, FLAG_FROM_COUNT, fill);
+    return run_elementwise(b, AlevelChainOpT<FCB_PL_U, FCB_PL_MB, 2, O_TD, PLEVEL>{(compute >= 9) ? H_T0 : 0.f}, in, pf, humout, fDefined, undef, FLAG_FROM_COUNT, fill);
   if (to_ah[compute] == 7 || to_ah[compute] == 11) // T, RH -> Td (p-level numbering 5 / 9): p is not used, not even when it is undefined
-    return run_elementwise(b, AlevelChainOpT<2, 3, 2, O_TDRH, PLEVEL>{(compute >= 9) ? H_T0 : 0.f}, in, pf, humout, fDefined, undef, FLAG_FROM_COUNT, fill);
+    return run_elementwise(b, AlevelChainOpT<FCB_PL_U, FCB_PL_MB, 2, O_TDRH, PLEVEL>{(compute >= 9) ? H_T0 : 0.f}, in, pf, humout, fDefined, undef, FLAG_FROM_COUNT, fill);
   return run_elementwise(b, op, in, pf, humout, fDefined, undef, FLAG_FROM_COUNT, [&](int k, FieldMeta& m) {
     if (p[k] == undef && !rh_td)
       m.all |= 2; // fillUndef -> every point undefined -> NONE_DEFINED (FC.cc:429-432)
