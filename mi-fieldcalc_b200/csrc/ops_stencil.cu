@@ -1338,7 +1338,7 @@ __device__ __forceinline__ void shapiro_pass(const float (&lo)[W], const float (
   }
 }
 
-template <int W, bool ALL, bool FLOATPATH>
+template <int W, bool ALL, bool FLOATPATH, bool ANYCOL = false>
 __device__ __forceinline__ void shapiro_xpass(const float (&f)[W], float (&out)[W], float s, unsigned wbits, unsigned copybits)
 {
   float lo[W], hi[W], r[W];
@@ -1350,11 +1350,11 @@ __device__ __forceinline__ void shapiro_xpass(const float (&f)[W], float (&out)[
     hi[j - 1] = f[j];
   }
   shapiro_pass<W, ALL, FLOATPATH>(lo, f, hi, r, s, wbits);
-  // columns 0 and nx-1 are copied.  W = 4: x0 and nx are multiples of 4, so they can only be the lane's
-  // first resp. last column
+  // columns 0 and nx-1 are copied.  W = 4 with float4 rows: x0 and nx are multiples of 4, so they can only be the lane's
+  // first resp. last column (ANYCOL: rows of any alignment, any of the lane's columns)
 #pragma unroll
   for (int j = 0; j < W; ++j)
-    out[j] = ((W == 1 || j == 0 || j == W - 1) && ((copybits >> j) & 1u)) ? f[j] : r[j];
+    out[j] = ((W == 1 || ANYCOL || j == 0 || j == W - 1) && ((copybits >> j) & 1u)) ? f[j] : r[j];
 }
 
 template <int W, bool ALL, bool FLOATPATH>
@@ -1370,13 +1370,24 @@ __device__ __forceinline__ void shapiro_ypass(const float (&lo)[W], const float 
   shapiro_pass<W, ALL, FLOATPATH>(lo, f, hi, out, s, wbits);
 }
 
-template <int W, bool ALL>
+// VEC = the lane's W = 4 columns are one float4 (every row on a 16-byte boundary).  W = 4 without VEC: rows of ANY alignment (an odd
+// row length: MEPS) -- the same register arithmetic on four adjacent columns, but four 4-byte loads and stores per row, each
+// column with its own bounds test (the lane's columns may straddle the grid's last column).  The accesses of a warp then have a
+// 16-byte stride: four times the L1 wavefronts of the float4 form, which this kernel has room for (it is issue-bound), against
+// the one-column-per-lane form (W = 1), which needs twice the instructions per point.
+template <int W, bool ALL, bool VEC = (W == 4)>
 __device__ __forceinline__ void shapiro_band(const float* __restrict__ src, float* __restrict__ dst, int nx, int ny, int x0, int r0, int r1, float undef)
 {
   constexpr int HL = ShapiroGeom<W>::HL;
+  constexpr bool ANYCOL = (W == 4) && !VEC;
   const int lane = threadIdx.x & 31;
-  const bool col_ok = x0 >= 0 && x0 + W <= nx; // W = 4: nx % 4 == 0 and x0 % 4 == 0, a float4 is entirely in or out
+  const bool col_ok = ANYCOL ? (x0 + W > 0 && x0 < nx) : (x0 >= 0 && x0 + W <= nx); // VEC: nx % 4 == 0 and x0 % 4 == 0, a float4 is entirely in or out
   const bool store_lane = col_ok && lane >= HL && lane < 32 - HL;
+  unsigned okbits = 0; // ANYCOL: the lane's columns inside the grid
+#pragma unroll
+  for (int j = 0; j < W; ++j)
+    if (x0 + j >= 0 && x0 + j < nx)
+      okbits |= 1u << j;
   unsigned copybits = 0; // columns 0 and nx-1 are copied by the x passes
 #pragma unroll
   for (int j = 0; j < W; ++j)
@@ -1387,7 +1398,11 @@ __device__ __forceinline__ void shapiro_band(const float* __restrict__ src, floa
   auto load_row = [&](int r, float (&q)[W]) {
     if (col_ok && r >= 0 && r < ny && r < rend) {
       const float* p = src + (long long)r * nx + x0;
-      if (W == 4) {
+      if (ANYCOL) {
+#pragma unroll
+        for (int j = 0; j < W; ++j)
+          q[j] = ((okbits >> j) & 1u) ? p[j] : 0.f;
+      } else if (W == 4) {
         const float4 t = *reinterpret_cast<const float4*>(p);
         q[0] = t.x;
         q[W > 1 ? 1 : 0] = t.y;
@@ -1445,15 +1460,20 @@ __device__ __forceinline__ void shapiro_band(const float* __restrict__ src, floa
       }
       // iteration 1: x pass on row r, y pass on row r-1
       float a2[W], b[W], c2[W], d[W];
-      shapiro_xpass<W, ALL, true>(f, a2, 0.25f, mx, copybits);
+      shapiro_xpass<W, ALL, true, ANYCOL>(f, a2, 0.25f, mx, copybits);
       shapiro_ypass<W, ALL, true>(a0, a1, a2, b, 0.25f, my, r - 1 <= 0 || r - 1 >= ny - 1);
       // iteration 2: x pass on row r-1, y pass on row r-2
-      shapiro_xpass<W, ALL, true>(b, c2, -0.25f, mx_prev, copybits);
+      shapiro_xpass<W, ALL, true, ANYCOL>(b, c2, -0.25f, mx_prev, copybits);
       shapiro_ypass<W, ALL, W == 4>(c0, c1, c2, d, -0.25f, my_prev, r - 2 <= 0 || r - 2 >= ny - 1); // (W = 4: the packed float form for all four passes)
       const int ro = r - 2;
       if (store_lane && ro >= r0 && ro < r1) {
         float* p = dst + (long long)ro * nx + x0;
-        if (W == 4)
+        if (ANYCOL) {
+#pragma unroll
+          for (int j = 0; j < W; ++j)
+            if ((okbits >> j) & 1u)
+              p[j] = d[j];
+        } else if (W == 4)
           *reinterpret_cast<float4*>(p) = make_float4(d[0], d[W > 1 ? 1 : 0], d[W > 2 ? 2 : 0], d[W > 3 ? 3 : 0]);
         else
           *p = d[0];
@@ -1473,7 +1493,7 @@ __device__ __forceinline__ void shapiro_band(const float* __restrict__ src, floa
   }
 }
 
-template <int W>
+template <int W, bool VEC = (W == 4)>
 __global__ void __launch_bounds__(SH_WARPS * 32) shapiro2_kernel(const float* __restrict__ fin, float* __restrict__ fout, int nx, int ny, int strips,
                                                                 int bands, int rows_per_band, const FieldMeta* meta, float undef)
 {
@@ -1494,9 +1514,9 @@ __global__ void __launch_bounds__(SH_WARPS * 32) shapiro2_kernel(const float* __
   const float* src = fin + (long long)field * nx * ny;
   float* dst = fout + (long long)field * nx * ny;
   if (meta[field].all != 0)
-    shapiro_band<W, true>(src, dst, nx, ny, x0, r0, r1, undef);
+    shapiro_band<W, true, VEC>(src, dst, nx, ny, x0, r0, r1, undef);
   else
-    shapiro_band<W, false>(src, dst, nx, ny, x0, r0, r1, undef);
+    shapiro_band<W, false, VEC>(src, dst, nx, ny, x0, r0, r1, undef);
 }
 
 } // namespace
@@ -1899,7 +1919,10 @@ int fcb200_shapiro2_filter_batched(int nx, int ny, int nfields, float* field, fl
     return -1;
   // W = 4 needs every row of every field on a 16-byte boundary
   const bool vec = (nx % 4 == 0) && ((reinterpret_cast<uintptr_t>(d_in) | reinterpret_cast<uintptr_t>(d_tmp)) & 15) == 0;
-  const int useful = vec ? ShapiroGeom<4>::USEFUL : ShapiroGeom<1>::USEFUL;
+  // anything else: four adjacent columns per lane with 4-byte accesses (the one-column form, W = 1, is kept for comparison:
+  // FCB200_SHAPIRO_W1; MEPS x 96, 30 % masked: 0.29 of the roofline with W = 1)
+  static const bool w1 = getenv("FCB200_SHAPIRO_W1") != nullptr; // (development switch)
+  const int useful = (vec || !w1) ? ShapiroGeom<4>::USEFUL : ShapiroGeom<1>::USEFUL;
   const int strips = (nx + useful - 1) / useful;
   const int strip_groups = (strips + SH_WARPS - 1) / SH_WARPS;
   // rows per band: as tall as possible (a band re-reads 4 halo rows) while the launch still fills the GPU
@@ -1914,6 +1937,8 @@ int fcb200_shapiro2_filter_batched(int nx, int ny, int nfields, float* field, fl
   }
   if (vec)
     shapiro2_kernel<4><<<(unsigned)grid, SH_WARPS * 32, 0, call.stream()>>>(d_in, d_tmp, nx, ny, strips, bands, rows_per_band, meta, undef);
+  else if (!w1)
+    shapiro2_kernel<4, false><<<(unsigned)grid, SH_WARPS * 32, 0, call.stream()>>>(d_in, d_tmp, nx, ny, strips, bands, rows_per_band, meta, undef);
   else
     shapiro2_kernel<1><<<(unsigned)grid, SH_WARPS * 32, 0, call.stream()>>>(d_in, d_tmp, nx, ny, strips, bands, rows_per_band, meta, undef);
   count_launch();
