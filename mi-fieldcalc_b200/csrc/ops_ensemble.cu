@@ -168,13 +168,142 @@ __device__ __forceinline__ void ensemble_points(const EnsArgs& a, const float* c
     out[base] = r[0];
 }
 
+// stddevValue on members with undefined points, WITHOUT a branch per point (BF kernel instantiation): the reference's
+//   if (defined) { delta = x - m; n += 1; m += delta / n; m2 += delta * (x - m); }          (FC.cc:2739-2747)
+// is computed for every point.  An undefined value is replaced by the running mean itself: delta = +0, the quotient is +0
+// and both accumulators keep their bits (m is never -0: it starts at +0 and a sum of opposite numbers is +0), so nothing has
+// to be selected afterwards.  The divisor is the point's own count of defined members so far: {n, RN(1/n)} comes from the
+// shared-memory table indexed by that count (entry 0 = a dummy for "none yet") and the quotient is Markstein's corrected
+// product exactly as in the all-defined form above (same proof: an integer divisor <= 4096, a normal delta; a ZERO delta
+// gives q0 = rem = q = 0 exactly, in both signs the same sums as the IEEE quotient).
+// Definedness is ONE comparison per point, `x != u` (unordered: FSETP.NEU) with u = undef, or u = NaN for a member whose
+// field flag is ALL_DEFINED (the reference does not look at its values): true for every x in the second case, and in the
+// first for every x but undef -- including a NaN x, which the reference skips.  Such a NaN makes m NaN for good, which is
+// tested once at the end: the group is then redone by the branching form (as is a group whose NaN the reference does use).
+// The host keeps a NaN `undef` away from this kernel.
+// Four points of a thread are independent instruction streams and the loads run D members ahead -- with a branch per
+// point (BSSY / BSYNC, an IEEE division with its slow-path call inside) neither happens: 25 instructions per point and
+// member against 15, one load in flight per warp.  A non-zero delta below 1e-30 (found as the unsigned minimum of
+// 2 * bits - 1, which sends both zeros to the top), or one above 1e30, also sends the group to the branching form.
+template <int W>
+__device__ __forceinline__ bool stddev_points_bf(const EnsArgs& a, const float* const* mptr, const int* mflag, const float2* recip0, long long base,
+                                                 float* out, unsigned& nundef)
+{
+  constexpr int D = 3; // members in flight
+  struct Pts
+  {
+    float v[W];
+  };
+  const float undef = a.undef;
+  const int M = a.nmembers;
+  float m[W], m2[W];
+  // the point's count of defined members, kept as the shared-memory address of its {n, RN(1/n)} table entry
+  const unsigned tab0 = (unsigned)__cvta_generic_to_shared(recip0);
+  unsigned tab[W];
+#pragma unroll
+  for (int w = 0; w < W; ++w) {
+    m[w] = 0.f;
+    m2[w] = 0.f;
+    tab[w] = tab0;
+  }
+  float dmax = 1.f;
+  unsigned vmin = 0xffffffffu;
+
+  auto load = [&](int j) {
+    Pts p;
+    // (volatile: the compiler otherwise sinks the loads back to their first use and one is in flight again)
+    if constexpr (W == 4)
+      asm volatile("ld.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(p.v[0]), "=f"(p.v[1]), "=f"(p.v[2]), "=f"(p.v[3]) : "l"(mptr[j] + base));
+    else
+      asm volatile("ld.global.f32 %0, [%1];" : "=f"(p.v[0]) : "l"(mptr[j] + base));
+    return p;
+  };
+  auto step = [&](int j, const Pts& x) {
+    const float u = (mflag[j] & MF_ALL) ? __int_as_float(0x7fc00000) : undef;
+    float delta[W];
+#pragma unroll
+    for (int w = 0; w < W; ++w) {
+      // def = x != u (unordered);  if (def) count += 1;  xv = def ? x : m;  {n, 1/n} = table[count]
+      float xv;
+      float2 ny;
+      asm("{\n\t.reg .pred p;\n\t"
+          "setp.neu.f32 p, %4, %5;\n\t"
+          "@p add.u32 %0, %0, 8;\n\t"
+          "selp.f32 %1, %4, %6, p;\n\t"
+          "ld.shared.v2.f32 {%2, %3}, [%0];\n\t}"
+          : "+r"(tab[w]), "=f"(xv), "=f"(ny.x), "=f"(ny.y)
+          : "f"(x.v[w]), "f"(u), "f"(m[w]));
+      delta[w] = xv - m[w];
+      const float q0 = delta[w] * ny.y;
+      const float rem = __fmaf_rn(-q0, ny.x, delta[w]);
+      m[w] += __fmaf_rn(rem, ny.y, q0);
+      m2[w] += delta[w] * (xv - m[w]);
+    }
+#pragma unroll
+    for (int w = 0; w < W; w += 2) {
+      if (w + 1 < W) {
+        dmax = fmaxf(fmaxf(dmax, fabsf(delta[w])), fabsf(delta[w + 1]));
+        vmin = min(min(vmin, 2u * __float_as_uint(delta[w]) - 1u), 2u * __float_as_uint(delta[w + 1]) - 1u);
+      } else {
+        dmax = fmaxf(dmax, fabsf(delta[w]));
+        vmin = min(vmin, 2u * __float_as_uint(delta[w]) - 1u);
+      }
+    }
+  };
+
+  Pts buf[D];
+#pragma unroll
+  for (int d = 0; d < D; ++d)
+    buf[d] = load(min(d, M - 1));
+  int j = 0;
+#pragma unroll 2
+  for (; j + D <= M; j += D) {
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+      const Pts x = buf[d];
+      buf[d] = load(min(j + d + D, M - 1));
+      step(j + d, x);
+    }
+  }
+#pragma unroll
+  for (int d = 0; d < D - 1; ++d)
+    if (j + d < M)
+      step(j + d, buf[d]);
+
+  bool ok = dmax <= 1e30f && vmin >= 2u * __float_as_uint(1e-30f) - 1u;
+#pragma unroll
+  for (int w = 0; w < W; ++w)
+    ok = ok && m[w] == m[w];
+  if (!ok)
+    return false;
+  float r[W];
+#pragma unroll
+  for (int w = 0; w < W; ++w) {
+    const int cnt = (int)((tab[w] - tab0) >> 3);
+    if (cnt > 0)
+      r[w] = sqrtf(m2[w] / (float)cnt);
+    else {
+      r[w] = undef;
+      nundef += 1;
+    }
+  }
+  if constexpr (W == 4)
+    *reinterpret_cast<float4*>(out + base) = make_float4(r[0], r[1], r[2], r[3]);
+  else
+    out[base] = r[0];
+  return true;
+}
+
 // TG (tables_global) = the member tables are too large for shared memory (more than 2048 members): read from the device tables
 // directly, the time offset added at each use.  A separate instantiation: the common kernel keeps its tables in shared memory
 // with shared-memory loads and no offset arithmetic (as one kernel with a run-time switch, generic loads and a 64-bit add per
 // member load cost stddevValue a fifth of its throughput: 0.82 -> 0.64 of the roofline).
-template <int MODE, int W, bool TG>
+// BF (stddevValue, tables in shared memory) = time steps with undefined points take stddev_points_bf.  Its own instantiation,
+// launched only when some time step of the batch is not all-defined: the all-defined kernel keeps its registers.
+template <int MODE, int W, bool TG, bool BF = false>
 __global__ void __launch_bounds__(EN_THREADS) ensemble_kernel(const EnsArgs a)
 {
+  static_assert(!BF || (MODE == EN_STDDEV && !TG), "the branch-free masked form exists for stddevValue with shared-memory tables");
   extern __shared__ unsigned char smem_raw[];
   const int time = blockIdx.x / a.chunks;
   const int chunk = blockIdx.x - time * a.chunks;
@@ -182,18 +311,21 @@ __global__ void __launch_bounds__(EN_THREADS) ensemble_kernel(const EnsArgs a)
   const long long n = a.n;
   const float** s_ptr = reinterpret_cast<const float**>(smem_raw);
   float2* s_recip = reinterpret_cast<float2*>(smem_raw + sizeof(float*) * M);
-  int* s_flag = reinterpret_cast<int*>(smem_raw + (sizeof(float*) + sizeof(float2)) * M);
+  // BF: the {n, 1/n} table has a leading dummy entry (index = number of defined members so far, 0 = none yet)
+  int* s_flag = reinterpret_cast<int*>(smem_raw + (sizeof(float*) + sizeof(float2)) * M + (BF ? sizeof(float2) : 0));
   if (!TG) {
     for (int j = threadIdx.x; j < M; j += EN_THREADS) {
       s_ptr[j] = a.members[j] + (long long)time * n;
       s_flag[j] = a.member_flags[(long long)time * M + j];
-      s_recip[j] = reinterpret_cast<const float2*>(a.recip)[j];
+      s_recip[j + (BF ? 1 : 0)] = reinterpret_cast<const float2*>(a.recip)[j];
     }
+    if (BF && threadIdx.x == 0)
+      s_recip[0] = make_float2(1.f, 1.f);
     __syncthreads();
   }
   const float* const* mptr = TG ? a.members : s_ptr;
   const int* mflag = TG ? a.member_flags + (long long)time * M : s_flag;
-  const float2* recip = TG ? reinterpret_cast<const float2*>(a.recip) : s_recip;
+  const float2* recip = TG ? reinterpret_cast<const float2*>(a.recip) : s_recip + (BF ? 1 : 0);
   const long long moff = TG ? (long long)time * n : 0;
 
   // per-time peel so that the float4 groups are 16-byte aligned (see elementwise.cuh)
@@ -208,7 +340,7 @@ __global__ void __launch_bounds__(EN_THREADS) ensemble_kernel(const EnsArgs a)
   if (g < groups) {
     if (fast)
       ensemble_points<MODE, W, true>(a, mptr, mflag, recip, time, head + g * W, out, in_all, nundef, moff);
-    else
+    else if (!BF || !stddev_points_bf<W>(a, mptr, mflag, s_recip, head + g * W, out, nundef))
       ensemble_points<MODE, W, false>(a, mptr, mflag, recip, time, head + g * W, out, in_all, nundef, moff);
   }
 
@@ -353,7 +485,13 @@ int run_ensemble(const EnsHost& h)
   }
   // 20 bytes of shared memory per member: up to 2048 members fit the 48 KB every device grants without an opt-in
   a.tables_global = M > 2048 ? 1 : 0;
-  const size_t smem = a.tables_global ? 0 : (sizeof(float*) + sizeof(float2) + sizeof(int)) * Mp;
+  // stddevValue with some time step that is not all-defined: the kernel with the branch-free masked form (divisors <= 4096:
+  // implied by the shared-memory tables)
+  bool masked_steps = false;
+  for (int t = 0; t < h.ntimes; ++t)
+    masked_steps = masked_steps || meta[t].c == 0.f;
+  const bool bf = h.mode == EN_STDDEV && !a.tables_global && M > 0 && masked_steps && h.undef == h.undef;
+  const size_t smem = a.tables_global ? 0 : (sizeof(float*) + sizeof(float2) + sizeof(int)) * Mp + (bf ? sizeof(float2) : 0);
 
 #define FCB_LAUNCH_ENS(MODE)                                                                                                                         \
   do {                                                                                                                                               \
@@ -372,7 +510,12 @@ int run_ensemble(const EnsHost& h)
     FCB_LAUNCH_ENS(EN_MEAN);
     break;
   case EN_STDDEV:
-    FCB_LAUNCH_ENS(EN_STDDEV);
+    if (bf && vec)
+      ensemble_kernel<EN_STDDEV, 4, false, true><<<(unsigned)grid, EN_THREADS, smem, call.stream()>>>(a);
+    else if (bf)
+      ensemble_kernel<EN_STDDEV, 1, false, true><<<(unsigned)grid, EN_THREADS, smem, call.stream()>>>(a);
+    else
+      FCB_LAUNCH_ENS(EN_STDDEV);
     break;
   case EN_EXTREME:
     FCB_LAUNCH_ENS(EN_EXTREME);

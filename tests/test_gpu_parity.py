@@ -71,7 +71,7 @@ def test_output_may_alias_input(gpu, name, device):
 def test_other_undef_values(gpu):
     arb = _arbiter()
     for undef in (12356789.0, 1e30, 123456.0, -999.0):
-        for name in ("relvort", "alevelhum", "meanValue", "extremeValue", "probability", "fieldOPERfield"):
+        for name in ("relvort", "alevelhum", "meanValue", "stddevValue", "extremeValue", "probability", "fieldOPERfield"):
             case = cases.build(name, 19, 11, seed=11, undef=undef, flag_in=cases.SOME, mask="bernoulli", **matrix.VARIANTS[name][0])
             problems = cases.compare(case, cases.run(gpu, case), cases.run(arb, case), rtol=cases.TRANSCENDENTAL.get(name, 0.0))
             assert not problems, "%s undef=%g: %s" % (name, undef, "\n".join(problems))
@@ -85,6 +85,32 @@ def test_ensemble_member_flags(gpu):
             case = cases.build(name, 23, 9, seed=5, mask="bernoulli", nmembers=len(flags), member_flags=flags, **params)
             problems = cases.compare(case, cases.run(gpu, case), cases.run(arb, case))
             assert not problems, "%s %s: %s" % (name, params, "\n".join(problems))
+
+
+@pytest.mark.parametrize("member_flags", [None, [cases.SOME, cases.ALL, cases.SOME, cases.SOME, cases.ALL, cases.SOME, cases.NONE, cases.SOME, cases.SOME, cases.ALL, cases.SOME, cases.SOME]])
+def test_stddev_with_undefined_members_and_special_values(gpu, member_flags):
+    """stddevValue on members with undefined points runs a branch-free Welford update (ops_ensemble.cu, stddev_points_bf): the
+    quotient delta / n as a corrected product with a table reciprocal, an undefined value replaced by the running mean.  Exact
+    zeros (precipitation), negative zeros, deltas below and above the proven range, infinities and NaNs -- also inside members
+    whose flag claims ALL_DEFINED, which the reference then uses as values -- must give the reference's bits."""
+    arb = _arbiter()
+    rng = np.random.default_rng(77)
+    for nx, ny in ((131, 37), (64, 8), (5, 3)):
+        case = cases.build("stddevValue", nx, ny, seed=9, flag_in=cases.SOME, mask="bernoulli", nmembers=12, member_flags=member_flags)
+        members = case.args[2]
+        for m in members:
+            r = rng.random(m.shape)
+            keep = cases.undefined_mask(m, case.undef)
+            m[(r < 0.35) & ~keep] = 0.0
+            m[(r > 0.35) & (r < 0.37) & ~keep] = -0.0
+            m[(r > 0.37) & (r < 0.38) & ~keep] = 1e-38
+            m[(r > 0.38) & (r < 0.39) & ~keep] = -3e-33
+            m[(r > 0.39) & (r < 0.395) & ~keep] = 4e31
+            m[(r > 0.395) & (r < 0.398) & ~keep] = np.inf
+            m[(r > 0.398) & (r < 0.401) & ~keep] = np.nan
+        for dev in (None, _to_device):
+            problems = cases.compare(case, cases.run(gpu, case, to_device=dev), cases.run(arb, case))
+            assert not problems, "%dx%d %s: %s" % (nx, ny, "device" if dev else "host", "\n".join(problems))
 
 
 @pytest.mark.parametrize("name,grid", [("pleveltemp", (949, 1069)), ("relvort", (949, 1069)), ("divergence", (949, 1069)), ("aleveltemp", (949, 1069)),
