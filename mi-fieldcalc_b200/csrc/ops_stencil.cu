@@ -1251,7 +1251,10 @@ const FieldMeta* flags_to_meta(Call& call, const int* fDefined, int nfields)
 // (the result at column x depends on the input columns x-2 .. x+2); a band of RB rows loads RB+4.
 // The field is read once and written once: 8 B/point.
 constexpr int SH_WARPS = 4;
-constexpr int SH_PF = 4; // rows in flight per thread
+#ifndef FCB_SH_PF
+#define FCB_SH_PF 3
+#endif
+constexpr int SH_PF = FCB_SH_PF; // rows in flight per thread (tools/shape_variants.sh)
 
 template <int W>
 struct ShapiroGeom
@@ -1268,14 +1271,14 @@ struct ShapiroGeom
 // for which rounding through double and rounding once agree, and that single rounding is fmaf(s, T, f).
 // Anything else -- inexact T, NaN, infinities -- takes the double expression.  Half of the passes use
 // each path so that neither the XU pipe nor the issue slots saturate.
-__device__ __forceinline__ float shapiro_point_double(float lo, float f, float hi, double sd)
+// (every form takes S = RN(lo + hi), the float sum the reference forms first)
+__device__ __forceinline__ float shapiro_point_double(float S, float f, double sd)
 {
-  return (float)fma(sd, fma(-2.0, (double)f, (double)(lo + hi)), (double)f);
+  return (float)fma(sd, fma(-2.0, (double)f, (double)S), (double)f);
 }
 // float evaluation; `inexact` is raised when the result must not be used
-__device__ __forceinline__ float shapiro_point_float(float lo, float f, float hi, float sf, bool& inexact)
+__device__ __forceinline__ float shapiro_point_float(float S, float f, float sf, bool& inexact)
 {
-  const float S = lo + hi;
   const float b = f + f;
   const float T = S - b;
   const float a1 = T + b;    // TwoSum(S, -b): a1 ~ S
@@ -1286,70 +1289,80 @@ __device__ __forceinline__ float shapiro_point_float(float lo, float f, float hi
   inexact = inexact || !(err == 0.f);
   return __fmaf_rn(sf, T, f);
 }
-// shapiro_point_float for two adjacent columns at once on the packed FP32 instructions (FADD2 / FFMA2: one issue slot per pair;
-// same IEEE operations -- there is no product followed by an add here for ptxas to contract)
-__device__ __forceinline__ float2 shapiro_pair_float(float2 lo, float2 f, float2 hi, float sf, bool& inexact)
+// The same value with a ONE-comparison exactness test: |T| < |f| (T = RN(S - b), b = 2f) means that the real difference is
+// smaller than |b| / 2 too (rounding is monotone and |f| is a float), so S lies strictly between b/2 and 3b/2 and S - b is
+// exact by Sterbenz' lemma.  True wherever the second difference of the field is smaller than the field itself -- everywhere
+// but next to zeros of the field; a warp with a point that fails (or with a NaN / infinity: every comparison false) repeats the
+// pass with the TwoSum test above, which decides between the float and the double expression.  On the packed FP32 instructions
+// (FADD2 / FFMA2: one issue slot per pair of columns; the same IEEE operations -- there is no product followed by an add here
+// for ptxas to contract): 3 packed + 2 scalar instructions per pair of points after S, against 8 + 2 with the TwoSum test.
+__device__ __forceinline__ float2 shapiro_pair_sterbenz(float2 S, float2 f, float sf, bool& unsure)
 {
-  const float2 S = __fadd2_rn(lo, hi);
   const float2 b = __fadd2_rn(f, f);
-  const float2 nb = make_float2(-b.x, -b.y);
-  const float2 T = __fadd2_rn(S, nb);
-  const float2 a1 = __fadd2_rn(T, b);
-  const float2 b1 = __fadd2_rn(T, make_float2(-a1.x, -a1.y));
-  const float2 da = __fadd2_rn(S, make_float2(-a1.x, -a1.y));
-  const float2 db = __fadd2_rn(nb, make_float2(-b1.x, -b1.y));
-  const float2 err = __fadd2_rn(da, db);
-  inexact = inexact || !(err.x == 0.f) || !(err.y == 0.f);
+  const float2 T = __fadd2_rn(S, make_float2(-b.x, -b.y));
+  unsure = unsure || !(fabsf(T.x) < fabsf(f.x)) || !(fabsf(T.y) < fabsf(f.y));
   return __ffma2_rn(make_float2(sf, sf), T, f);
+}
+__device__ __forceinline__ float shapiro_point_sterbenz(float S, float f, float sf, bool& unsure)
+{
+  const float T = S - (f + f);
+  unsure = unsure || !(fabsf(T) < fabsf(f));
+  return __fmaf_rn(sf, T, f);
 }
 
 template <int W, bool ALL, bool FLOATPATH>
-__device__ __forceinline__ void shapiro_pass(const float (&lo)[W], const float (&f)[W], const float (&hi)[W], float (&r)[W], float s, unsigned wbits)
+__device__ __forceinline__ void shapiro_pass(const float (&S)[W], const float (&f)[W], float (&r)[W], float s, unsigned wbits)
 {
   if (!ALL) {
 #pragma unroll
     for (int j = 0; j < W; ++j) {
       const float w = ((wbits >> j) & 1u) ? 0.25f : 0.f;
-      r[j] = f[j] + w * (lo[j] + hi[j] - 2.f * f[j]);
+      r[j] = f[j] + w * (S[j] - 2.f * f[j]);
     }
   } else if (FLOATPATH) {
-    bool inexact = false;
+    bool unsure = false;
     if constexpr (W == 4) {
 #pragma unroll
       for (int j = 0; j < W; j += 2) {
-        const float2 v = shapiro_pair_float(make_float2(lo[j], lo[j + 1]), make_float2(f[j], f[j + 1]), make_float2(hi[j], hi[j + 1]), s, inexact);
+        const float2 v = shapiro_pair_sterbenz(make_float2(S[j], S[j + 1]), make_float2(f[j], f[j + 1]), s, unsure);
         r[j] = v.x;
         r[j + 1] = v.y;
       }
     } else {
 #pragma unroll
       for (int j = 0; j < W; ++j)
-        r[j] = shapiro_point_float(lo[j], f[j], hi[j], s, inexact);
+        r[j] = shapiro_point_sterbenz(S[j], f[j], s, unsure);
     }
-    if (__any_sync(0xffffffffu, inexact)) { // rare, warp-uniform: a real branch, not a select
+    if (__any_sync(0xffffffffu, unsure)) { // next to a zero of the field (warp-uniform: real branches, not selects)
+      bool inexact = false;
 #pragma unroll
       for (int j = 0; j < W; ++j)
-        r[j] = shapiro_point_double(lo[j], f[j], hi[j], (double)s);
+        r[j] = shapiro_point_float(S[j], f[j], s, inexact);
+      if (__any_sync(0xffffffffu, inexact)) { // rare
+#pragma unroll
+        for (int j = 0; j < W; ++j)
+          r[j] = shapiro_point_double(S[j], f[j], (double)s);
+      }
     }
   } else {
 #pragma unroll
     for (int j = 0; j < W; ++j)
-      r[j] = shapiro_point_double(lo[j], f[j], hi[j], (double)s);
+      r[j] = shapiro_point_double(S[j], f[j], (double)s);
   }
 }
 
 template <int W, bool ALL, bool FLOATPATH, bool ANYCOL = false>
 __device__ __forceinline__ void shapiro_xpass(const float (&f)[W], float (&out)[W], float s, unsigned wbits, unsigned copybits)
 {
-  float lo[W], hi[W], r[W];
-  lo[0] = __shfl_up_sync(0xffffffffu, f[W - 1], 1);
-  hi[W - 1] = __shfl_down_sync(0xffffffffu, f[0], 1);
+  // scalar sums: the neighbour pairs (left, f0), (f1, f2), (f3, right) are not register pairs of the row -- as packed operands
+  // they cost six moves per pass
+  float S[W], r[W];
+  const float left = __shfl_up_sync(0xffffffffu, f[W - 1], 1);
+  const float right = __shfl_down_sync(0xffffffffu, f[0], 1);
 #pragma unroll
-  for (int j = 1; j < W; ++j) {
-    lo[j] = f[j - 1];
-    hi[j - 1] = f[j];
-  }
-  shapiro_pass<W, ALL, FLOATPATH>(lo, f, hi, r, s, wbits);
+  for (int j = 0; j < W; ++j)
+    S[j] = (j == 0 ? left : f[j > 0 ? j - 1 : 0]) + (j == W - 1 ? right : f[j < W - 1 ? j + 1 : 0]);
+  shapiro_pass<W, ALL, FLOATPATH>(S, f, r, s, wbits);
   // columns 0 and nx-1 are copied.  W = 4 with float4 rows: x0 and nx are multiples of 4, so they can only be the lane's
   // first resp. last column (ANYCOL: rows of any alignment, any of the lane's columns)
 #pragma unroll
@@ -1361,13 +1374,25 @@ template <int W, bool ALL, bool FLOATPATH>
 __device__ __forceinline__ void shapiro_ypass(const float (&lo)[W], const float (&f)[W], const float (&hi)[W], float (&out)[W], float s, unsigned wbits,
                                               bool copy)
 {
-  if (copy) { // rows 0 and ny-1 (and rows outside the grid): warp-uniform
+  // rows 0 and ny-1 (and rows outside the grid) are copied: selected afterwards -- as a branch the copy is hoisted above it and
+  // costs every row eight moves
+  float S[W], r[W];
+  if constexpr (W == 4 && ALL) {
+#pragma unroll
+    for (int j = 0; j < W; j += 2) {
+      const float2 v = __fadd2_rn(make_float2(lo[j], lo[j + 1]), make_float2(hi[j], hi[j + 1]));
+      S[j] = v.x;
+      S[j + 1] = v.y;
+    }
+  } else {
 #pragma unroll
     for (int j = 0; j < W; ++j)
-      out[j] = f[j];
-    return;
+      S[j] = lo[j] + hi[j];
   }
-  shapiro_pass<W, ALL, FLOATPATH>(lo, f, hi, out, s, wbits);
+  shapiro_pass<W, ALL, FLOATPATH>(S, f, r, s, wbits);
+#pragma unroll
+  for (int j = 0; j < W; ++j)
+    out[j] = copy ? f[j] : r[j];
 }
 
 // VEC = the lane's W = 4 columns are one float4 (every row on a 16-byte boundary).  W = 4 without VEC: rows of ANY alignment (an odd
@@ -1395,26 +1420,34 @@ __device__ __forceinline__ void shapiro_band(const float* __restrict__ src, floa
       copybits |= 1u << j;
 
   const int rbeg = r0 - 2, rend = r1 + 2; // rows marched: [rbeg, rend), stores lag two rows
-  auto load_row = [&](int r, float (&q)[W]) {
-    if (col_ok && r >= 0 && r < ny && r < rend) {
-      const float* p = src + (long long)r * nx + x0;
-      if (ANYCOL) {
+  // Loads are unconditional: a row outside the grid (or past the band) is read as the nearest row inside, a column outside as
+  // the nearest column inside.  What is computed from such values never reaches a stored point: rows -1 and ny only feed the
+  // y passes of rows 0 and ny-1, columns -1 and nx only the x passes of columns 0 and nx-1, and those are copies; the masked
+  // branch takes its definedness bits from the row / column numbers as before.  (Zero fill under a predicate had cost every
+  // row a register copy of the loaded values.)
+  const int rlast = min(ny, rend) - 1;
+  int xc[ANYCOL ? W : 1];
+  if (ANYCOL) {
 #pragma unroll
-        for (int j = 0; j < W; ++j)
-          q[j] = ((okbits >> j) & 1u) ? p[j] : 0.f;
-      } else if (W == 4) {
-        const float4 t = *reinterpret_cast<const float4*>(p);
-        q[0] = t.x;
-        q[W > 1 ? 1 : 0] = t.y;
-        q[W > 2 ? 2 : 0] = t.z;
-        q[W > 3 ? 3 : 0] = t.w;
-      } else {
-        q[0] = *p;
-      }
-    } else {
+    for (int j = 0; j < W; ++j)
+      xc[ANYCOL ? j : 0] = min(max(x0 + j, 0), nx - 1);
+  } else {
+    xc[0] = min(max(x0, 0), nx - W);
+  }
+  auto load_row = [&](int r, float (&q)[W]) {
+    const float* p = src + (long long)min(max(r, 0), rlast) * nx;
+    if (ANYCOL) {
 #pragma unroll
       for (int j = 0; j < W; ++j)
-        q[j] = 0.f;
+        q[j] = p[xc[ANYCOL ? j : 0]];
+    } else if (W == 4) {
+      const float4 t = *reinterpret_cast<const float4*>(p + xc[0]);
+      q[0] = t.x;
+      q[W > 1 ? 1 : 0] = t.y;
+      q[W > 2 ? 2 : 0] = t.z;
+      q[W > 3 ? 3 : 0] = t.w;
+    } else {
+      q[0] = p[xc[0]];
     }
   };
 
