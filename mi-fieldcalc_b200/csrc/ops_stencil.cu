@@ -1251,6 +1251,12 @@ const FieldMeta* flags_to_meta(Call& call, const int* fDefined, int nfields)
 // (the result at column x depends on the input columns x-2 .. x+2); a band of RB rows loads RB+4.
 // The field is read once and written once: 8 B/point.
 constexpr int SH_WARPS = 4;
+#ifndef FCB_SH_ANYCOL_CTAS
+#define FCB_SH_ANYCOL_CTAS 5
+#endif
+#ifndef FCB_SH_ANYCOL_ALL_CTAS
+#define FCB_SH_ANYCOL_ALL_CTAS 6
+#endif
 #ifndef FCB_SH_PF
 #define FCB_SH_PF 3
 #endif
@@ -1314,10 +1320,27 @@ template <int W, bool ALL, bool FLOATPATH>
 __device__ __forceinline__ void shapiro_pass(const float (&S)[W], const float (&f)[W], float (&r)[W], float s, unsigned wbits)
 {
   if (!ALL) {
+    // f + w * (S - 2.f * f) in float, w = 0.25 or 0 (FC.cc:2136-2168).  2.f * f = f + f, and w * T is exact (a power of two or
+    // zero; NaN for 0 * inf either way), so the sum is the single rounding fmaf(w, T, f) -- three packed instructions per pair
+    // of points instead of two multiplications and three additions per point.  (Only a |T| below 2^-124 next to an f of that
+    // size could tell the difference: 0.25 * T then rounds in the subnormal range before the addition.)
+    if constexpr (W == 4) {
 #pragma unroll
-    for (int j = 0; j < W; ++j) {
-      const float w = ((wbits >> j) & 1u) ? 0.25f : 0.f;
-      r[j] = f[j] + w * (S[j] - 2.f * f[j]);
+      for (int j = 0; j < W; j += 2) {
+        const float2 ff = make_float2(f[j], f[j + 1]);
+        const float2 w = make_float2(((wbits >> j) & 1u) ? 0.25f : 0.f, ((wbits >> (j + 1)) & 1u) ? 0.25f : 0.f);
+        const float2 b = __fadd2_rn(ff, ff);
+        const float2 T = __fadd2_rn(make_float2(S[j], S[j + 1]), make_float2(-b.x, -b.y));
+        const float2 v = __ffma2_rn(w, T, ff);
+        r[j] = v.x;
+        r[j + 1] = v.y;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < W; ++j) {
+        const float w = ((wbits >> j) & 1u) ? 0.25f : 0.f;
+        r[j] = __fmaf_rn(w, S[j] - (f[j] + f[j]), f[j]);
+      }
     }
   } else if (FLOATPATH) {
     bool unsure = false;
@@ -1377,7 +1400,7 @@ __device__ __forceinline__ void shapiro_ypass(const float (&lo)[W], const float 
   // rows 0 and ny-1 (and rows outside the grid) are copied: selected afterwards -- as a branch the copy is hoisted above it and
   // costs every row eight moves
   float S[W], r[W];
-  if constexpr (W == 4 && ALL) {
+  if constexpr (W == 4) {
 #pragma unroll
     for (int j = 0; j < W; j += 2) {
       const float2 v = __fadd2_rn(make_float2(lo[j], lo[j + 1]), make_float2(hi[j], hi[j + 1]));
@@ -1451,83 +1474,88 @@ __device__ __forceinline__ void shapiro_band(const float* __restrict__ src, floa
     }
   };
 
-  float q[SH_PF][W];
+  // The march is unrolled over 2 * SH_PF = 6 rows with everything that rotates in statically indexed slots: two row buffers
+  // that alternate between "being loaded" and "being consumed", and the three-row windows of the two iterations (a, c), the
+  // definedness words and the weights of the previous rows in slots numbered by the row's position in the body (6 is a
+  // multiple of every period), so that no value is ever moved from one register to another to change its role.
+  static_assert((2 * SH_PF) % 3 == 0 && (2 * SH_PF) % 2 == 0, "the unrolled body must close the three-row rotation");
+  float qa[SH_PF][W], qb[SH_PF][W];
 #pragma unroll
   for (int k = 0; k < SH_PF; ++k)
-    load_row(rbeg + k, q[k]);
+    load_row(rbeg + k, qa[k]);
 
-  float a0[W] = {}, a1[W] = {}, c0[W] = {}, c1[W] = {};
-  unsigned d0 = 0, d1 = 0;       // definedness bits of the original rows r-2, r-1
-  unsigned mx_prev = 0;          // x weights of row r-1
-  unsigned my_prev = 0;          // y weights of row r-2
+  float a[3][W] = {}, c[3][W] = {};
+  unsigned dd[3] = {0, 0, 0};  // definedness bits of the original rows (slot = position % 3)
+  unsigned mxs[2] = {0, 0};    // x weights (slot = position % 2): this row's and the previous row's
+  unsigned mys[2] = {0, 0};    // y weights
 
-  for (int rb = rbeg; rb < rend; rb += SH_PF) {
-    float cur[SH_PF][W];
+  // position k of the body (a compile-time number after unrolling), row r, loaded values f
+  auto do_row = [&](const int k, const int r, const float (&f)[W]) {
+    const int s2 = k % 3, s1 = (k + 2) % 3, s0 = (k + 1) % 3; // slots of rows r, r-1, r-2
+    const int t1 = k % 2, t0 = (k + 1) % 2;
+    if (!ALL) {
+      unsigned d2 = 0;
+      if (r >= 0 && r < ny) {
+#pragma unroll
+        for (int j = 0; j < W; ++j)
+          if (is_def(f[j], undef))
+            d2 |= 1u << j;
+      }
+      const unsigned dl = (__shfl_up_sync(0xffffffffu, d2, 1) >> (W - 1)) & 1u;
+      const unsigned dr = __shfl_down_sync(0xffffffffu, d2, 1) & 1u;
+      const unsigned ext = dl | (d2 << 1) | (dr << (W + 1));
+      dd[s2] = d2;
+      mxs[t1] = ext & (ext >> 1) & (ext >> 2);
+      mys[t1] = dd[s0] & dd[s1] & d2;
+    }
+    // iteration 1: x pass on row r, y pass on row r-1
+    float b[W], d[W];
+    shapiro_xpass<W, ALL, true, ANYCOL>(f, a[s2], 0.25f, mxs[t1], copybits);
+    shapiro_ypass<W, ALL, true>(a[s0], a[s1], a[s2], b, 0.25f, mys[t1], r - 1 <= 0 || r - 1 >= ny - 1);
+    // iteration 2: x pass on row r-1, y pass on row r-2
+    shapiro_xpass<W, ALL, true, ANYCOL>(b, c[s2], -0.25f, mxs[t0], copybits);
+    shapiro_ypass<W, ALL, W == 4>(c[s0], c[s1], c[s2], d, -0.25f, mys[t0], r - 2 <= 0 || r - 2 >= ny - 1); // (W = 4: the packed float form for all four passes)
+    const int ro = r - 2;
+    if (store_lane && ro >= r0 && ro < r1) {
+      float* p = dst + (long long)ro * nx + x0;
+      if (ANYCOL) {
+#pragma unroll
+        for (int j = 0; j < W; ++j)
+          if ((okbits >> j) & 1u)
+            p[j] = d[j];
+      } else if (W == 4)
+        *reinterpret_cast<float4*>(p) = make_float4(d[0], d[W > 1 ? 1 : 0], d[W > 2 ? 2 : 0], d[W > 3 ? 3 : 0]);
+      else
+        *p = d[0];
+    }
+  };
+
+  for (int rb = rbeg; rb < rend; rb += 2 * SH_PF) {
 #pragma unroll
     for (int k = 0; k < SH_PF; ++k)
-#pragma unroll
-      for (int j = 0; j < W; ++j)
-        cur[k][j] = q[k][j];
-#pragma unroll
-    for (int k = 0; k < SH_PF; ++k)
-      load_row(rb + SH_PF + k, q[k]);
+      load_row(rb + SH_PF + k, qb[k]);
 #pragma unroll
     for (int k = 0; k < SH_PF; ++k) {
-      const int r = rb + k;
-      if (r >= rend)
-        break;
-      const float(&f)[W] = cur[k];
-      unsigned d2 = 0, mx = 0, my = 0;
-      if (!ALL) {
-        if (r >= 0 && r < ny) {
+      if (rb + k >= rend)
+        return;
+      do_row(k, rb + k, qa[k]);
+    }
 #pragma unroll
-          for (int j = 0; j < W; ++j)
-            if (is_def(f[j], undef))
-              d2 |= 1u << j;
-        }
-        const unsigned dl = (__shfl_up_sync(0xffffffffu, d2, 1) >> (W - 1)) & 1u;
-        const unsigned dr = __shfl_down_sync(0xffffffffu, d2, 1) & 1u;
-        const unsigned ext = dl | (d2 << 1) | (dr << (W + 1));
-        mx = ext & (ext >> 1) & (ext >> 2);
-        my = d0 & d1 & d2;
-      }
-      // iteration 1: x pass on row r, y pass on row r-1
-      float a2[W], b[W], c2[W], d[W];
-      shapiro_xpass<W, ALL, true, ANYCOL>(f, a2, 0.25f, mx, copybits);
-      shapiro_ypass<W, ALL, true>(a0, a1, a2, b, 0.25f, my, r - 1 <= 0 || r - 1 >= ny - 1);
-      // iteration 2: x pass on row r-1, y pass on row r-2
-      shapiro_xpass<W, ALL, true, ANYCOL>(b, c2, -0.25f, mx_prev, copybits);
-      shapiro_ypass<W, ALL, W == 4>(c0, c1, c2, d, -0.25f, my_prev, r - 2 <= 0 || r - 2 >= ny - 1); // (W = 4: the packed float form for all four passes)
-      const int ro = r - 2;
-      if (store_lane && ro >= r0 && ro < r1) {
-        float* p = dst + (long long)ro * nx + x0;
-        if (ANYCOL) {
+    for (int k = 0; k < SH_PF; ++k)
+      load_row(rb + 2 * SH_PF + k, qa[k]);
 #pragma unroll
-          for (int j = 0; j < W; ++j)
-            if ((okbits >> j) & 1u)
-              p[j] = d[j];
-        } else if (W == 4)
-          *reinterpret_cast<float4*>(p) = make_float4(d[0], d[W > 1 ? 1 : 0], d[W > 2 ? 2 : 0], d[W > 3 ? 3 : 0]);
-        else
-          *p = d[0];
-      }
-#pragma unroll
-      for (int j = 0; j < W; ++j) {
-        a0[j] = a1[j];
-        a1[j] = a2[j];
-        c0[j] = c1[j];
-        c1[j] = c2[j];
-      }
-      d0 = d1;
-      d1 = d2;
-      mx_prev = mx;
-      my_prev = my;
+    for (int k = 0; k < SH_PF; ++k) {
+      if (rb + SH_PF + k >= rend)
+        return;
+      do_row(SH_PF + k, rb + SH_PF + k, qb[k]);
     }
   }
 }
 
-template <int W, bool VEC = (W == 4)>
-__global__ void __launch_bounds__(SH_WARPS * 32) shapiro2_kernel(const float* __restrict__ fin, float* __restrict__ fout, int nx, int ny, int strips,
+// ONLY_ALL: every field of the batch is flagged all-defined (known on the host) -- the kernel then holds the all-defined march
+// alone and gets its register budget
+template <int W, bool VEC = (W == 4), bool ONLY_ALL = false>
+__device__ __forceinline__ void shapiro2_body(const float* __restrict__ fin, float* __restrict__ fout, int nx, int ny, int strips,
                                                                 int bands, int rows_per_band, const FieldMeta* meta, float undef)
 {
   constexpr int HL = ShapiroGeom<W>::HL;
@@ -1546,10 +1574,30 @@ __global__ void __launch_bounds__(SH_WARPS * 32) shapiro2_kernel(const float* __
   const int r1 = min(r0 + rows_per_band, ny);
   const float* src = fin + (long long)field * nx * ny;
   float* dst = fout + (long long)field * nx * ny;
-  if (meta[field].all != 0)
+  if (ONLY_ALL || meta[field].all != 0)
     shapiro_band<W, true, VEC>(src, dst, nx, ny, x0, r0, r1, undef);
   else
     shapiro_band<W, false, VEC>(src, dst, nx, ny, x0, r0, r1, undef);
+}
+
+template <int W, bool ONLY_ALL>
+__global__ void __launch_bounds__(SH_WARPS * 32) shapiro2_kernel(const float* __restrict__ fin, float* __restrict__ fout, int nx, int ny, int strips, int bands,
+                                                                int rows_per_band, const FieldMeta* meta, float undef)
+{
+  shapiro2_body<W, W == 4, ONLY_ALL>(fin, fout, nx, ny, strips, bands, rows_per_band, meta, undef);
+}
+// rows of any alignment: their own register budgets (four separate loads and stores per row keep more addresses alive)
+__global__ void __launch_bounds__(SH_WARPS * 32, FCB_SH_ANYCOL_CTAS) shapiro2_kernel_anycol(const float* __restrict__ fin, float* __restrict__ fout, int nx, int ny,
+                                                                                           int strips, int bands, int rows_per_band, const FieldMeta* meta,
+                                                                                           float undef)
+{
+  shapiro2_body<4, false, false>(fin, fout, nx, ny, strips, bands, rows_per_band, meta, undef);
+}
+__global__ void __launch_bounds__(SH_WARPS * 32, FCB_SH_ANYCOL_ALL_CTAS) shapiro2_kernel_anycol_all(const float* __restrict__ fin, float* __restrict__ fout, int nx,
+                                                                                                   int ny, int strips, int bands, int rows_per_band,
+                                                                                                   const FieldMeta* meta, float undef)
+{
+  shapiro2_body<4, false, true>(fin, fout, nx, ny, strips, bands, rows_per_band, meta, undef);
 }
 
 } // namespace
@@ -1968,12 +2016,21 @@ int fcb200_shapiro2_filter_batched(int nx, int ny, int nfields, float* field, fl
     set_error("fcb200: batch too large for one launch (%lld CTAs)", grid);
     return -1;
   }
-  if (vec)
-    shapiro2_kernel<4><<<(unsigned)grid, SH_WARPS * 32, 0, call.stream()>>>(d_in, d_tmp, nx, ny, strips, bands, rows_per_band, meta, undef);
+  bool only_all = true; // every field flagged all-defined: the kernels that hold the all-defined march alone
+  for (int k = 0; k < nfields; ++k)
+    only_all = only_all && fDefined[k] == ALL_DEFINED;
+#define FCB_SHAPIRO_LAUNCH(K) K<<<(unsigned)grid, SH_WARPS * 32, 0, call.stream()>>>(d_in, d_tmp, nx, ny, strips, bands, rows_per_band, meta, undef)
+  if (vec && only_all)
+    FCB_SHAPIRO_LAUNCH((shapiro2_kernel<4, true>));
+  else if (vec)
+    FCB_SHAPIRO_LAUNCH((shapiro2_kernel<4, false>));
+  else if (!w1 && only_all)
+    FCB_SHAPIRO_LAUNCH(shapiro2_kernel_anycol_all);
   else if (!w1)
-    shapiro2_kernel<4, false><<<(unsigned)grid, SH_WARPS * 32, 0, call.stream()>>>(d_in, d_tmp, nx, ny, strips, bands, rows_per_band, meta, undef);
+    FCB_SHAPIRO_LAUNCH(shapiro2_kernel_anycol);
   else
-    shapiro2_kernel<1><<<(unsigned)grid, SH_WARPS * 32, 0, call.stream()>>>(d_in, d_tmp, nx, ny, strips, bands, rows_per_band, meta, undef);
+    FCB_SHAPIRO_LAUNCH((shapiro2_kernel<1, false>));
+#undef FCB_SHAPIRO_LAUNCH
   count_launch();
   if (aliased) {
     if (!cuda_ok(cudaMemcpyAsync(d_out, d_tmp, sizeof(float) * n * nfields, cudaMemcpyDeviceToDevice, call.stream()), "cudaMemcpyAsync(D2D)"))

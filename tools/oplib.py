@@ -170,6 +170,7 @@ def extra_rows():
         Row("ilevelgwind", "8a", "ilevelgwind_batched", MEPS, 64, 12, ["nx", "ny", "nf", ("F", "z"), ("G", "xm"), ("G", "ym"), ("G", "fc"), "OUT", "OUT", "FLAGS", "UNDEF"]),
         Row("advection_meps", "8a", "advection_batched", MEPS, 48, 16, _stencil(3, extra=(1.0,))),
         Row("thermalFrontParameter_meps", "8a", "thermalFrontParameter_batched", MEPS, 96, 8, _stencil(1)),
+        Row("shapiro2_filter_meps", "8a", "shapiro2_filter_batched", MEPS, 96, 8, ["nx", "ny", "nf", ("F", "tens"), "OUT", "FLAGS", "UNDEF"]),
         Row("pleveltemp_c4", "8a", "pleveltemp_batched", MEPS, 128, 8, ["nx", "ny", "nf", ("F", "t"), ("SV", np.full(128, 500.0, np.float32)), ("S", "kelvin"), ("S", 4), "OUT", "FLAGS", "UNDEF"]),
         Row("plevelhum_c1", "8a", "plevelhum_batched", MEPS, 96, 12, ["nx", "ny", "nf", ("F", "t"), ("F", "q"), ("SV", np.full(96, 850.0, np.float32)), ("S", "celsius"), ("S", 1), "OUT", "FLAGS", "UNDEF"]),
         Row("plevelhum_c7", "8a", "plevelhum_batched", MEPS, 96, 12, ["nx", "ny", "nf", ("F", "t"), ("F", "q"), ("SV", np.full(96, 850.0, np.float32)), ("S", "celsius"), ("S", 7), "OUT", "FLAGS", "UNDEF"]),
