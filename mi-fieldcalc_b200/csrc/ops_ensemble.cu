@@ -21,6 +21,10 @@ namespace {
 using dev::is_def;
 
 constexpr int EN_THREADS = 256;
+#ifndef FCB_EN_AHEAD
+#define FCB_EN_AHEAD 3
+#endif
+constexpr int EN_AHEAD = FCB_EN_AHEAD; // members in flight per thread in the load-ahead kernels
 enum { EN_MEAN = 0, EN_STDDEV = 1, EN_EXTREME = 2, EN_PROB = 3 };
 enum { MF_ALL = 1, MF_NOT_NONE = 2 }; // per (time, member) flag bits
 
@@ -52,7 +56,10 @@ struct EnsArgs
 // quotient of a 24-bit float by an integer n <= 4096 that is not itself a float is at least 2^-36 away
 // (relative) from every rounding boundary, and cannot be an exact tie (n*midpoint has >= 25 significant
 // bits).  Zero, tiny, huge and non-finite deltas take the IEEE division.
-template <int MODE, int W, bool FAST>
+// AHEAD > 0 (kernels launched for batches with undefined points, tables in shared memory): the member loads run AHEAD
+// members in front of their use as volatile loads.  The per-point tests split the plain loop into basic blocks and the compiler
+// then keeps ONE load in flight per warp (ncu: 8 warps per issue waiting on it).
+template <int MODE, int W, bool FAST, int AHEAD = 0>
 __device__ __forceinline__ void ensemble_points(const EnsArgs& a, const float* const* mptr, const int* mflag, const float2* recip, int time,
                                                 long long base, float* out, bool in_all, unsigned& nundef, long long moff = 0)
 {
@@ -69,27 +76,38 @@ __device__ __forceinline__ void ensemble_points(const EnsArgs& a, const float* c
   const bool want_max = (a.compute == 1 || a.compute == 3);
   float dmax = 1.f, dmin = 1.f; // range of |delta| seen by the reciprocal-based Welford update
 
-#pragma unroll 6
-  for (int j = 0; j < M; ++j) {
+  struct Pts
+  {
+    float v[W];
+  };
+  auto load = [&](int j) {
+    Pts p;
+    if constexpr (AHEAD > 0) {
+      if constexpr (W == 4)
+        asm volatile("ld.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(p.v[0]), "=f"(p.v[1]), "=f"(p.v[2]), "=f"(p.v[3]) : "l"(mptr[j] + moff + base));
+      else
+        asm volatile("ld.global.f32 %0, [%1];" : "=f"(p.v[0]) : "l"(mptr[j] + moff + base));
+    } else if constexpr (W == 4) {
+      const float4 q = *reinterpret_cast<const float4*>(mptr[j] + moff + base);
+      p.v[0] = q.x;
+      p.v[1] = q.y;
+      p.v[2] = q.z;
+      p.v[3] = q.w;
+    } else {
+      p.v[0] = mptr[j][moff + base];
+    }
+    return p;
+  };
+  auto member = [&](const int j, const Pts& x) {
     const int fl = FAST ? (MF_ALL | MF_NOT_NONE) : mflag[j];
     if (MODE == EN_PROB && !(fl & MF_NOT_NONE))
-      continue; // a member whose FIELD flag is NONE_DEFINED is not counted (FC.cc:2841)
+      return; // a member whose FIELD flag is NONE_DEFINED is not counted (FC.cc:2841)
     float2 ny = make_float2(0.f, 0.f);
     if (MODE == EN_STDDEV && FAST)
       ny = recip[j];
-    float x[W];
-    if constexpr (W == 4) {
-      const float4 q = *reinterpret_cast<const float4*>(mptr[j] + moff + base);
-      x[0] = q.x;
-      x[1] = q.y;
-      x[2] = q.z;
-      x[3] = q.w;
-    } else {
-      x[0] = mptr[j][moff + base];
-    }
 #pragma unroll
     for (int w = 0; w < W; ++w) {
-      const float xv = x[w];
+      const float xv = x.v[w];
       if (MODE == EN_MEAN) { // FC.cc:2709-2714
         if ((fl & MF_ALL) || is_def(xv, undef)) {
           cnt[w] += 1;
@@ -120,6 +138,31 @@ __device__ __forceinline__ void ensemble_points(const EnsArgs& a, const float* c
           acc0[w] += 1.f;
       }
     }
+  };
+
+  if constexpr (AHEAD > 0) {
+    Pts buf[AHEAD > 0 ? AHEAD : 1];
+#pragma unroll
+    for (int d = 0; d < AHEAD; ++d)
+      buf[d] = load(min(d, M - 1));
+    int j = 0;
+#pragma unroll 2
+    for (; j + AHEAD <= M; j += AHEAD) {
+#pragma unroll
+      for (int d = 0; d < AHEAD; ++d) {
+        const Pts x = buf[d];
+        buf[d] = load(min(j + d + AHEAD, M - 1));
+        member(j + d, x);
+      }
+    }
+#pragma unroll
+    for (int d = 0; d < AHEAD - 1; ++d)
+      if (j + d < M)
+        member(j + d, buf[d]);
+  } else {
+#pragma unroll 6
+    for (int j = 0; j < M; ++j)
+      member(j, load(j));
   }
 
   if (MODE == EN_STDDEV && FAST && !(dmin >= 1e-30f && dmax <= 1e30f)) {
@@ -300,9 +343,11 @@ __device__ __forceinline__ bool stddev_points_bf(const EnsArgs& a, const float* 
 // member load cost stddevValue a fifth of its throughput: 0.82 -> 0.64 of the roofline).
 // BF (stddevValue, tables in shared memory) = time steps with undefined points take stddev_points_bf.  Its own instantiation,
 // launched only when some time step of the batch is not all-defined: the all-defined kernel keeps its registers.
-template <int MODE, int W, bool TG, bool BF = false>
+// AH (the other three reductions, tables in shared memory) = time steps with undefined points load AH members ahead; launched like BF.
+template <int MODE, int W, bool TG, bool BF = false, int AH = 0>
 __global__ void __launch_bounds__(EN_THREADS) ensemble_kernel(const EnsArgs a)
 {
+  static_assert(AH == 0 || (!TG && !BF), "load-ahead form: shared-memory tables, not stddevValue");
   static_assert(!BF || (MODE == EN_STDDEV && !TG), "the branch-free masked form exists for stddevValue with shared-memory tables");
   extern __shared__ unsigned char smem_raw[];
   const int time = blockIdx.x / a.chunks;
@@ -341,7 +386,7 @@ __global__ void __launch_bounds__(EN_THREADS) ensemble_kernel(const EnsArgs a)
     if (fast)
       ensemble_points<MODE, W, true>(a, mptr, mflag, recip, time, head + g * W, out, in_all, nundef, moff);
     else if (!BF || !stddev_points_bf<W>(a, mptr, mflag, s_recip, head + g * W, out, nundef))
-      ensemble_points<MODE, W, false>(a, mptr, mflag, recip, time, head + g * W, out, in_all, nundef, moff);
+      ensemble_points<MODE, W, false, AH>(a, mptr, mflag, recip, time, head + g * W, out, in_all, nundef, moff);
   }
 
   if (W == 4 && chunk == 0) {
@@ -493,6 +538,8 @@ int run_ensemble(const EnsHost& h)
   const bool bf = h.mode == EN_STDDEV && !a.tables_global && M > 0 && masked_steps && h.undef == h.undef;
   const size_t smem = a.tables_global ? 0 : (sizeof(float*) + sizeof(float2) + sizeof(int)) * Mp + (bf ? sizeof(float2) : 0);
 
+  // batches with undefined points (some time step not all-defined): the kernels whose member loads run ahead of their use
+  const bool ahead = h.mode != EN_STDDEV && !a.tables_global && M > 0 && masked_steps;
 #define FCB_LAUNCH_ENS(MODE)                                                                                                                         \
   do {                                                                                                                                               \
     if (a.tables_global) {                                                                                                                           \
@@ -500,6 +547,11 @@ int run_ensemble(const EnsHost& h)
         ensemble_kernel<MODE, 4, true><<<(unsigned)grid, EN_THREADS, smem, call.stream()>>>(a);                                                     \
       else                                                                                                                                           \
         ensemble_kernel<MODE, 1, true><<<(unsigned)grid, EN_THREADS, smem, call.stream()>>>(a);                                                     \
+    } else if (ahead && MODE != EN_STDDEV) {                                                                                                         \
+      if (vec)                                                                                                                                       \
+        ensemble_kernel<MODE, 4, false, false, (MODE != EN_STDDEV ? EN_AHEAD : 0)><<<(unsigned)grid, EN_THREADS, smem, call.stream()>>>(a);         \
+      else                                                                                                                                           \
+        ensemble_kernel<MODE, 1, false, false, (MODE != EN_STDDEV ? EN_AHEAD : 0)><<<(unsigned)grid, EN_THREADS, smem, call.stream()>>>(a);         \
     } else if (vec)                                                                                                                                  \
       ensemble_kernel<MODE, 4, false><<<(unsigned)grid, EN_THREADS, smem, call.stream()>>>(a);                                                      \
     else                                                                                                                                             \
