@@ -384,7 +384,7 @@ __global__ void __launch_bounds__(EN_THREADS) ensemble_kernel(const EnsArgs a)
   const long long g = (long long)chunk * EN_THREADS + threadIdx.x;
   if (g < groups) {
     if (fast)
-      ensemble_points<MODE, W, true>(a, mptr, mflag, recip, time, head + g * W, out, in_all, nundef, moff);
+      ensemble_points<MODE, W, true, AH>(a, mptr, mflag, recip, time, head + g * W, out, in_all, nundef, moff);
     else if (!BF || !stddev_points_bf<W>(a, mptr, mflag, s_recip, head + g * W, out, nundef))
       ensemble_points<MODE, W, false, AH>(a, mptr, mflag, recip, time, head + g * W, out, in_all, nundef, moff);
   }
@@ -538,8 +538,11 @@ int run_ensemble(const EnsHost& h)
   const bool bf = h.mode == EN_STDDEV && !a.tables_global && M > 0 && masked_steps && h.undef == h.undef;
   const size_t smem = a.tables_global ? 0 : (sizeof(float*) + sizeof(float2) + sizeof(int)) * Mp + (bf ? sizeof(float2) : 0);
 
-  // batches with undefined points (some time step not all-defined): the kernels whose member loads run ahead of their use
-  const bool ahead = h.mode != EN_STDDEV && !a.tables_global && M > 0 && masked_steps;
+  // the kernels whose member loads run ahead of their use: batches with undefined points (some time step not all-defined), and
+  // two of the reductions always
+  // (all-defined batches, measured: extremeValue 0.86 -> 0.91 and meanValue 0.93 -> 0.94 of the roofline with the loads ahead,
+  // stddevValue unchanged, probability 0.90 -> 0.88)
+  const bool ahead = !a.tables_global && M > 0 && ((h.mode != EN_STDDEV && masked_steps) || h.mode == EN_EXTREME || h.mode == EN_MEAN);
 #define FCB_LAUNCH_ENS(MODE)                                                                                                                         \
   do {                                                                                                                                               \
     if (a.tables_global) {                                                                                                                           \
@@ -547,11 +550,11 @@ int run_ensemble(const EnsHost& h)
         ensemble_kernel<MODE, 4, true><<<(unsigned)grid, EN_THREADS, smem, call.stream()>>>(a);                                                     \
       else                                                                                                                                           \
         ensemble_kernel<MODE, 1, true><<<(unsigned)grid, EN_THREADS, smem, call.stream()>>>(a);                                                     \
-    } else if (ahead && MODE != EN_STDDEV) {                                                                                                         \
+    } else if (ahead) {                                                                                                                              \
       if (vec)                                                                                                                                       \
-        ensemble_kernel<MODE, 4, false, false, (MODE != EN_STDDEV ? EN_AHEAD : 0)><<<(unsigned)grid, EN_THREADS, smem, call.stream()>>>(a);         \
+        ensemble_kernel<MODE, 4, false, false, EN_AHEAD>                            <<<(unsigned)grid, EN_THREADS, smem, call.stream()>>>(a);         \
       else                                                                                                                                           \
-        ensemble_kernel<MODE, 1, false, false, (MODE != EN_STDDEV ? EN_AHEAD : 0)><<<(unsigned)grid, EN_THREADS, smem, call.stream()>>>(a);         \
+        ensemble_kernel<MODE, 1, false, false, EN_AHEAD>                            <<<(unsigned)grid, EN_THREADS, smem, call.stream()>>>(a);         \
     } else if (vec)                                                                                                                                  \
       ensemble_kernel<MODE, 4, false><<<(unsigned)grid, EN_THREADS, smem, call.stream()>>>(a);                                                      \
     else                                                                                                                                             \
