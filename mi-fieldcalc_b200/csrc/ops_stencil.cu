@@ -1251,6 +1251,9 @@ const FieldMeta* flags_to_meta(Call& call, const int* fDefined, int nfields)
 // (the result at column x depends on the input columns x-2 .. x+2); a band of RB rows loads RB+4.
 // The field is read once and written once: 8 B/point.
 constexpr int SH_WARPS = 4;
+#ifndef FCB_SH_VEC_ALL_CTAS
+#define FCB_SH_VEC_ALL_CTAS 8
+#endif
 #ifndef FCB_SH_ANYCOL_CTAS
 #define FCB_SH_ANYCOL_CTAS 5
 #endif
@@ -1585,6 +1588,14 @@ __global__ void __launch_bounds__(SH_WARPS * 32) shapiro2_kernel(const float* __
                                                                 int rows_per_band, const FieldMeta* meta, float undef)
 {
   shapiro2_body<W, W == 4, ONLY_ALL>(fin, fout, nx, ny, strips, bands, rows_per_band, meta, undef);
+}
+// float4 rows, every field all-defined: 8 CTAs per SM at 64 registers (ECMWF x 32: 0.78 -> 0.82 of the roofline against the
+// 66 registers / 7 CTAs the compiler picks on its own)
+__global__ void __launch_bounds__(SH_WARPS * 32, FCB_SH_VEC_ALL_CTAS) shapiro2_kernel_vec_all(const float* __restrict__ fin, float* __restrict__ fout, int nx, int ny,
+                                                                                             int strips, int bands, int rows_per_band, const FieldMeta* meta,
+                                                                                             float undef)
+{
+  shapiro2_body<4, true, true>(fin, fout, nx, ny, strips, bands, rows_per_band, meta, undef);
 }
 // rows of any alignment: their own register budgets (four separate loads and stores per row keep more addresses alive)
 __global__ void __launch_bounds__(SH_WARPS * 32, FCB_SH_ANYCOL_CTAS) shapiro2_kernel_anycol(const float* __restrict__ fin, float* __restrict__ fout, int nx, int ny,
@@ -2021,7 +2032,7 @@ int fcb200_shapiro2_filter_batched(int nx, int ny, int nfields, float* field, fl
     only_all = only_all && fDefined[k] == ALL_DEFINED;
 #define FCB_SHAPIRO_LAUNCH(K) K<<<(unsigned)grid, SH_WARPS * 32, 0, call.stream()>>>(d_in, d_tmp, nx, ny, strips, bands, rows_per_band, meta, undef)
   if (vec && only_all)
-    FCB_SHAPIRO_LAUNCH((shapiro2_kernel<4, true>));
+    FCB_SHAPIRO_LAUNCH(shapiro2_kernel_vec_all);
   else if (vec)
     FCB_SHAPIRO_LAUNCH((shapiro2_kernel<4, false>));
   else if (!w1 && only_all)
