@@ -165,6 +165,7 @@ __device__ __forceinline__ float half_map_diff_f(float mapr, float hi, float lo)
 template <int MODE>
 struct VortDivOp
 {
+  static constexpr bool ASM_STORE = true; // (stencil_tile.cuh, tile_compute)
   static constexpr int NOUT = 1;
   static constexpr bool TESTS_WHEN_ALL = false;
   const float *u, *v, *xm, *ym, *fc;
@@ -443,6 +444,7 @@ struct GradientOp
 // jacobian (FC.cc:2424-2460): four derivatives rounded to float, a*b - c*d in float without FMA
 struct JacobianOp
 {
+  static constexpr bool ASM_STORE = true; // (stencil_tile.cuh, tile_compute)
   static constexpr int NOUT = 1;
   static constexpr bool TESTS_WHEN_ALL = false;
   const float *f1, *f2, *xm, *ym;
