@@ -1246,7 +1246,7 @@ const FieldMeta* flags_to_meta(Call& call, const int* fDefined, int nfields)
 //   +0.25 (the `s = -0.25` update is dead, FC.cc:2136-2168), all-float arithmetic.
 //
 // All four passes run in REGISTERS: a thread owns W adjacent columns (W = 4: one float4 per row when
-// every row is 16-byte aligned; W = 1 otherwise) and marches down a band of rows.  x passes take their
+// every row is 16-byte aligned, four 4-byte accesses otherwise; W = 1 is kept for comparison) and marches down a band of rows.  x passes take their
 // neighbour columns from the adjacent lanes by warp shuffle; y passes use a three-row window of the
 // previous pass kept in registers (the pipeline lags two rows behind the load).  A warp strip of 32*W
 // loaded columns yields (32 - 2*HL)*W final columns: the HL outermost lanes on each side are halo
@@ -1280,8 +1280,8 @@ struct ShapiroGeom
 // roofline.  FLOATPATH evaluates the same value in float: T = S - 2f (S = lo + hi) is checked for
 // exactness with Knuth's TwoSum; if it is exact (smooth data: always), f + s*T is a sum of two floats,
 // for which rounding through double and rounding once agree, and that single rounding is fmaf(s, T, f).
-// Anything else -- inexact T, NaN, infinities -- takes the double expression.  Half of the passes use
-// each path so that neither the XU pipe nor the issue slots saturate.
+// Anything else -- inexact T, NaN, infinities -- takes the double expression.  All four passes take the float form; the
+// TwoSum test itself is the second level behind the one-comparison test of shapiro_pair_sterbenz below.
 // (every form takes S = RN(lo + hi), the float sum the reference forms first)
 __device__ __forceinline__ float shapiro_point_double(float S, float f, double sd)
 {
